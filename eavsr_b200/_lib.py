@@ -1,0 +1,82 @@
+"""ctypes binding of libeavsr_b200.so (the C ABI declared in include/eavsr_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a
+call fails, the error is raised -- loudly -- to the caller.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint, c_uint64, c_void_p, POINTER
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libeavsr_b200.so"
+_lib = None
+
+F32, BF16 = 0, 1
+FLOW_N2HW, FLOW_NHW2 = 0, 1
+PAD_ZEROS, PAD_BORDER = 0, 1
+DCN_FORCE_GENERIC = 1
+
+Strides = c_int64 * 4
+_P64 = POINTER(c_int64)
+_PF = c_void_p  # float* passed as raw device address
+
+
+class EavsrError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "eavsr_version": (c_int, []),
+    "eavsr_last_error": (c_char_p, []),
+    "eavsr_launch_count": (c_uint64, []),
+    "eavsr_flow_warp_forward": (c_int, [c_void_p, _P64, _PF, c_int, c_void_p, _P64, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p]),
+    "eavsr_flow_warp_backward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, c_int, _PF, _P64, _PF, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_void_p]),
+    "eavsr_dcn_forward_workspace": (c_size_t, [c_int] * 7),
+    "eavsr_dcn_forward_uses_tensor_cores": (c_int, [_P64, _P64] + [c_int] * 12 + [c_uint]),
+    "eavsr_dcn_forward": (c_int, [c_void_p, _P64, _PF, _PF, c_void_p, c_void_p, c_void_p, _P64] + [c_int] * 16 +
+                          [c_void_p, c_size_t, c_uint, c_void_p]),
+    "eavsr_dcn_backward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, _PF, c_void_p, _PF, _P64, _PF, _PF, _PF,
+                                   _PF] + [c_int] * 16 + [c_void_p]),
+    "eavsr_correlation_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p]),
+    "eavsr_correlation_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                           c_int, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("EAVSR_B200_LIB", _LIB_PATH))
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises EavsrError if the .so is not built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not path.exists():
+            raise EavsrError(
+                f"{path} not found: build it with `python -m eavsr_b200.build` "
+                "(eavsr_b200 has no CPU or PyTorch fallback)")
+        lib = ctypes.CDLL(str(path))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().eavsr_last_error().decode("utf-8", "replace")
+        raise EavsrError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().eavsr_launch_count())

@@ -1,0 +1,405 @@
+// flow_warp forward / backward for sm_100a.
+//
+// Replaces the reference's flow_warp (models/networks.py:699-739, models/eavsrp_model.py:587-626):
+// host-side meshgrid + normalise + F.grid_sample(bilinear, align_corners=True).  Because
+// align_corners=True maps the normalised grid back to exactly (x + flow_x, y + flow_y) the kernel
+// samples at that pixel coordinate directly; no grid tensor ever exists.
+//
+// HBM-bound gather.  Fast path: NHWC features, one thread per (pixel, 16-byte channel chunk),
+// 8x16-pixel CTA tiles so that the 4 bilinear corners of neighbouring outputs hit L1, all four
+// 16-byte corner loads of a thread in flight together.  Algorithmic bytes per pixel:
+// 2*C*sizeof(T) + 8 (read x once, read flow, write out) -- see DESIGN.md.
+#include "common.cuh"
+
+namespace eavsr {
+
+namespace {
+
+constexpr int TILE_H = 8;
+constexpr int TILE_W = 16;
+constexpr int TILE_PIX = TILE_H * TILE_W;
+constexpr int WARP_THREADS = 256;
+
+struct Corner {
+  int off[4];    // pixel index (y*W+x) of the 4 corners, clamped in-range
+  float wgt[4];  // bilinear weight, 0 for out-of-image corners
+  float gxm, gym;  // d(coord)/d(flow): 0 when the border clamp is active
+  float ly, lx;
+  bool ok[4];
+};
+
+template <int PAD>
+__device__ __forceinline__ Corner make_corner(float sy, float sx, int H, int W) {
+  Corner c;
+  c.gxm = 1.f;
+  c.gym = 1.f;
+  if (PAD == EAVSR_PAD_BORDER) {
+    // grid_sampler clip_coordinates_set_grad: gradient 0 when in<=0 or in>=size-1.
+    if (sx <= 0.f) { sx = 0.f; c.gxm = 0.f; } else if (sx >= (float)(W - 1)) { sx = (float)(W - 1); c.gxm = 0.f; }
+    if (sy <= 0.f) { sy = 0.f; c.gym = 0.f; } else if (sy >= (float)(H - 1)) { sy = (float)(H - 1); c.gym = 0.f; }
+  }
+  // keep the int conversion defined for wild flows
+  sx = fminf(fmaxf(sx, -2.f), (float)W + 1.f);
+  sy = fminf(fmaxf(sy, -2.f), (float)H + 1.f);
+  float fy = floorf(sy), fx = floorf(sx);
+  int y0 = (int)fy, x0 = (int)fx;
+  float ly = sy - fy, lx = sx - fx;
+  c.ly = ly;
+  c.lx = lx;
+  int y1 = y0 + 1, x1 = x0 + 1;
+  bool vy0 = (y0 >= 0) && (y0 < H), vy1 = (y1 >= 0) && (y1 < H);
+  bool vx0 = (x0 >= 0) && (x0 < W), vx1 = (x1 >= 0) && (x1 < W);
+  int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+  int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+  c.ok[0] = vy0 && vx0; c.ok[1] = vy0 && vx1; c.ok[2] = vy1 && vx0; c.ok[3] = vy1 && vx1;
+  c.off[0] = cy0 * W + cx0; c.off[1] = cy0 * W + cx1; c.off[2] = cy1 * W + cx0; c.off[3] = cy1 * W + cx1;
+  c.wgt[0] = c.ok[0] ? (1.f - ly) * (1.f - lx) : 0.f;
+  c.wgt[1] = c.ok[1] ? (1.f - ly) * lx : 0.f;
+  c.wgt[2] = c.ok[2] ? ly * (1.f - lx) : 0.f;
+  c.wgt[3] = c.ok[3] ? ly * lx : 0.f;
+  return c;
+}
+
+__device__ __forceinline__ void load_flow(const float* __restrict__ flow, int layout, int n, int y, int x, int H,
+                                          int W, float& fx, float& fy) {
+  if (layout == EAVSR_FLOW_N2HW) {
+    size_t b = ((size_t)n * 2) * H * W + (size_t)y * W + x;
+    fx = __ldg(flow + b);
+    fy = __ldg(flow + b + (size_t)H * W);
+  } else {
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)n * H + y) * W + x);
+    fx = f.x;
+    fy = f.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path: NHWC, C * sizeof(T) multiple of 16.
+// ------------------------------------------------------------------------------------------
+template <typename T, int PAD>
+__global__ void __launch_bounds__(WARP_THREADS)
+flow_warp_fwd_nhwc(const T* __restrict__ x, const float* __restrict__ flow, T* __restrict__ out, int C, int H,
+                   int W, int layout, int tiles_x, int tiles_y, long long xs_n, long long os_n) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int cpp = C / VEC;
+  int tile = blockIdx.x;
+  const int n = tile / (tiles_x * tiles_y);
+  tile -= n * tiles_x * tiles_y;
+  const int ty0 = (tile / tiles_x) * TILE_H, tx0 = (tile % tiles_x) * TILE_W;
+  const T* xn = x + (size_t)n * xs_n;
+  T* on = out + (size_t)n * os_n;
+  const int items = TILE_PIX * cpp;
+#pragma unroll 2
+  for (int idx = threadIdx.x; idx < items; idx += WARP_THREADS) {
+    const int p = idx / cpp, ch = idx - p * cpp;
+    const int y = ty0 + p / TILE_W, xq = tx0 + p % TILE_W;
+    if (y >= H || xq >= W) continue;
+    float fx, fy;
+    load_flow(flow, layout, n, y, xq, H, W, fx, fy);
+    Corner c = make_corner<PAD>((float)y + fy, (float)xq + fx, H, W);
+    float v[4][VEC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c.ok[k]) {
+        VecLoad<T, VEC>::ld(xn + (size_t)c.off[k] * C + ch * VEC, v[k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[k][j] = 0.f;
+      }
+    }
+    float r[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      r[j] = c.wgt[0] * v[0][j] + c.wgt[1] * v[1][j] + c.wgt[2] * v[2][j] + c.wgt[3] * v[3][j];
+    VecLoad<T, VEC>::st(on + ((size_t)y * W + xq) * C + ch * VEC, r);
+  }
+}
+
+// Backward of the fast path.  gx32 (fp32, NHWC, zero-filled by the host wrapper) receives the
+// scatter; gflow is reduced over the channel chunks of a pixel with warp shuffles when the
+// chunks of one pixel sit in one warp, otherwise with atomics.
+template <typename T, int PAD, bool SHFL>
+__global__ void __launch_bounds__(WARP_THREADS)
+flow_warp_bwd_nhwc(const T* __restrict__ gout, const T* __restrict__ x, const float* __restrict__ flow,
+                   float* __restrict__ gx32, float* __restrict__ gflow, int C, int H, int W, int layout,
+                   int tiles_x, int tiles_y, long long gs_n, long long xs_n, long long gxs_n) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int cpp = C / VEC;
+  int tile = blockIdx.x;
+  const int n = tile / (tiles_x * tiles_y);
+  tile -= n * tiles_x * tiles_y;
+  const int ty0 = (tile / tiles_x) * TILE_H, tx0 = (tile % tiles_x) * TILE_W;
+  const T* xn = x + (size_t)n * xs_n;
+  const T* gn = gout + (size_t)n * gs_n;
+  float* gxn = gx32 ? gx32 + (size_t)n * gxs_n : nullptr;
+  const int items = TILE_PIX * cpp;
+  // SHFL: items % 256 == 0 and cpp | 32, so every warp iteration is full and pixel-aligned.
+  for (int idx = threadIdx.x; idx < items; idx += WARP_THREADS) {
+    const int p = idx / cpp, ch = idx - p * cpp;
+    const int y = ty0 + p / TILE_W, xq = tx0 + p % TILE_W;
+    const bool live = (y < H) && (xq < W);
+    float dfx = 0.f, dfy = 0.f;
+    if (live) {
+      float fx, fy;
+      load_flow(flow, layout, n, y, xq, H, W, fx, fy);
+      Corner c = make_corner<PAD>((float)y + fy, (float)xq + fx, H, W);
+      float g[VEC];
+      VecLoad<T, VEC>::ld(gn + ((size_t)y * W + xq) * C + ch * VEC, g);
+      if (gxn) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (c.ok[k]) {
+            float* dst = gxn + (size_t)c.off[k] * C + ch * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; j += 4) {
+              atomicAdd(reinterpret_cast<float4*>(dst + j),
+                        make_float4(c.wgt[k] * g[j], c.wgt[k] * g[j + 1], c.wgt[k] * g[j + 2],
+                                    c.wgt[k] * g[j + 3]));
+            }
+          }
+        }
+      }
+      if (gflow) {
+        float v[4][VEC];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (c.ok[k]) {
+            VecLoad<T, VEC>::ld(xn + (size_t)c.off[k] * C + ch * VEC, v[k]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[k][j] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          dfx += g[j] * ((v[1][j] - v[0][j]) * (1.f - c.ly) + (v[3][j] - v[2][j]) * c.ly);
+          dfy += g[j] * ((v[2][j] - v[0][j]) * (1.f - c.lx) + (v[3][j] - v[1][j]) * c.lx);
+        }
+        dfx *= c.gxm;
+        dfy *= c.gym;
+      }
+    }
+    if (gflow) {
+      if (SHFL) {
+        for (int s = cpp >> 1; s > 0; s >>= 1) {
+          dfx += __shfl_xor_sync(0xffffffffu, dfx, s);
+          dfy += __shfl_xor_sync(0xffffffffu, dfy, s);
+        }
+        if (live && ch == 0) {
+          if (layout == EAVSR_FLOW_N2HW) {
+            size_t b = ((size_t)n * 2) * H * W + (size_t)y * W + xq;
+            gflow[b] = dfx;
+            gflow[b + (size_t)H * W] = dfy;
+          } else {
+            reinterpret_cast<float2*>(gflow)[((size_t)n * H + y) * W + xq] = make_float2(dfx, dfy);
+          }
+        }
+      } else if (live) {
+        if (layout == EAVSR_FLOW_N2HW) {
+          size_t b = ((size_t)n * 2) * H * W + (size_t)y * W + xq;
+          atomicAdd(gflow + b, dfx);
+          atomicAdd(gflow + b + (size_t)H * W, dfy);
+        } else {
+          size_t b = (((size_t)n * H + y) * W + xq) * 2;
+          atomicAdd(gflow + b, dfx);
+          atomicAdd(gflow + b + 1, dfy);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Strided path: any layout / any C (the 2-channel flow-composition warp and the 3-channel
+// SPyNet image warps are NCHW with C*sizeof(T) < 16).  One thread per pixel, channel loop.
+// ------------------------------------------------------------------------------------------
+template <typename T, int PAD>
+__global__ void __launch_bounds__(256)
+flow_warp_fwd_strided(const T* __restrict__ x, Strides4 xs, const float* __restrict__ flow, T* __restrict__ out,
+                      Strides4 os, int N, int C, int H, int W, int layout) {
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  int xq = (int)(pix % W);
+  int y = (int)((pix / W) % H);
+  int n = (int)(pix / ((long long)W * H));
+  float fx, fy;
+  load_flow(flow, layout, n, y, xq, H, W, fx, fy);
+  Corner c = make_corner<PAD>((float)y + fy, (float)xq + fx, H, W);
+  const T* xn = x + n * xs.n;
+  long long o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = (long long)(c.off[k] / W) * xs.h + (long long)(c.off[k] % W) * xs.w;
+  T* op = out + n * os.n + y * os.h + xq * os.w;
+  for (int ch = 0; ch < C; ++ch) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c.ok[k]) r += c.wgt[k] * to_f32<T>(xn[o[k] + ch * xs.c]);
+    op[ch * os.c] = from_f32<T>(r);
+  }
+}
+
+template <typename T, int PAD>
+__global__ void __launch_bounds__(256)
+flow_warp_bwd_strided(const T* __restrict__ gout, Strides4 gs, const T* __restrict__ x, Strides4 xs,
+                      const float* __restrict__ flow, float* __restrict__ gx32, Strides4 gxs,
+                      float* __restrict__ gflow, int N, int C, int H, int W, int layout) {
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  int xq = (int)(pix % W);
+  int y = (int)((pix / W) % H);
+  int n = (int)(pix / ((long long)W * H));
+  float fx, fy;
+  load_flow(flow, layout, n, y, xq, H, W, fx, fy);
+  Corner c = make_corner<PAD>((float)y + fy, (float)xq + fx, H, W);
+  const T* xn = x + n * xs.n;
+  const T* gp = gout + n * gs.n + y * gs.h + xq * gs.w;
+  float dfx = 0.f, dfy = 0.f;
+  for (int ch = 0; ch < C; ++ch) {
+    float g = to_f32<T>(gp[ch * gs.c]);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int cy = c.off[k] / W, cx = c.off[k] % W;
+      v[k] = c.ok[k] ? to_f32<T>(xn[(long long)cy * xs.h + (long long)cx * xs.w + ch * xs.c]) : 0.f;
+      if (gx32 && c.ok[k])
+        atomicAdd(gx32 + n * gxs.n + (long long)cy * gxs.h + (long long)cx * gxs.w + ch * gxs.c, c.wgt[k] * g);
+    }
+    dfx += g * ((v[1] - v[0]) * (1.f - c.ly) + (v[3] - v[2]) * c.ly);
+    dfy += g * ((v[2] - v[0]) * (1.f - c.lx) + (v[3] - v[1]) * c.lx);
+  }
+  if (gflow) {
+    dfx *= c.gxm;
+    dfy *= c.gym;
+    if (layout == EAVSR_FLOW_N2HW) {
+      size_t b = ((size_t)n * 2) * H * W + (size_t)y * W + xq;
+      gflow[b] = dfx;
+      gflow[b + (size_t)H * W] = dfy;
+    } else {
+      reinterpret_cast<float2*>(gflow)[((size_t)n * H + y) * W + xq] = make_float2(dfx, dfy);
+    }
+  }
+}
+
+bool is_nhwc_dense(const int64_t s[4], int c, int h, int w) {
+  return s[1] == 1 && s[3] == c && s[2] == (int64_t)w * c && s[0] >= (int64_t)h * w * c;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+int fwd_dispatch(const void* x, const int64_t* xs, const float* flow, int layout, void* out, const int64_t* os,
+                 int n, int c, int h, int w, int pad, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool fast = is_nhwc_dense(xs, c, h, w) && is_nhwc_dense(os, c, h, w) && (c % VEC == 0) && aligned16(x) &&
+                    aligned16(out) && ((xs[0] * sizeof(T)) % 16 == 0) && ((os[0] * sizeof(T)) % 16 == 0);
+  if (fast) {
+    int tx = ceil_div(w, TILE_W), ty = ceil_div(h, TILE_H);
+    long long blocks = (long long)n * tx * ty;
+    if (pad == EAVSR_PAD_ZEROS)
+      flow_warp_fwd_nhwc<T, EAVSR_PAD_ZEROS><<<(unsigned)blocks, WARP_THREADS, 0, st>>>(
+          (const T*)x, flow, (T*)out, c, h, w, layout, tx, ty, xs[0], os[0]);
+    else
+      flow_warp_fwd_nhwc<T, EAVSR_PAD_BORDER><<<(unsigned)blocks, WARP_THREADS, 0, st>>>(
+          (const T*)x, flow, (T*)out, c, h, w, layout, tx, ty, xs[0], os[0]);
+  } else {
+    Strides4 a{xs[0], xs[1], xs[2], xs[3]}, b{os[0], os[1], os[2], os[3]};
+    long long blocks = ((long long)n * h * w + 255) / 256;
+    if (pad == EAVSR_PAD_ZEROS)
+      flow_warp_fwd_strided<T, EAVSR_PAD_ZEROS><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, a, flow, (T*)out, b,
+                                                                                  n, c, h, w, layout);
+    else
+      flow_warp_fwd_strided<T, EAVSR_PAD_BORDER><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, a, flow, (T*)out,
+                                                                                   b, n, c, h, w, layout);
+  }
+  return check_launch("flow_warp_forward");
+}
+
+template <typename T>
+int bwd_dispatch(const void* gout, const int64_t* gs, const void* x, const int64_t* xs, const float* flow,
+                 int layout, float* gx32, const int64_t* gxs, float* gflow, int n, int c, int h, int w, int pad,
+                 cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int cpp = c / VEC;
+  const bool fast = is_nhwc_dense(xs, c, h, w) && is_nhwc_dense(gs, c, h, w) &&
+                    (!gx32 || is_nhwc_dense(gxs, c, h, w)) && (c % VEC == 0) && aligned16(x) && aligned16(gout) &&
+                    (!gx32 || aligned16(gx32)) && ((xs[0] * sizeof(T)) % 16 == 0) &&
+                    ((gs[0] * sizeof(T)) % 16 == 0) && (!gx32 || (gxs[0] * 4) % 16 == 0);
+  if (fast) {
+    const bool shfl = (cpp >= 2) && (cpp <= 32) && ((cpp & (cpp - 1)) == 0);
+    int tx = ceil_div(w, TILE_W), ty = ceil_div(h, TILE_H);
+    long long blocks = (long long)n * tx * ty;
+    if (gflow && !shfl && cpp > 1) {
+      cudaMemsetAsync(gflow, 0, (size_t)n * 2 * h * w * sizeof(float), st);
+    }
+#define EAVSR_LAUNCH_BWD(PADV, SH)                                                                       \
+  flow_warp_bwd_nhwc<T, PADV, SH><<<(unsigned)blocks, WARP_THREADS, 0, st>>>(                            \
+      (const T*)gout, (const T*)x, flow, gx32, gflow, c, h, w, layout, tx, ty, gs[0], xs[0], gx32 ? gxs[0] : 0)
+    // cpp == 1: one thread owns the pixel; the SHFL variant degenerates to a plain store.
+    const bool sh = shfl || cpp == 1;
+    if (pad == EAVSR_PAD_ZEROS) { if (sh) EAVSR_LAUNCH_BWD(EAVSR_PAD_ZEROS, true); else EAVSR_LAUNCH_BWD(EAVSR_PAD_ZEROS, false); }
+    else                        { if (sh) EAVSR_LAUNCH_BWD(EAVSR_PAD_BORDER, true); else EAVSR_LAUNCH_BWD(EAVSR_PAD_BORDER, false); }
+#undef EAVSR_LAUNCH_BWD
+  } else {
+    Strides4 a{gs[0], gs[1], gs[2], gs[3]}, b{xs[0], xs[1], xs[2], xs[3]}, g{0, 0, 0, 0};
+    if (gx32) g = Strides4{gxs[0], gxs[1], gxs[2], gxs[3]};
+    long long blocks = ((long long)n * h * w + 255) / 256;
+    if (pad == EAVSR_PAD_ZEROS)
+      flow_warp_bwd_strided<T, EAVSR_PAD_ZEROS><<<(unsigned)blocks, 256, 0, st>>>(
+          (const T*)gout, a, (const T*)x, b, flow, gx32, g, gflow, n, c, h, w, layout);
+    else
+      flow_warp_bwd_strided<T, EAVSR_PAD_BORDER><<<(unsigned)blocks, 256, 0, st>>>(
+          (const T*)gout, a, (const T*)x, b, flow, gx32, g, gflow, n, c, h, w, layout);
+  }
+  return check_launch("flow_warp_backward");
+}
+
+// extent (in elements) of a strided (n,c,h,w) tensor, for zero-filling accumulation buffers
+size_t strided_extent(const int64_t s[4], int n, int c, int h, int w) {
+  return (size_t)((n - 1) * s[0] + (c - 1) * s[1] + (h - 1) * s[2] + (w - 1) * s[3] + 1);
+}
+
+}  // namespace
+
+size_t strided_extent_elems(const int64_t s[4], int n, int c, int h, int w) { return strided_extent(s, n, c, h, w); }
+
+}  // namespace eavsr
+
+using namespace eavsr;
+
+extern "C" int eavsr_flow_warp_forward(const void* x, const int64_t x_strides[4], const float* flow,
+                                       int flow_layout, void* out, const int64_t out_strides[4], int n, int c,
+                                       int h, int w, int dtype, int padding_mode, void* stream) {
+  EAVSR_REQUIRE(x && flow && out && x_strides && out_strides, "flow_warp_forward: null pointer");
+  EAVSR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "flow_warp_forward: empty tensor (n=%d c=%d h=%d w=%d)", n, c, h, w);
+  EAVSR_REQUIRE(flow_layout == EAVSR_FLOW_N2HW || flow_layout == EAVSR_FLOW_NHW2, "flow_warp_forward: bad flow_layout %d", flow_layout);
+  EAVSR_REQUIRE(padding_mode == EAVSR_PAD_ZEROS || padding_mode == EAVSR_PAD_BORDER,
+                "flow_warp_forward: padding_mode %d not supported (zeros/border only)", padding_mode);
+  EAVSR_REQUIRE((long long)h * w < (1ll << 31), "flow_warp_forward: image too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == EAVSR_F32) return fwd_dispatch<float>(x, x_strides, flow, flow_layout, out, out_strides, n, c, h, w, padding_mode, st);
+  if (dtype == EAVSR_BF16) return fwd_dispatch<__nv_bfloat16>(x, x_strides, flow, flow_layout, out, out_strides, n, c, h, w, padding_mode, st);
+  set_error("flow_warp_forward: bad dtype %d", dtype);
+  return EAVSR_ERR_INVALID;
+}
+
+extern "C" int eavsr_flow_warp_backward(const void* gout, const int64_t gout_strides[4], const void* x,
+                                        const int64_t x_strides[4], const float* flow, int flow_layout, float* gx32,
+                                        const int64_t gx_strides[4], float* gflow, int n, int c, int h, int w,
+                                        int dtype, int padding_mode, void* stream) {
+  EAVSR_REQUIRE(gout && x && flow && gout_strides && x_strides, "flow_warp_backward: null pointer");
+  EAVSR_REQUIRE(!gx32 || gx_strides, "flow_warp_backward: gx32 without strides");
+  EAVSR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "flow_warp_backward: empty tensor");
+  EAVSR_REQUIRE(flow_layout == EAVSR_FLOW_N2HW || flow_layout == EAVSR_FLOW_NHW2, "flow_warp_backward: bad flow_layout %d", flow_layout);
+  EAVSR_REQUIRE(padding_mode == EAVSR_PAD_ZEROS || padding_mode == EAVSR_PAD_BORDER, "flow_warp_backward: bad padding_mode %d", padding_mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!gx32 && !gflow) return EAVSR_OK;
+  if (gx32) {
+    cudaError_t e = cudaMemsetAsync(gx32, 0, strided_extent(gx_strides, n, c, h, w) * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("flow_warp_backward: memset: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  }
+  if (dtype == EAVSR_F32) return bwd_dispatch<float>(gout, gout_strides, x, x_strides, flow, flow_layout, gx32, gx_strides, gflow, n, c, h, w, padding_mode, st);
+  if (dtype == EAVSR_BF16) return bwd_dispatch<__nv_bfloat16>(gout, gout_strides, x, x_strides, flow, flow_layout, gx32, gx_strides, gflow, n, c, h, w, padding_mode, st);
+  set_error("flow_warp_backward: bad dtype %d", dtype);
+  return EAVSR_ERR_INVALID;
+}

@@ -1,0 +1,370 @@
+"""Host-side mirror of the reference's alignment operators, bound to the CUDA library.
+
+Same names, argument meaning and error behaviour as the symbols the reference resolves:
+
+  * ``ModulatedDeformConv2d`` / ``modulated_deform_conv2d``  -- ``from mmcv.ops import ...`` at
+    models/networks.py:573, subclassed at :575-583, called at :627-630
+  * ``flow_warp`` (flow ``(n,2,h,w)``)      -- models/networks.py:699-739
+  * ``flow_warp_nhw2`` (flow ``(n,h,w,2)``) -- models/eavsrp_model.py:587-626,
+    models/eavsrpx2_model.py:588-627
+  * ``FunctionCorrelation`` / ``ModuleCorrelation`` -- pwc/correlation/correlation.py:385-397
+
+PyTorch is plumbing here (device memory, streams, autograd glue); every op runs in
+libeavsr_b200.so.  CPU tensors raise NotImplementedError -- there is no fallback.
+
+Precision policy: features/weights run in the dtype of ``x`` (fp32 or bf16, fp32 accumulate);
+flow / offset / mask are always consumed as fp32 so sampling coordinates are never rounded.
+Memory format: channels_last (NHWC) inputs take the vectorised / tensor-core paths with no
+copies; 64-channel NCHW inputs to the DCN are converted once to channels_last.  Outputs of the
+fast paths are channels_last.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from . import _lib as L
+
+__all__ = [
+    "modulated_deform_conv2d", "ModulatedDeformConv2d", "flow_warp", "flow_warp_nhw2",
+    "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
+]
+
+_DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _require_cuda(name: str, *tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NotImplementedError(
+                f"eavsr_b200.{name}: CUDA tensors only (the B200 library has no CPU fallback)")
+
+
+def _dtype_code(name: str, t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"eavsr_b200.{name}: dtype {t.dtype} not supported (float32 / bfloat16)") from None
+
+
+def _strides(t: torch.Tensor):
+    return L.Strides(*t.stride())
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _is_channels_last(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.stride(1) == 1 and t.size(1) > 1
+
+
+def _empty_like_layout(t: torch.Tensor, dtype=None, channels: Optional[int] = None,
+                       hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Dense tensor shaped like ``t`` (optionally other C/H/W), channels_last iff ``t`` is."""
+    n, c, h, w = t.shape
+    c = c if channels is None else channels
+    h, w = (h, w) if hw is None else hw
+    fmt = torch.channels_last if _is_channels_last(t) else torch.contiguous_format
+    return torch.empty((n, c, h, w), dtype=dtype or t.dtype, device=t.device, memory_format=fmt)
+
+
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    """Return ``t`` if it is dense NCHW or dense NHWC, else a dense copy in its nearest format."""
+    if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    fmt = torch.channels_last if _is_channels_last(t) else torch.contiguous_format
+    return t.contiguous(memory_format=fmt)
+
+
+# ------------------------------------------------------------------------------------------
+# flow_warp
+# ------------------------------------------------------------------------------------------
+class _FlowWarpFn(Function):
+    @staticmethod
+    def forward(ctx, x, flow, layout: int, pad: int):
+        lib = L.load()
+        with torch.cuda.device(x.device):
+            if (x.shape[1] * x.element_size()) % 16 == 0:
+                xd = x.contiguous(memory_format=torch.channels_last)  # vectorised NHWC path
+            else:
+                xd = _dense(x)                                        # 2/3-channel maps: strided path
+            flow32 = flow.detach().to(torch.float32).contiguous()
+            out = _empty_like_layout(xd)
+            n, c, h, w = xd.shape
+            L.check(lib.eavsr_flow_warp_forward(xd.data_ptr(), _strides(xd), flow32.data_ptr(), layout,
+                                                out.data_ptr(), _strides(out), n, c, h, w,
+                                                _dtype_code("flow_warp", xd), pad, _stream(xd)),
+                    "flow_warp_forward")
+        ctx.save_for_backward(xd, flow32)
+        ctx.layout, ctx.pad, ctx.flow_dtype = layout, pad, flow.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        xd, flow32 = ctx.saved_tensors
+        lib = L.load()
+        need_x, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx32 = gflow = None
+        with torch.cuda.device(xd.device):
+            fmt = torch.channels_last if _is_channels_last(xd) else torch.contiguous_format
+            g = gout.to(xd.dtype).contiguous(memory_format=fmt)
+            if need_x:
+                gx32 = _empty_like_layout(xd, dtype=torch.float32)
+            if need_f:
+                gflow = torch.empty_like(flow32)
+            n, c, h, w = xd.shape
+            L.check(lib.eavsr_flow_warp_backward(g.data_ptr(), _strides(g), xd.data_ptr(), _strides(xd),
+                                                 flow32.data_ptr(), ctx.layout, _ptr(gx32),
+                                                 _strides(gx32) if gx32 is not None else None, _ptr(gflow),
+                                                 n, c, h, w, _dtype_code("flow_warp", xd), ctx.pad, _stream(xd)),
+                    "flow_warp_backward")
+        gx = gx32.to(xd.dtype) if gx32 is not None else None
+        gf = gflow.to(ctx.flow_dtype) if gflow is not None else None
+        return gx, gf, None, None
+
+
+def _flow_warp(name, x, flow, layout, interpolation, padding_mode, align_corners):
+    hw = tuple(flow.shape[-2:]) if layout == L.FLOW_N2HW else tuple(flow.shape[1:3])
+    if tuple(x.shape[-2:]) != hw:
+        raise ValueError(f'The spatial sizes of input ({x.size()[-2:]}) and '
+                         f'flow ({torch.Size(hw)}) are not the same.')
+    if interpolation != 'bilinear' or not align_corners:
+        raise NotImplementedError(
+            f"eavsr_b200.{name}: only interpolation='bilinear', align_corners=True (what EAVSR uses)")
+    if padding_mode not in ('zeros', 'border'):
+        raise NotImplementedError(f"eavsr_b200.{name}: padding_mode {padding_mode!r} (zeros/border only)")
+    _require_cuda(name, x, flow)
+    if x.dim() != 4 or flow.dim() != 4 or flow.shape[0] != x.shape[0]:
+        raise ValueError(f"eavsr_b200.{name}: expected x (n,c,h,w) and a matching flow, got "
+                         f"{tuple(x.shape)} / {tuple(flow.shape)}")
+    two = flow.shape[1] if layout == L.FLOW_N2HW else flow.shape[3]
+    if two != 2:
+        raise ValueError(f"eavsr_b200.{name}: flow must have 2 channels, got {tuple(flow.shape)}")
+    return _FlowWarpFn.apply(x, flow, layout, L.PAD_ZEROS if padding_mode == 'zeros' else L.PAD_BORDER)
+
+
+def flow_warp(x, flow, interpolation='bilinear', padding_mode='zeros', align_corners=True):
+    """Drop-in for ``models.networks.flow_warp`` (models/networks.py:699-739): ``flow`` is
+    ``(n, 2, h, w)``, channel 0 = x displacement, in pixels."""
+    return _flow_warp("flow_warp", x, flow, L.FLOW_N2HW, interpolation, padding_mode, align_corners)
+
+
+def flow_warp_nhw2(x, flow, interpolation='bilinear', padding_mode='zeros', align_corners=True):
+    """Drop-in for ``models.eavsrp_model.flow_warp`` (models/eavsrp_model.py:587-626) and its
+    eavsrpx2 twin: ``flow`` is ``(n, h, w, 2)``."""
+    return _flow_warp("flow_warp", x, flow, L.FLOW_NHW2, interpolation, padding_mode, align_corners)
+
+
+# ------------------------------------------------------------------------------------------
+# DCNv2
+# ------------------------------------------------------------------------------------------
+def _dcn_prepare_x(x: torch.Tensor, weight: torch.Tensor, groups: int) -> torch.Tensor:
+    """64->64 3x3 features go to the tensor-core kernel, which wants NHWC."""
+    if x.shape[1] == 64 and weight.shape[0] == 64 and groups == 1 and tuple(weight.shape[2:]) == (3, 3):
+        return x.contiguous(memory_format=torch.channels_last)
+    return _dense(x)
+
+
+def dcn_uses_tensor_cores(x, weight, stride=1, padding=0, dilation=1, groups=1, deform_groups=1) -> bool:
+    """True when this call would run the tcgen05 implicit-GEMM kernel (tests/bench assert it)."""
+    lib = L.load()
+    sh, sw = _pair(stride)
+    ph, pw = _pair(padding)
+    dh, dw = _pair(dilation)
+    xd = _dcn_prepare_x(x, weight, groups)
+    cout, _, kh, kw = weight.shape
+    out = _empty_like_layout(xd, channels=cout)
+    return bool(lib.eavsr_dcn_forward_uses_tensor_cores(_strides(xd), _strides(out), xd.shape[1], cout, kh, kw,
+                                                        sh, sw, ph, pw, dh, dw, groups, deform_groups, 0))
+
+
+class _ModulatedDeformConv2dFn(Function):
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups,
+                flags=0):
+        if input is not None and input.dim() != 4:
+            raise ValueError(f'Expected 4D tensor as input, got {input.dim()}D tensor instead.')
+        _require_cuda("modulated_deform_conv2d", input, offset, mask, weight, bias)
+        lib = L.load()
+        sh, sw = _pair(stride)
+        ph, pw = _pair(padding)
+        dh, dw = _pair(dilation)
+        cout, cin_g, kh, kw = weight.shape
+        n, cin, h, w = input.shape
+        ho = (h + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+        wo = (w + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+        K = kh * kw
+        if cin_g * groups != cin:
+            raise ValueError(f"modulated_deform_conv2d: weight {tuple(weight.shape)} does not match "
+                             f"{cin} input channels with groups={groups}")
+        if tuple(offset.shape) != (n, deform_groups * 2 * K, ho, wo):
+            raise ValueError(f"modulated_deform_conv2d: offset shape {tuple(offset.shape)}, expected "
+                             f"{(n, deform_groups * 2 * K, ho, wo)}")
+        if tuple(mask.shape) != (n, deform_groups * K, ho, wo):
+            raise ValueError(f"modulated_deform_conv2d: mask shape {tuple(mask.shape)}, expected "
+                             f"{(n, deform_groups * K, ho, wo)}")
+        with torch.cuda.device(input.device):
+            code = _dtype_code("modulated_deform_conv2d", input)
+            xd = _dcn_prepare_x(input, weight, groups)
+            off32 = offset.detach().to(torch.float32).contiguous()
+            msk32 = mask.detach().to(torch.float32).contiguous()
+            wd = weight.detach().to(input.dtype).contiguous()
+            bd = bias.detach().to(input.dtype).contiguous() if bias is not None else None
+            out = _empty_like_layout(xd, channels=cout, hw=(ho, wo))
+            ws_bytes = lib.eavsr_dcn_forward_workspace(cin, cout, kh, kw, groups, deform_groups, code)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=input.device)
+            L.check(lib.eavsr_dcn_forward(xd.data_ptr(), _strides(xd), off32.data_ptr(), msk32.data_ptr(),
+                                          wd.data_ptr(), _ptr(bd), out.data_ptr(), _strides(out), n, cin, h, w,
+                                          cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, deform_groups, code,
+                                          ws.data_ptr(), ws.numel(), flags, _stream(xd)),
+                    "dcn_forward")
+        ctx.save_for_backward(xd, off32, msk32, wd)
+        ctx.geom = (sh, sw, ph, pw, dh, dw, groups, deform_groups)
+        ctx.has_bias = bias is not None
+        ctx.in_dtypes = (offset.dtype, mask.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        xd, off32, msk32, wd = ctx.saved_tensors
+        lib = L.load()
+        sh, sw, ph, pw, dh, dw, groups, dg = ctx.geom
+        need = ctx.needs_input_grad
+        n, cin, h, w = xd.shape
+        cout, _, kh, kw = wd.shape
+        with torch.cuda.device(xd.device):
+            fmt = torch.channels_last if _is_channels_last(xd) else torch.contiguous_format
+            g = gout.to(xd.dtype).contiguous(memory_format=fmt)
+            gx32 = _empty_like_layout(xd, dtype=torch.float32) if need[0] else None
+            goff = torch.empty_like(off32) if need[1] else None
+            gmsk = torch.empty_like(msk32) if need[2] else None
+            gw32 = torch.empty(wd.shape, dtype=torch.float32, device=xd.device) if need[3] else None
+            gb32 = torch.empty(cout, dtype=torch.float32, device=xd.device) if (need[4] and ctx.has_bias) else None
+            L.check(lib.eavsr_dcn_backward(g.data_ptr(), _strides(g), xd.data_ptr(), _strides(xd),
+                                           off32.data_ptr(), msk32.data_ptr(), wd.data_ptr(), _ptr(gx32),
+                                           _strides(gx32) if gx32 is not None else None, _ptr(goff), _ptr(gmsk),
+                                           _ptr(gw32), _ptr(gb32), n, cin, h, w, cout, kh, kw, sh, sw, ph, pw,
+                                           dh, dw, groups, dg, _dtype_code("modulated_deform_conv2d", xd),
+                                           _stream(xd)),
+                    "dcn_backward")
+        od, md, wdt, bdt = ctx.in_dtypes
+        return (gx32.to(xd.dtype) if gx32 is not None else None,
+                goff.to(od) if goff is not None else None,
+                gmsk.to(md) if gmsk is not None else None,
+                gw32.to(wdt) if gw32 is not None else None,
+                gb32.to(bdt) if gb32 is not None else None,
+                None, None, None, None, None, None)
+
+
+def modulated_deform_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
+                            groups=1, deform_groups=1):
+    """Drop-in for ``mmcv.ops.modulated_deform_conv2d`` with the positional order the reference
+    uses at models/networks.py:627-630."""
+    return _ModulatedDeformConv2dFn.apply(input, offset, mask, weight, bias, stride, padding, dilation,
+                                          groups, deform_groups)
+
+
+class ModulatedDeformConv2d(nn.Module):
+    """Drop-in for ``mmcv.ops.ModulatedDeformConv2d`` (parameter container + forward), subclassable
+    exactly as ``MultiAdSTN`` does (models/networks.py:575-583).  Parameter names, shapes and
+    initialisation follow mmcv-full 1.x: weight ~ U(+-1/sqrt(in*kh*kw)), bias = 0."""
+
+    _version = 2
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: Union[int, Tuple[int, int]],
+                 stride: int = 1, padding: int = 0, dilation: int = 1, groups: int = 1,
+                 deform_groups: int = 1, bias: Union[bool, str] = True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride)
+        self.padding = _pair(padding)
+        self.dilation = _pair(dilation)
+        self.groups = groups
+        self.deform_groups = deform_groups
+        self.transposed = False
+        self.output_padding = _pair(0)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.init_weights()
+
+    def init_weights(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def forward(self, x, offset, mask):
+        return modulated_deform_conv2d(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                       self.dilation, self.groups, self.deform_groups)
+
+
+# ------------------------------------------------------------------------------------------
+# correlation
+# ------------------------------------------------------------------------------------------
+class _FunctionCorrelation(Function):
+    @staticmethod
+    def forward(ctx, first, second):
+        assert first.is_contiguous() is True    # pwc/correlation/correlation.py:286-287
+        assert second.is_contiguous() is True
+        if not first.is_cuda:
+            raise NotImplementedError()          # pwc/correlation/correlation.py:324-325
+        if first.shape != second.shape or first.dim() != 4:
+            raise ValueError(f"correlation: shapes {tuple(first.shape)} / {tuple(second.shape)}")
+        lib = L.load()
+        n, c, h, w = first.shape
+        with torch.cuda.device(first.device):
+            code = _dtype_code("FunctionCorrelation", first)
+            second = second.to(first.dtype)
+            out = first.new_empty((n, 81, h, w))
+            L.check(lib.eavsr_correlation_forward(first.data_ptr(), second.data_ptr(), out.data_ptr(), n, c, h, w,
+                                                  code, _stream(first)), "correlation_forward")
+        ctx.save_for_backward(first, second)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        first, second = ctx.saved_tensors
+        lib = L.load()
+        n, c, h, w = first.shape
+        with torch.cuda.device(first.device):
+            g = gout.to(first.dtype).contiguous()
+            g1 = torch.empty_like(first) if ctx.needs_input_grad[0] else None
+            g2 = torch.empty_like(second) if ctx.needs_input_grad[1] else None
+            if g1 is not None or g2 is not None:
+                L.check(lib.eavsr_correlation_backward(first.data_ptr(), second.data_ptr(), g.data_ptr(), _ptr(g1),
+                                                       _ptr(g2), n, c, h, w, _dtype_code("FunctionCorrelation", first),
+                                                       _stream(first)), "correlation_backward")
+        return g1, g2
+
+
+def FunctionCorrelation(tenFirst, tenSecond):
+    """Drop-in for ``pwc.correlation.correlation.FunctionCorrelation`` (keyword names as used at
+    models/pwc_net.py:157-158,165-167)."""
+    return _FunctionCorrelation.apply(tenFirst, tenSecond)
+
+
+class ModuleCorrelation(nn.Module):
+    def forward(self, tenFirst, tenSecond):
+        return _FunctionCorrelation.apply(tenFirst, tenSecond)

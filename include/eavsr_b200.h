@@ -1,0 +1,122 @@
+/*
+ * eavsr_b200 -- C ABI of the B200-native (sm_100a) inter-frame alignment kernels for EAVSR.
+ *
+ * The reference (HITRainer/EAVSR) has no C ABI: its hot path is reached through Python
+ * symbols.  Each entry point below replaces the native code that sits under one of those
+ * symbols; the Python mirror of the reference interface lives in eavsr_b200/ops.py and
+ * binds these functions with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - feature tensors are described by 4 element strides in (n, c, h, w) order, so NCHW and
+ *     channels_last (NHWC) buffers are both accepted without copies;  the vectorised /
+ *     tensor-core fast paths need stride_c == 1 (NHWC), 16-byte aligned rows;
+ *   - flow / offset / mask are always fp32 (sampling coordinates are never rounded to bf16);
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream);  calls are asynchronous,
+ *     re-entrant, keep no global mutable state besides an atomic launch counter, and are
+ *     CUDA-graph capturable;
+ *   - return value: EAVSR_OK or an error code; eavsr_last_error() gives the message of
+ *     the calling thread's last failure;
+ *   - inputs are borrowed and never written; outputs/workspaces are caller-allocated.
+ */
+#ifndef EAVSR_B200_H_
+#define EAVSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAVSR_OK 0
+#define EAVSR_ERR_INVALID 1     /* bad argument (shape, alignment, enum)            */
+#define EAVSR_ERR_CUDA 2        /* CUDA runtime error (message has the cuda string) */
+#define EAVSR_ERR_UNSUPPORTED 3 /* valid request that this build does not implement */
+
+#define EAVSR_F32 0
+#define EAVSR_BF16 1
+
+#define EAVSR_FLOW_N2HW 0 /* models/networks.py:699  flow_warp(x, flow[n,2,h,w])      */
+#define EAVSR_FLOW_NHW2 1 /* models/eavsrp_model.py:587 flow_warp(x, flow[n,h,w,2])   */
+
+#define EAVSR_PAD_ZEROS 0
+#define EAVSR_PAD_BORDER 1
+
+#define EAVSR_DCN_FORCE_GENERIC 1u /* flags bit: skip the tcgen05 path (validation only) */
+
+/* ---- library ------------------------------------------------------------------------ */
+int eavsr_version(void);
+const char* eavsr_last_error(void);
+/* number of CUDA kernels launched by this library in this process (all threads). */
+uint64_t eavsr_launch_count(void);
+
+/* ---- flow_warp -------------------------------------------------------------------------
+ * Replaces F.grid_sample(bilinear, align_corners=True) under
+ *   models/networks.py:699-739 (flow_layout N2HW) and
+ *   models/eavsrp_model.py:587-626 / models/eavsrpx2_model.py:588-627 (flow_layout NHW2),
+ * including the meshgrid/normalise prologue those functions run on the host per call.
+ * out[n,c,y,x] = bilinear(x[n,c], y + flow_y, x + flow_x); flow channel 0 is x.
+ * padding: zeros (each out-of-image corner contributes 0) or border (clamp coordinate). */
+int eavsr_flow_warp_forward(const void* x, const int64_t x_strides[4], const float* flow, int flow_layout,
+                            void* out, const int64_t out_strides[4], int n, int c, int h, int w, int dtype,
+                            int padding_mode, void* stream);
+
+/* Gradients of the above.  gx32 is an fp32 accumulation buffer with strides gx_strides that
+ * the call zero-fills and scatter-adds into (for dtype F32 it is the final gradient);
+ * gflow (fp32, same layout as flow) may be NULL when the flow needs no gradient.
+ * gx32 may be NULL when x needs no gradient. */
+int eavsr_flow_warp_backward(const void* gout, const int64_t gout_strides[4], const void* x,
+                             const int64_t x_strides[4], const float* flow, int flow_layout, float* gx32,
+                             const int64_t gx_strides[4], float* gflow, int n, int c, int h, int w, int dtype,
+                             int padding_mode, void* stream);
+
+/* ---- modulated deformable convolution (DCNv2) --------------------------------------------
+ * Replaces mmcv.ops.modulated_deform_conv2d as called at models/networks.py:627-630
+ * (ext_module.modulated_deform_conv_forward / _backward of mmcv-full 1.x).
+ *   offset: (n, dg*2*kh*kw, ho, wo) fp32 contiguous, channel (g*K+k)*2 = dy, +1 = dx
+ *   mask:   (n, dg*kh*kw,   ho, wo) fp32 contiguous
+ *   weight: (cout, cin/groups, kh, kw) contiguous, dtype = `dtype`;  bias: (cout) or NULL
+ *   x / out: `dtype`, described by strides.
+ * Fast path (tcgen05 implicit GEMM): cin=cout=64, 3x3, stride 1, pad 1, dilation 1, groups 1,
+ * dg in {1,2,4,8,16}, NHWC x/out.  It needs `workspace` of eavsr_dcn_forward_workspace() bytes
+ * (packed weights).  Everything else runs the generic kernel (no workspace). */
+size_t eavsr_dcn_forward_workspace(int cin, int cout, int kh, int kw, int groups, int deform_groups,
+                                   int dtype);
+/* 1 if the arguments select the tcgen05 path, 0 for the generic kernel. */
+int eavsr_dcn_forward_uses_tensor_cores(const int64_t x_strides[4], const int64_t out_strides[4], int cin,
+                                        int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
+                                        int dw, int groups, int deform_groups, unsigned flags);
+int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], const float* offset, const float* mask,
+                      const void* weight, const void* bias, void* out, const int64_t out_strides[4], int n,
+                      int cin, int h, int w, int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
+                      int dw, int groups, int deform_groups, int dtype, void* workspace,
+                      size_t workspace_bytes, unsigned flags, void* stream);
+
+/* Gradients wrt x, offset, mask, weight, bias (any output pointer may be NULL = not needed).
+ * gx32: fp32 accumulation buffer (zero-filled by the call) with strides gx_strides;
+ * goffset/gmask: fp32, layouts of offset/mask;  gweight32: fp32 (cout,cin/groups,kh,kw),
+ * gbias32: fp32 (cout) -- both zero-filled by the call. */
+int eavsr_dcn_backward(const void* gout, const int64_t gout_strides[4], const void* x,
+                       const int64_t x_strides[4], const float* offset, const float* mask, const void* weight,
+                       float* gx32, const int64_t gx_strides[4], float* goffset, float* gmask,
+                       float* gweight32, float* gbias32, int n, int cin, int h, int w, int cout, int kh, int kw,
+                       int sh, int sw, int ph, int pw, int dh, int dw, int groups, int deform_groups,
+                       int dtype, void* stream);
+
+/* ---- PWC-Net cost volume -----------------------------------------------------------------
+ * Replaces kernel_Correlation_rearrange + kernel_Correlation_updateOutput
+ * (pwc/correlation/correlation.py:8-103, launched :293-322) and the two backward kernels
+ * (:105-233, launched :343-373).  first/second: (n,c,h,w) NCHW contiguous (the reference
+ * asserts contiguity, :286-287); out: (n,81,h,w) NCHW contiguous, same dtype.
+ * out[n,(dy+4)*9+(dx+4),y,x] = 1/c * sum_ch first[n,ch,y,x]*second[n,ch,y+dy,x+dx]. */
+int eavsr_correlation_forward(const void* first, const void* second, void* out, int n, int c, int h, int w,
+                              int dtype, void* stream);
+/* gfirst/gsecond: (n,c,h,w) same dtype, either may be NULL. */
+int eavsr_correlation_backward(const void* first, const void* second, const void* gout, void* gfirst,
+                               void* gsecond, int n, int c, int h, int w, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAVSR_B200_H_ */
