@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- LR frames/s of EAVSR+ x4 on synthetic 270x480 clips (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload model|hotpath] [--impl reference]
+
+One "step" = one pass over one synthetic 30-frame 270x480 LR clip per GPU:
+  * workload "model"   : full EAVSR+ x4 forward (eavsr_b200.model.EAVSRP: SPyNet + encoder + 4
+                         second-order propagation branches + upsampler) with the alignment hot path
+                         (DCNv2 / flow_warp) on this repo's CUDA kernels, bf16 channels_last.
+  * workload "hotpath" : only the alignment operators of that clip, in the model's call order and
+                         shapes (228 DCNv2, 1140 64-ch warps, 112 2-ch warps, 12 border warps).
+Clips are independent, so N GPUs run N clips per step with no collective (scaling = weak); the only
+torch.distributed traffic is the timing barrier and the max-over-ranks of the elapsed time.
+
+The JSON line carries `roofline` for the dominant hot-path kernel (tcgen05 DCNv2 forward), timed
+live with CUDA events, `cpu_baseline` (the oracle port timed on the host cores on a bounded
+sample) and `e2e` (host buffers in, host buffers out, copies inside the timed region).
+`--impl reference` times the CPU oracle port of the same workload (the reference's own
+`--gpu_ids -1` path cannot travel to the GPU box: /root/reference and mmcv are not there).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES = 30
+LR_H, LR_W = 270, 480
+PAD_H = 272   # the reference's 3-level pyramid needs H, W % 4 == 0: replicate-pad 270 -> 272
+METRIC = "LR frames/s, EAVSR+ x4, 270x480"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+class HotpathWorkload:
+    """The alignment operators of one 30-frame clip, in the model's order and shapes
+    (4 branches x (2T-3) MultiAdSTN calls = 5 warps + 1 DCN each; T-2 flow
+    compositions per branch; 6-level SPyNet border warps for both directions)."""
+    name = "eavsrp_x4_alignment_hotpath_30x272x480_bf16"
+
+    def __init__(self, device, dtype=torch.bfloat16, t=T_FRAMES, h=PAD_H, w=LR_W, dg=8):
+        import eavsr_b200 as E
+        self.E, self.t, self.h, self.w, self.dg, self.dtype = E, t, h, w, dg, dtype
+        g = torch.Generator(device="cpu").manual_seed(1234)
+
+        def feat(hh, ww, n=3):
+            return [torch.randn(1, 64, hh, ww, generator=g).to(device, dtype).contiguous(
+                memory_format=torch.channels_last) for _ in range(n)]
+
+        def flow(hh, ww, n=3, sigma=2.0):
+            return [(torch.randn(1, 2, hh, ww, generator=g) * sigma).to(device) for _ in range(n)]
+
+        self.f1, self.f2, self.f4 = feat(h, w, 6), feat(h // 2, w // 2), feat(h // 4, w // 4)
+        self.fl1, self.fl2, self.fl4 = flow(h, w), flow(h // 2, w // 2, sigma=1.0), flow(h // 4, w // 4, sigma=0.5)
+        # offsets / masks pool larger than L2 (3 x 112 MB) so consecutive DCN calls stream from HBM
+        self.off = [(torch.randn(1, dg * 18, h, w, generator=g) * 2).clamp(-12, 12).to(device) for _ in range(3)]
+        self.msk = [torch.sigmoid(torch.randn(1, dg * 9, h, w, generator=g)).to(device) for _ in range(3)]
+        self.weight = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24).to(device, dtype)
+        self.bias = torch.zeros(64, device=device, dtype=dtype)
+        self.flow2 = [torch.randn(1, 2, h, w, generator=g).to(device) for _ in range(2)]
+        self.flow2_nhw2 = [f.permute(0, 2, 3, 1).contiguous() for f in self.fl1]
+        self.img = [torch.rand(t - 1, 3, 288 >> i, 480 >> i, generator=g).to(device) for i in range(6)]
+        self.imgflow = [(torch.randn(t - 1, 288 >> i, 480 >> i, 2, generator=g)).to(device) for i in range(6)]
+        self.frames_per_step = t
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def step(self):
+        E, t = self.E, self.t
+        k = 0
+        out = None
+        for _branch in range(4):
+            for i in range(1, t):
+                for order in (1, 2):
+                    if order == 2 and i < 2:
+                        continue
+                    if order == 2:
+                        E.flow_warp_nhw2(self.flow2[k % 2], self.flow2_nhw2[k % 3])
+                    E.flow_warp(self.f4[k % 3], self.fl4[k % 3])
+                    E.flow_warp(self.f2[k % 3], self.fl2[k % 3])
+                    E.flow_warp(self.f1[k % 6], self.fl1[k % 3])
+                    E.flow_warp(self.f1[(k + 1) % 6], self.fl1[(k + 1) % 3])
+                    feat = E.flow_warp(self.f1[(k + 2) % 6], self.fl1[(k + 1) % 3])
+                    out = E.modulated_deform_conv2d(feat, self.off[k % 3], self.msk[k % 3], self.weight, self.bias,
+                                                    1, 1, 1, 1, self.dg)
+                    k += 1
+        for _direction in range(2):
+            for lvl in range(6):
+                E.flow_warp_nhw2(self.img[lvl], self.imgflow[lvl], padding_mode="border")
+        return out
+
+    def e2e_step(self):
+        return None
+
+
+def make_workload(name, device):
+    if name == "hotpath":
+        return HotpathWorkload(device)
+    if name == "model":
+        from eavsr_b200.bench_model import ModelWorkload
+        return ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline of the dominant kernel: tcgen05 DCNv2 forward, timed live with CUDA events
+# ------------------------------------------------------------------------------------------------
+def dcn_roofline(device, peaks, dg=8, iters=60):
+    import eavsr_b200 as E
+    h, w = LR_H, LR_W
+    g = torch.Generator().manual_seed(0)
+    nbuf = 4                                        # 4 x 145 MB of inputs: every launch streams from HBM (> L2)
+    xs = [torch.randn(1, 64, h, w, generator=g).to(device, torch.bfloat16).contiguous(
+        memory_format=torch.channels_last) for _ in range(nbuf)]
+    offs = [(torch.randn(1, dg * 18, h, w, generator=g) * 2).clamp(-12, 12).to(device) for _ in range(nbuf)]
+    msks = [torch.sigmoid(torch.randn(1, dg * 9, h, w, generator=g)).to(device) for _ in range(nbuf)]
+    wgt = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24).to(device, torch.bfloat16)
+    bias = torch.zeros(64, device=device, dtype=torch.bfloat16)
+    assert E.dcn_uses_tensor_cores(xs[0], wgt, 1, 1, 1, 1, dg)
+    for i in range(4):
+        E.modulated_deform_conv2d(xs[i % nbuf], offs[i % nbuf], msks[i % nbuf], wgt, bias, 1, 1, 1, 1, dg)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(iters):
+        E.modulated_deform_conv2d(xs[i % nbuf], offs[i % nbuf], msks[i % nbuf], wgt, bias, 1, 1, 1, 1, dg)
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / 1e3 / iters           # includes the 2 us weight-pack launch of each call
+    px = h * w
+    bytes_alg = px * (64 * 2 + dg * 18 * 4 + dg * 9 * 4 + 64 * 2)       # 1120 B/px at dg=8
+    flops = 2.0 * px * 64 * 64 * 9
+    ach = bytes_alg / sec / 1e9
+    return {"kernel": "dcn_fwd_tc_kernel<bf16,dg=%d> 1x64x270x480" % dg, "bound": "hbm", "achieved": round(ach, 1),
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+            "peak_source": peaks["source"], "us_per_launch": round(sec * 1e6, 2),
+            "algorithmic_bytes_per_launch": bytes_alg,
+            "tensor": {"achieved_tflops": round(flops / sec / 1e12, 1), "peak_tflops": peaks["bf16_tflops"],
+                       "frac": round(flops / sec / 1e12 / peaks["bf16_tflops"], 4)}}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port on the host cores) -- also the `--impl reference` arm
+# ------------------------------------------------------------------------------------------------
+def cpu_hotpath_frames_per_s(budget_s=20.0):
+    """Times the CPU path the reference would run for the same operators (torchvision's CPU DCNv2 --
+    the mmcv stand-in -- and ATen grid_sample through the oracle's reference-faithful wrappers) on
+    a bounded sample: whole MultiAdSTN-equivalents (5 warps + 1 DCN at 272x480) until the budget
+    is spent, scaled to the 228 calls of a 30-frame clip."""
+    from oracle import cpu_reference as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    return R.time_hotpath_sample(PAD_H, LR_W, T_FRAMES, budget_s)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.workload == "model":
+        from oracle import cpu_reference as R
+        torch.set_num_threads(os.cpu_count() or 1)
+        fps, sample = R.time_model_sample(budget_s=60.0 * max(1, args.steps))
+        name = "eavsrp_x4_full_clip_30x270x480"
+    else:
+        fps, sample = cpu_hotpath_frames_per_s(20.0 * max(1, args.steps))
+        name = HotpathWorkload.name
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("EAVSR_BENCH_WORKLOAD", "model"))
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from eavsr_b200 import _lib
+    _lib.load()     # fail loudly if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    peaks = load_peaks()
+    wl = make_workload(args.workload, device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            wl.step()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        for _ in range(args.steps):
+            wl.step()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop(t0, t1)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+
+        # end to end: pinned host clip in, host result out, through the public API
+        e2e = None
+        if hasattr(wl, "e2e_step") and wl.h2d_bytes:
+            for _ in range(2):
+                wl.e2e_step()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                wl.e2e_step()
+            e1.record()
+            barrier()
+            ems = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([ems], device=device)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ems = tt.item()
+            e2e = {"value": round(world * wl.frames_per_step * args.steps / (ems / 1e3), 3), "unit": "frames/s",
+                   "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes}
+
+        roof = dcn_roofline(device, peaks) if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            if args.workload == "model":
+                from oracle import cpu_reference as R
+                torch.set_num_threads(os.cpu_count() or 1)
+                fps, sample = R.time_model_sample(budget_s=25.0)
+            else:
+                fps, sample = cpu_hotpath_frames_per_s(15.0)
+            cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": sample}
+        except Exception as exc:  # the baseline is a reported number, never a reason to lose the bench line
+            cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {exc!r}"}
+
+    if rank == 0:
+        value = world * wl.frames_per_step * args.steps / (ms / 1e3)
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": wl.name, "clip": f"{T_FRAMES}x3x{LR_H}x{LR_W}",
+                           "clips_per_step": world, "parallelism": f"clip-parallel x{world} (no collective)",
+                           "l2": "working set per step >> 126 MB L2 (rotating HBM-resident buffers)"},
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

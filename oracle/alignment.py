@@ -48,8 +48,10 @@ def bilinear_gather(x: torch.Tensor, py: torch.Tensor, px: torch.Tensor,
     """
     n, c, h, w = x.shape
     if border:
-        py = py.clamp(0, h - 1)
-        px = px.clamp(0, w - 1)
+        # grid_sampler's clip_coordinates_set_grad: the coordinate gradient is zero when the
+        # clamp is active, boundary included (in <= 0 or in >= size-1).
+        py = torch.where((py > 0) & (py < h - 1), py, py.detach().clamp(0, h - 1))
+        px = torch.where((px > 0) & (px < w - 1), px, px.detach().clamp(0, w - 1))
     y0 = torch.floor(py)
     x0 = torch.floor(px)
     ly = py - y0

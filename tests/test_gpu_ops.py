@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path (through the ctypes/C-ABI binding) against the CPU oracle on
+the same seeded inputs.  Tolerances: fp32 path max-abs <= 1e-3 (BASELINE.json north_star; the
+kernels are far inside it), bf16 path relative to the output RMS."""
+import pytest
+import torch
+
+import eavsr_b200 as E
+from eavsr_b200 import _lib as L
+from eavsr_b200.ops import _ModulatedDeformConv2dFn
+from oracle import alignment as O
+
+from helpers import dcn_inputs, max_err, rel_err, smooth_flow_mask, warp_inputs
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3     # north_star: max abs error <= 1e-3 fp32
+BF16_REL = 3e-2     # bf16 storage rounding (2^-9) relative to output RMS, worst element
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+# ---------------------------------------------------------------------------------------------
+# flow_warp
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["n2hw", "nhw2"])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("shape,cl", [((2, 64, 33, 47), True), ((1, 64, 67, 120), True), ((2, 64, 16, 24), False),
+                                      ((3, 2, 31, 45), False), ((2, 3, 9, 15), False), ((1, 20, 17, 19), True),
+                                      ((1, 196, 5, 8), False), ((1, 32, 1, 1), True)])
+def test_flow_warp_fp32(cuda, layout, pad, shape, cl):
+    x, flow = warp_inputs(*shape, seed=1, layout=layout)
+    ref = O.flow_warp(x.double(), flow.double(), layout, pad)
+    xg = x.to(cuda)
+    xg = _cl(xg) if cl else xg
+    fn = E.flow_warp if layout == "n2hw" else E.flow_warp_nhw2
+    out = fn(xg, flow.to(cuda), padding_mode=pad)
+    assert out.shape == ref.shape
+    assert max_err(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_flow_warp_bf16(cuda, pad):
+    x, flow = warp_inputs(2, 64, 40, 56, seed=2)
+    xb = x.bfloat16()
+    ref = O.flow_warp(xb.double(), flow.double(), "n2hw", pad)
+    out = E.flow_warp(_cl(xb.to(cuda)), flow.to(cuda), padding_mode=pad)
+    assert out.dtype == torch.bfloat16
+    assert rel_err(out, ref) < BF16_REL
+
+
+def test_flow_warp_identity_and_integer_shift(cuda):
+    x = torch.randn(1, 64, 20, 30)
+    flow = torch.zeros(1, 2, 20, 30)
+    out = E.flow_warp(_cl(x.to(cuda)), flow.to(cuda))
+    assert torch.equal(out.cpu(), x)
+    flow[:, 0] = 3.0
+    flow[:, 1] = -2.0
+    out = E.flow_warp(_cl(x.to(cuda)), flow.to(cuda)).cpu()
+    exp = torch.zeros_like(x)
+    exp[:, :, 2:, :27] = x[:, :, :18, 3:]
+    assert torch.equal(out, exp)
+
+
+@pytest.mark.parametrize("layout", ["n2hw", "nhw2"])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("shape,cl", [((2, 64, 19, 23), True), ((2, 2, 21, 17), False), ((1, 24, 9, 11), True),
+                                      ((1, 12, 7, 9), True)])
+def test_flow_warp_backward(cuda, layout, pad, shape, cl):
+    x, flow = warp_inputs(*shape, seed=3, layout=layout, sigma=2.0)
+    g = torch.randn(shape, generator=torch.Generator().manual_seed(4))
+    xr = x.double().requires_grad_()
+    fr = flow.double().requires_grad_()
+    ref = O.flow_warp(xr, fr, layout, pad)
+    gx_ref, gf_ref = torch.autograd.grad(ref, [xr, fr], g.double())
+    xg = (_cl(x.to(cuda)) if cl else x.to(cuda)).requires_grad_()
+    fg = flow.to(cuda).requires_grad_()
+    fn = E.flow_warp if layout == "n2hw" else E.flow_warp_nhw2
+    out = fn(xg, fg, padding_mode=pad)
+    gx, gf = torch.autograd.grad(out, [xg, fg], g.to(cuda))
+    assert max_err(gx, gx_ref) < 1e-4
+    m = smooth_flow_mask(flow, layout)
+    assert max_err(gf.cpu().double() * m, gf_ref * m) < 2e-3 * max(1.0, gf_ref.abs().max().item())
+
+
+def test_flow_warp_errors(cuda):
+    x = torch.zeros(1, 4, 8, 8, device=cuda)
+    with pytest.raises(ValueError):
+        E.flow_warp(x, torch.zeros(1, 2, 8, 9, device=cuda))
+    with pytest.raises(NotImplementedError):
+        E.flow_warp(x, torch.zeros(1, 2, 8, 8, device=cuda), padding_mode="reflection")
+    with pytest.raises(NotImplementedError):
+        E.flow_warp(x.cpu(), torch.zeros(1, 2, 8, 8))
+
+
+# ---------------------------------------------------------------------------------------------
+# DCNv2 forward
+# ---------------------------------------------------------------------------------------------
+def _dcn_ref(x, off, mask, w, b, stride=1, padding=1, dilation=1, groups=1, dg=8):
+    return O.modulated_deform_conv2d(x.double(), off.double(), mask.double(), w.double(),
+                                     None if b is None else b.double(), stride, padding, dilation, groups, dg)
+
+
+@pytest.mark.parametrize("dg", [8, 16, 1, 4])
+@pytest.mark.parametrize("shape", [(1, 37, 53), (2, 16, 24), (1, 67, 120), (1, 11, 13)])
+def test_dcn_tc_fp32(cuda, dg, shape):
+    n, h, w = shape
+    x, off, mask, wgt, bias = dcn_inputs(n, 64, h, w, 64, dg, seed=5)
+    ref = _dcn_ref(x, off, mask, wgt, bias, dg=dg)
+    xg = _cl(x.to(cuda))
+    assert E.dcn_uses_tensor_cores(xg, wgt.to(cuda), 1, 1, 1, 1, dg)
+    out = E.modulated_deform_conv2d(xg, off.to(cuda), mask.to(cuda), wgt.to(cuda), bias.to(cuda), 1, 1, 1, 1, dg)
+    assert out.shape == ref.shape
+    assert max_err(out, ref) < FP32_TOL
+    assert max_err(out, ref) < 1e-4     # bf16x3 split keeps fp32-level accuracy
+
+
+@pytest.mark.parametrize("dg", [8, 16])
+def test_dcn_tc_bf16(cuda, dg):
+    x, off, mask, wgt, bias = dcn_inputs(2, 64, 45, 61, 64, dg, seed=6)
+    xb, wb, bb = x.bfloat16(), wgt.bfloat16(), bias.bfloat16()
+    ref = _dcn_ref(xb, off, mask, wb, bb, dg=dg)
+    out = E.modulated_deform_conv2d(_cl(xb.to(cuda)), off.to(cuda), mask.to(cuda), wb.to(cuda), bb.to(cuda),
+                                    1, 1, 1, 1, dg)
+    assert out.dtype == torch.bfloat16
+    assert rel_err(out, ref) < BF16_REL
+
+
+def test_dcn_tc_nchw_input_and_no_bias(cuda):
+    x, off, mask, wgt, _ = dcn_inputs(1, 64, 21, 35, 64, 8, seed=7)
+    ref = _dcn_ref(x, off, mask, wgt, None, dg=8)
+    out = E.modulated_deform_conv2d(x.to(cuda), off.to(cuda), mask.to(cuda), wgt.to(cuda), None, 1, 1, 1, 1, 8)
+    assert max_err(out, ref) < 1e-4
+
+
+def test_dcn_zero_offset_equals_conv2d(cuda):
+    x, _, _, wgt, bias = dcn_inputs(1, 64, 24, 40, 64, 8, seed=8)
+    off = torch.zeros(1, 144, 24, 40)
+    mask = torch.ones(1, 72, 24, 40)
+    ref = torch.nn.functional.conv2d(x.double(), wgt.double(), bias.double(), padding=1)
+    out = E.modulated_deform_conv2d(_cl(x.to(cuda)), off.to(cuda), mask.to(cuda), wgt.to(cuda), bias.to(cuda),
+                                    1, 1, 1, 1, 8)
+    assert max_err(out, ref) < 1e-4
+
+
+def test_dcn_tc_matches_generic(cuda):
+    x, off, mask, wgt, bias = dcn_inputs(1, 64, 40, 72, 64, 8, seed=9)
+    args = (_cl(x.to(cuda)), off.to(cuda), mask.to(cuda), wgt.to(cuda), bias.to(cuda), 1, 1, 1, 1, 8)
+    a = _ModulatedDeformConv2dFn.apply(*args, 0)
+    b = _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_GENERIC)
+    assert max_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(cin=16, cout=8, k=3, stride=1, padding=1, dilation=1, groups=1, dg=4),
+    dict(cin=16, cout=8, k=3, stride=2, padding=2, dilation=2, groups=2, dg=4),
+    dict(cin=6, cout=10, k=1, stride=1, padding=0, dilation=1, groups=1, dg=3),
+    dict(cin=64, cout=64, k=3, stride=1, padding=1, dilation=1, groups=1, dg=64),
+    dict(cin=128, cout=64, k=3, stride=1, padding=1, dilation=1, groups=1, dg=8),
+])
+@pytest.mark.parametrize("cl", [False, True])
+def test_dcn_generic_fp32(cuda, cfg, cl):
+    n, h, w = 2, 13, 17
+    k, s, p, d = cfg["k"], cfg["stride"], cfg["padding"], cfg["dilation"]
+    ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+    wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+    x, off, mask, wgt, bias = dcn_inputs(n, cfg["cin"], h, w, cfg["cout"], cfg["dg"], k=k, seed=10,
+                                         groups=cfg["groups"], ho=ho, wo=wo)
+    ref = _dcn_ref(x, off, mask, wgt, bias, s, p, d, cfg["groups"], cfg["dg"])
+    xg = _cl(x.to(cuda)) if cl else x.to(cuda)
+    out = E.modulated_deform_conv2d(xg, off.to(cuda), mask.to(cuda), wgt.to(cuda), bias.to(cuda), s, p, d,
+                                    cfg["groups"], cfg["dg"])
+    assert out.shape == ref.shape
+    assert max_err(out, ref) < 1e-4
+
+
+def test_dcn_module_and_errors(cuda):
+    m = E.ModulatedDeformConv2d(64, 64, 3, padding=1, deform_groups=8).to(cuda)
+    assert m.weight.shape == (64, 64, 3, 3) and m.bias.abs().sum().item() == 0
+    x, off, mask, _, _ = dcn_inputs(1, 64, 12, 12, 64, 8, seed=11)
+    out = m(x.to(cuda), off.to(cuda), mask.to(cuda))
+    ref = _dcn_ref(x, off, mask, m.weight.detach().cpu(), m.bias.detach().cpu(), dg=8)
+    assert max_err(out, ref) < 1e-4
+    with pytest.raises(ValueError):
+        E.modulated_deform_conv2d(x[0].to(cuda), off.to(cuda), mask.to(cuda), m.weight, m.bias, 1, 1, 1, 1, 8)
+    with pytest.raises(ValueError):
+        E.modulated_deform_conv2d(x.to(cuda), off[:, :18].to(cuda), mask.to(cuda), m.weight, m.bias, 1, 1, 1, 1, 8)
+    with pytest.raises(NotImplementedError):
+        E.modulated_deform_conv2d(x, off, mask, m.weight.cpu(), None, 1, 1, 1, 1, 8)
+
+
+# ---------------------------------------------------------------------------------------------
+# DCNv2 backward
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(cin=64, cout=64, k=3, stride=1, padding=1, dilation=1, groups=1, dg=8, cl=True),
+    dict(cin=64, cout=64, k=3, stride=1, padding=1, dilation=1, groups=1, dg=16, cl=True),
+    dict(cin=16, cout=8, k=3, stride=2, padding=2, dilation=2, groups=2, dg=4, cl=False),
+])
+def test_dcn_backward_fp32(cuda, cfg):
+    n, h, w = 2, 12, 15
+    k, s, p, d = cfg["k"], cfg["stride"], cfg["padding"], cfg["dilation"]
+    ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+    wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+    x, off, mask, wgt, bias = dcn_inputs(n, cfg["cin"], h, w, cfg["cout"], cfg["dg"], k=k, seed=12,
+                                         groups=cfg["groups"], ho=ho, wo=wo, sigma=1.5)
+    g = torch.randn(n, cfg["cout"], ho, wo, generator=torch.Generator().manual_seed(13))
+    leaves = [t.double().requires_grad_() for t in (x, off, mask, wgt, bias)]
+    ref = O.modulated_deform_conv2d(*leaves, s, p, d, cfg["groups"], cfg["dg"])
+    grefs = torch.autograd.grad(ref, leaves, g.double())
+    xg = _cl(x.to(cuda)) if cfg["cl"] else x.to(cuda)
+    gl = [t.requires_grad_() for t in (xg, off.to(cuda), mask.to(cuda), wgt.to(cuda), bias.to(cuda))]
+    out = E.modulated_deform_conv2d(*gl, s, p, d, cfg["groups"], cfg["dg"])
+    grads = torch.autograd.grad(out, gl, g.to(cuda))
+    for name, a, r in zip(("x", "offset", "mask", "weight", "bias"), grads, grefs):
+        assert a.shape == r.shape, name
+        assert max_err(a, r) < 1e-3 * max(1.0, r.abs().max().item()), name
+
+
+# ---------------------------------------------------------------------------------------------
+# correlation
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 32, 20, 32), (1, 196, 5, 8), (8, 64, 4, 4), (8, 196, 1, 1), (2, 96, 10, 16),
+                                   (1, 7, 9, 13), (1, 16, 33, 70)])
+def test_correlation_forward_backward(cuda, shape):
+    g = torch.Generator().manual_seed(14)
+    f1 = torch.randn(shape, generator=g)
+    f2 = torch.randn(shape, generator=g)
+    ref = O.correlation(f1.double(), f2.double())
+    a = f1.to(cuda).requires_grad_()
+    b = f2.to(cuda).requires_grad_()
+    out = E.FunctionCorrelation(tenFirst=a, tenSecond=b)
+    assert out.shape == ref.shape
+    assert max_err(out, ref) < 1e-5 * max(1.0, shape[1] ** 0.5)
+    go = torch.randn(ref.shape, generator=g)
+    g1r, g2r = O.correlation_backward(f1.double(), f2.double(), go.double())
+    g1, g2 = torch.autograd.grad(out, [a, b], go.to(cuda))
+    assert max_err(g1, g1r) < 1e-4
+    assert max_err(g2, g2r) < 1e-4
+
+
+def test_correlation_module_and_errors(cuda):
+    m = E.ModuleCorrelation()
+    f = torch.randn(1, 8, 6, 6)
+    with pytest.raises(NotImplementedError):
+        m(f, f)
+    with pytest.raises(AssertionError):
+        m(f.to(cuda).permute(0, 1, 3, 2), f.to(cuda))
+    out = m(f.to(cuda), f.to(cuda))
+    assert out.shape == (1, 81, 6, 6)
+
+
+def test_launch_counter_counts_native_kernels(cuda):
+    before = L.launch_count()
+    x, flow = warp_inputs(1, 64, 8, 8)
+    E.flow_warp(_cl(x.to(cuda)), flow.to(cuda))
+    assert L.launch_count() == before + 1

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks on one B200 (SURVEY.md 8d shapes): achieved GB/s / TFLOP/s vs the
+measured peaks.  Inputs rotate over > L2-sized pools; timing with CUDA events after warm-up.
+Writes gpurun_out/microbench.json."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import eavsr_b200 as E  # noqa: E402
+from bench import load_peaks  # noqa: E402
+
+dev = torch.device("cuda:0")
+peaks = load_peaks()
+res = []
+
+
+def timeit(fn, iters, warm=3):
+    for i in range(warm):
+        fn(i)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / 1e3 / iters
+
+
+def pool(make, total_bytes, each_bytes, lo=2, hi=12):
+    n = max(lo, min(hi, int(total_bytes // max(1, each_bytes)) + 1))
+    return [make() for _ in range(n)]
+
+
+def rec(name, sec, bytes_alg, flops=0.0, **kw):
+    r = {"name": name, "us": round(sec * 1e6, 2), "GBps": round(bytes_alg / sec / 1e9, 1),
+         "hbm_frac": round(bytes_alg / sec / 1e9 / peaks["hbm_gbs"], 4)}
+    if flops:
+        r["TFLOPs"] = round(flops / sec / 1e12, 2)
+        r["tc_frac"] = round(flops / sec / 1e12 / peaks["bf16_tflops"], 4)
+    r.update(kw)
+    res.append(r)
+    print(json.dumps(r), flush=True)
+
+
+def bench_warp():
+    for dt, es in ((torch.bfloat16, 2), (torch.float32, 4)):
+        for n, h, w in ((1, 270, 480), (8, 270, 480), (1, 135, 240), (1, 67, 120)):
+            each = n * 64 * h * w * es
+            xs = pool(lambda: torch.randn(n, 64, h, w, device=dev).to(dt).contiguous(memory_format=torch.channels_last),
+                      400e6, each)
+            fl = pool(lambda: torch.randn(n, 2, h, w, device=dev) * 3, 0, 1, lo=len(xs), hi=len(xs))
+            sec = timeit(lambda i: E.flow_warp(xs[i % len(xs)], fl[i % len(xs)]), 100)
+            rec(f"flow_warp fwd {dt} {n}x64x{h}x{w}", sec, n * h * w * (2 * 64 * es + 8))
+            xg = [x.clone().requires_grad_() for x in xs[:4]]
+            fg = [f.clone().requires_grad_() for f in fl[:4]]
+            outs = [E.flow_warp(a, b) for a, b in zip(xg, fg)]
+            gs = [torch.randn_like(o) for o in outs]
+            sec = timeit(lambda i: torch.autograd.grad(outs[i % 4], [xg[i % 4], fg[i % 4]], gs[i % 4], retain_graph=True), 30)
+            rec(f"flow_warp bwd(x,flow) {dt} {n}x64x{h}x{w}", sec, n * h * w * (3 * 64 * es + 16))
+    x2 = torch.randn(1, 2, 270, 480, device=dev)
+    f2 = torch.randn(1, 270, 480, 2, device=dev)
+    sec = timeit(lambda i: E.flow_warp_nhw2(x2, f2), 100)
+    rec("flow_warp fwd f32 1x2x270x480 (flow composition, NCHW)", sec, 270 * 480 * (2 * 2 * 4 + 8))
+    x3 = torch.rand(29, 3, 288, 480, device=dev)
+    f3 = torch.randn(29, 288, 480, 2, device=dev)
+    sec = timeit(lambda i: E.flow_warp_nhw2(x3, f3, padding_mode="border"), 50)
+    rec("flow_warp fwd f32 29x3x288x480 border (SPyNet, NCHW)", sec, 29 * 288 * 480 * (2 * 3 * 4 + 8))
+
+
+def bench_dcn():
+    from eavsr_b200.ops import _ModulatedDeformConv2dFn
+    from eavsr_b200 import _lib as L
+    h, w = 270, 480
+    for dt, es in ((torch.bfloat16, 2), (torch.float32, 4)):
+        for dg in (8, 16):
+            for n in (1, 4):
+                each = n * h * w * (dg * 27 * 4)
+                k = max(2, min(6, int(500e6 // each) + 1))
+                xs = [torch.randn(n, 64, h, w, device=dev).to(dt).contiguous(memory_format=torch.channels_last) for _ in range(k)]
+                offs = [(torch.randn(n, dg * 18, h, w, device=dev) * 2).clamp(-12, 12) for _ in range(k)]
+                msks = [torch.sigmoid(torch.randn(n, dg * 9, h, w, device=dev)) for _ in range(k)]
+                wgt = ((torch.rand(64, 64, 3, 3, device=dev) * 2 - 1) / 24).to(dt)
+                bias = torch.zeros(64, device=dev, dtype=dt)
+                px = n * h * w
+                by = px * (128 * es + dg * 27 * 4)
+                fl = 2.0 * px * 64 * 64 * 9
+                sec = timeit(lambda i: E.modulated_deform_conv2d(xs[i % k], offs[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg), 40)
+                rec(f"dcn fwd tc {dt} dg={dg} {n}x64x{h}x{w} sigma=2", sec, by, fl)
+                if n == 1:
+                    small = [o * 0.25 for o in offs]
+                    sec = timeit(lambda i: E.modulated_deform_conv2d(xs[i % k], small[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg), 40)
+                    rec(f"dcn fwd tc {dt} dg={dg} {n}x64x{h}x{w} sigma=0.5", sec, by, fl)
+                    del small
+                if n == 1 and dg == 8:
+                    sec = timeit(lambda i: _ModulatedDeformConv2dFn.apply(xs[i % k], offs[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg, L.DCN_FORCE_GENERIC), 3, warm=1)
+                    rec(f"dcn fwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by, fl)
+                    xg = xs[0].clone().requires_grad_()
+                    og, mg, wg, bg = offs[0].clone().requires_grad_(), msks[0].clone().requires_grad_(), wgt.clone().requires_grad_(), bias.clone().requires_grad_()
+                    out = E.modulated_deform_conv2d(xg, og, mg, wg, bg, 1, 1, 1, 1, dg)
+                    go = torch.randn_like(out)
+                    sec = timeit(lambda i: torch.autograd.grad(out, [xg, og, mg, wg, bg], go, retain_graph=True), 3, warm=1)
+                    rec(f"dcn bwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by * 2, fl * 2)
+                del xs, offs, msks
+                torch.cuda.empty_cache()
+
+
+def bench_corr():
+    for n, c, h, w in ((30, 32, 80, 128), (30, 64, 40, 64), (30, 96, 20, 32), (30, 128, 10, 16), (30, 196, 5, 8),
+                       (8, 32, 16, 16), (8, 196, 1, 1)):
+        each = 2 * n * c * h * w * 4
+        k = max(2, min(8, int(300e6 // each) + 1))
+        a = [torch.randn(n, c, h, w, device=dev) for _ in range(k)]
+        b = [torch.randn(n, c, h, w, device=dev) for _ in range(k)]
+        sec = timeit(lambda i: E.FunctionCorrelation(tenFirst=a[i % k], tenSecond=b[i % k]), 50)
+        rec(f"correlation fwd f32 {n}x{c}x{h}x{w}", sec, n * h * w * (2 * c + 81) * 4, 2.0 * 81 * c * n * h * w)
+        ag, bg = a[0].clone().requires_grad_(), b[0].clone().requires_grad_()
+        out = E.FunctionCorrelation(tenFirst=ag, tenSecond=bg)
+        go = torch.randn_like(out)
+        sec = timeit(lambda i: torch.autograd.grad(out, [ag, bg], go, retain_graph=True), 10)
+        rec(f"correlation bwd f32 {n}x{c}x{h}x{w}", sec, n * h * w * (4 * c + 81) * 4, 4.0 * 81 * c * n * h * w)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["warp", "dcn", "corr"]
+    for wname in which:
+        globals()["bench_" + wname]()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"peaks": peaks, "results": res}, open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w"), indent=1)
