@@ -156,11 +156,70 @@ class HotpathWorkload:
         return None
 
 
+class ModelWorkload:
+    """Full EAVSR+ x4 forward of one synthetic 30-frame 270x480 clip per step (BASELINE.json config 3).
+    Seeded weights (all checkpoints are stripped from the reference), bf16 channels_last features,
+    fp32 flows/offsets/masks; the clip is replicate-padded 270 -> 272 and the SR cropped back to
+    1080x1920.  The forward is captured once into a CUDA graph (the reference issues
+    ~20k launches per clip from one Python thread) and replayed per step."""
+    name = "eavsrp_x4_full_clip_30x270x480_bf16"
+
+    def __init__(self, device, t=T_FRAMES, h=LR_H, w=LR_W, dtype=torch.bfloat16, graph=True):
+        from eavsr_b200.model import EAVSRP, pad_clip
+        from eavsr_b200.synthetic import clip_inputs, seeded_parameters
+        self.device, self.t, self.h, self.w = device, t, h, w
+        net = EAVSRP(4).eval()
+        seeded_parameters(net)
+        self.net = net.to(device).prepare(dtype)
+        clip = clip_inputs(1, t, h, w, seed=1234)
+        self.host_clip = clip.pin_memory()
+        self.pad = lambda x: pad_clip(x, 4)
+        self.static_in = self.pad(clip.to(device))
+        self.frames_per_step = t
+        self.h2d_bytes = clip.numel() * 4
+        self.host_out = torch.empty((1, t, 3, 4 * h, 4 * w), dtype=torch.uint8).pin_memory()
+        self.d2h_bytes = self.host_out.numel()
+        self.graph = None
+        self.use_graph = graph and os.environ.get("EAVSR_BENCH_GRAPH", "1") == "1"
+        self.out = None
+
+    def _forward(self):
+        sr = self.net(self.static_in)
+        return sr[..., : 4 * self.h, : 4 * self.w]
+
+    def step(self):
+        if not self.use_graph:
+            self.out = self._forward()
+            return self.out
+        if self.graph is None:
+            torch.cuda.synchronize()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._forward()                      # warm-up outside capture (cuDNN autotune, lazy init)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._forward()
+        self.graph.replay()
+        return self.out
+
+    def e2e_step(self):
+        """Host clip in (pinned) -> H2D -> forward -> clamp*255 round (the reference's visuals,
+        models/base_model.py:146-150) -> D2H uint8 frames."""
+        self.static_in.copy_(self.pad(self.host_clip.to(self.device, non_blocking=True)))
+        sr = self.step()
+        vis = torch.clamp(sr.float() * 255, 0, 255).round().to(torch.uint8)
+        self.host_out.copy_(vis, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host_out
+
+
 def make_workload(name, device):
     if name == "hotpath":
         return HotpathWorkload(device)
     if name == "model":
-        from eavsr_b200.bench_model import ModelWorkload
         return ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W)
     raise SystemExit(f"unknown workload {name}")
 
@@ -220,9 +279,9 @@ def run_reference_arm(args):
     if rank != 0:
         return
     if args.workload == "model":
-        from oracle import cpu_reference as R
+        from oracle import eavsrp_cpu as R
         torch.set_num_threads(os.cpu_count() or 1)
-        fps, sample = R.time_model_sample(budget_s=60.0 * max(1, args.steps))
+        fps, sample = R.time_model_sample(budget_s=60.0)
         name = "eavsrp_x4_full_clip_30x270x480"
     else:
         fps, sample = cpu_hotpath_frames_per_s(20.0 * max(1, args.steps))
@@ -324,7 +383,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         try:
             if args.workload == "model":
-                from oracle import cpu_reference as R
+                from oracle import eavsrp_cpu as R
                 torch.set_num_threads(os.cpu_count() or 1)
                 fps, sample = R.time_model_sample(budget_s=25.0)
             else:

@@ -1,0 +1,367 @@
+"""EAVSR+ (x4 / x2) forward on the B200 alignment kernels -- the callers of the hot path.
+
+This is the host-side orchestration that sits directly above the hot path in the reference
+(SURVEY.md section 8 row a8): ``EAVSRP.forward / compute_flow / propagate / upsample``
+(models/eavsrp_model.py:179-364, x2 twin models/eavsrpx2_model.py), ``MultiAdSTN.forward``
+(models/networks.py:597-631), ``AdaptBlockOffset`` / ``AdaptBlock2_3x3`` (:280-348) and the live
+``SPyNet`` (models/eavsrp_model.py:402-585).  The module tree reproduces the reference's parameter
+names and shapes, so a reference ``EAVSRP_model_*.pth`` state dict loads with ``strict=True``.
+
+What is B200-specific here:
+  * every bilinear warp and the DCNv2 run in libeavsr_b200.so (no grid tensors, no im2col buffer);
+  * activations are channels_last and (by default) bf16, flows / offsets / masks stay fp32;
+  * SPyNet runs once on both directions stacked in one batch;
+  * the per-group affine offset expansion is a broadcast expression, not a (n*P*D) x 2x2 bmm with
+    four permute copies.
+Dense 3x3/5x5/7x7 convolutions stay on cuDNN (out of scope).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .ops import ModulatedDeformConv2d, flow_warp, flow_warp_nhw2, modulated_deform_conv2d
+
+__all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
+
+
+# --------------------------------------------------------------------------------------------
+# small blocks (names chosen so that state-dict keys equal the reference's)
+# --------------------------------------------------------------------------------------------
+class _CALayer(nn.Module):
+    def __init__(self, ch=64, reduction=16):
+        super().__init__()
+        self.conv_du = nn.Sequential(nn.Conv2d(ch, ch // reduction, 1), nn.ReLU(inplace=True),
+                                     nn.Conv2d(ch // reduction, ch, 1), nn.Sigmoid())
+
+    def forward(self, x):
+        return x * self.conv_du(x.mean((2, 3), keepdim=True))
+
+
+class _RCABlock(nn.Module):
+    def __init__(self, ch=64):
+        super().__init__()
+        self.res = nn.Sequential(nn.Conv2d(ch, ch, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv2d(ch, ch, 3, 1, 1))
+        self.ca = _CALayer(ch)
+
+    def forward(self, x):
+        return self.ca(self.res(x)) + x
+
+
+class _RCAGroup(nn.Module):
+    def __init__(self, ch=64, nb=30):
+        super().__init__()
+        self.rg = nn.Sequential(*[_RCABlock(ch) for _ in range(nb)], nn.Conv2d(ch, ch, 3, 1, 1))
+
+    def forward(self, x):
+        return self.rg(x) + x
+
+
+class _ResidualStack(nn.Module):
+    """conv3x3 + LeakyReLU(0.1) + RCAGroup (reference: ResidualBlocksWithInputConv)."""
+
+    def __init__(self, cin, ch=64, nb=30):
+        super().__init__()
+        self.main = nn.Sequential(nn.Conv2d(cin, ch, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True), _RCAGroup(ch, nb))
+
+    def forward(self, x):
+        return self.main(x)
+
+
+class _Encoder(nn.Module):
+    """VGG16 conv1_1..conv3_1 with the pools removed + 3x3 tail (reference: ContrasExtractorLayer)."""
+
+    def __init__(self, ch=64):
+        super().__init__()
+        spec = (("conv1_1", 3, 64), ("conv1_2", 64, 64), ("conv2_1", 64, 128), ("conv2_2", 128, 128),
+                ("conv3_1", 128, 256))
+        layers = OrderedDict()
+        for i, (name, ci, co) in enumerate(spec):
+            layers[name] = nn.Conv2d(ci, co, 3, 1, 1)
+            if i + 1 < len(spec):
+                layers[name.replace("conv", "relu")] = nn.ReLU(inplace=True)
+        self.model = nn.Sequential(layers)
+        self.tail = nn.Conv2d(256, ch, 3, 1, 1)
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+    def forward(self, x):
+        return self.tail(self.model((x - self.mean) / self.std))
+
+
+_R = ((-1., -1., -1., 0., 0., 0., 1., 1., 1.), (-1., 0., 1., -1., 0., 1., -1., 0., 1.))
+
+
+def _affine_offsets(T, t, D):
+    """offset[n, (g*9+k)*2+i] = sum_j T[n,g,i,j] * R[j,k] - R[i,k] + t[n,g,i]
+    (reference: matmul + 4 permute/reshape copies at models/networks.py:302-310)."""
+    n, _, h, w = T.shape
+    R = T.new_tensor(_R)                                   # (2, 9)
+    T = T.reshape(n, D, 1, 2, 2, h, w)                     # g, -, i, j
+    Rk = R.t().reshape(1, 1, 9, 1, 2, 1, 1)                # -, -, k, -, j
+    off = (T * Rk).sum(4) - R.t().reshape(1, 1, 9, 2, 1, 1) + t.reshape(n, D, 1, 2, h, w)
+    return off.reshape(n, D * 18, h, w)
+
+
+class _AdaptBase(nn.Module):
+    def __init__(self, ch, n_mat, n_trans, k):
+        super().__init__()
+        self.register_buffer("regular_matrix", torch.tensor(_R))
+        self.concat = nn.Sequential(nn.Conv2d(2 * ch, 2 * ch, 3, 1, 1, groups=2 * ch), nn.LeakyReLU(0.2, inplace=True))
+        self.concat2 = nn.Sequential(nn.Conv2d(2 * ch, ch, 3, 1, 1, groups=ch), nn.LeakyReLU(0.2, inplace=True))
+        self.transform_matrix_conv = nn.Conv2d(ch, n_mat, k, 1, k // 2)
+        self.translation_conv = nn.Conv2d(ch, n_trans, k, 1, k // 2)
+
+    def _mix(self, x, ref):
+        return self.concat2(self.concat(torch.cat([x, ref], 1)))
+
+
+class _AdaptBlock2_3x3(_AdaptBase):
+    """One affine matrix + translation -> 18-channel offset (models/networks.py:318-348)."""
+
+    def __init__(self, ch=64):
+        super().__init__(ch, 4, 2, 3)
+
+    def forward(self, x, ref):
+        f = self._mix(x, ref)
+        return _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), 1)
+
+
+class _AdaptBlockOffset(_AdaptBase):
+    """Per-deformable-group affine offsets + sigmoid mask (models/networks.py:280-315)."""
+
+    def __init__(self, ch=64, D=8):
+        super().__init__(ch, 4 * D, 2 * D, 5)
+        self.D = D
+        self.mask_conv = nn.Conv2d(ch, 9 * D, 5, 1, 2)
+
+    def forward(self, x, ref):
+        f = self._mix(x, ref)
+        off = _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), self.D)
+        return off, torch.sigmoid(self.mask_conv(f).float())
+
+
+class _TransOffset(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv_first = nn.Conv2d(18, 2, 3, 1, 1)
+
+    def forward(self, off):
+        return self.conv_first(off)
+
+
+def _resize_flow(flow, scale):
+    """bilinear, align_corners=True resize of a flow field, magnitudes scaled with it."""
+    return F.interpolate(flow, scale_factor=scale, mode="bilinear", align_corners=True) * scale
+
+
+class MultiAdSTN(ModulatedDeformConv2d):
+    """Coarse-to-fine flow refinement on a 3-level pyramid, then DCNv2 with per-group affine
+    offsets (reference: models/networks.py:575-631)."""
+
+    def __init__(self, ch=64, deformable_groups=8):
+        super().__init__(ch, ch, kernel_size=3, padding=1, stride=1, dilation=1, deform_groups=deformable_groups)
+        for i in (1, 2, 3):
+            setattr(self, f"flow_l{i}", _AdaptBlock2_3x3(ch))
+        self.adastn = _AdaptBlockOffset(ch, deformable_groups)
+        for i in (3, 2, 1):
+            setattr(self, f"trans_l{i}", _TransOffset())
+
+    def _residual(self, lvl, warped, ref):
+        off18 = getattr(self, f"flow_l{lvl}")(warped, ref)
+        return getattr(self, f"trans_l{lvl}")(off18.to(warped.dtype)).float()
+
+    def forward(self, nbr, ref, feat_prop, flow):
+        flow = flow.float()
+        f4 = _resize_flow(flow, 0.25)
+        f2 = _resize_flow(flow, 0.5)
+        p1 = self._residual(3, flow_warp(nbr[2], f4), ref[2])
+        p1_up = _resize_flow(p1, 2)
+        p2 = self._residual(2, flow_warp(nbr[1], f2 + p1_up), ref[1])
+        p2_up = _resize_flow(p2 + p1_up, 2)
+        p3 = self._residual(1, flow_warp(nbr[0], flow + p2_up), ref[0])
+        flow = p3 + p2_up + flow
+        nbr_w = flow_warp(nbr[0], flow)
+        feat = flow_warp(feat_prop, flow)
+        offset, mask = self.adastn(nbr_w, ref[0])
+        return modulated_deform_conv2d(feat, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                       self.dilation, self.groups, self.deform_groups)
+
+
+class _ConvModule(nn.Module):
+    def __init__(self, cin, cout, act):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 7, 1, 3)
+        self.activate = nn.ReLU(inplace=True) if act else None
+
+    def forward(self, x):
+        x = self.conv(x)
+        return self.activate(x) if self.activate is not None else x
+
+
+class _SPyNetLevel(nn.Module):
+    def __init__(self):
+        super().__init__()
+        chans = (8, 32, 64, 32, 16, 2)
+        self.basic_module = nn.Sequential(*[_ConvModule(chans[i], chans[i + 1], i < 4) for i in range(5)])
+
+    def forward(self, x):
+        return self.basic_module(x)
+
+
+class SPyNet(nn.Module):
+    """6-level SPyNet (reference: models/eavsrp_model.py:402-585); always evaluated in fp32."""
+
+    def __init__(self):
+        super().__init__()
+        self.basic_module = nn.ModuleList([_SPyNetLevel() for _ in range(6)])
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+    def compute_flow(self, ref, supp):
+        n, _, h, w = ref.shape
+        ref = [(ref - self.mean) / self.std]
+        supp = [(supp - self.mean) / self.std]
+        for _ in range(5):
+            ref.append(F.avg_pool2d(ref[-1], 2, 2, count_include_pad=False))
+            supp.append(F.avg_pool2d(supp[-1], 2, 2, count_include_pad=False))
+        ref, supp = ref[::-1], supp[::-1]
+        flow = ref[0].new_zeros(n, 2, h // 32, w // 32)
+        for lvl in range(6):
+            up = flow if lvl == 0 else _resize_flow(flow, 2)
+            warped = flow_warp_nhw2(supp[lvl], up.permute(0, 2, 3, 1), padding_mode="border")
+            flow = up + self.basic_module[lvl](torch.cat([ref[lvl], warped, up], 1))
+        return flow
+
+    def forward(self, ref, supp):
+        h, w = ref.shape[2:]
+        hu, wu = -(-h // 32) * 32, -(-w // 32) * 32
+        ref = F.interpolate(ref, size=(hu, wu), mode="bilinear", align_corners=False)
+        supp = F.interpolate(supp, size=(hu, wu), mode="bilinear", align_corners=False)
+        flow = F.interpolate(self.compute_flow(ref, supp), size=(h, w), mode="bilinear", align_corners=False)
+        return flow * flow.new_tensor([w / wu, h / hu]).view(1, 2, 1, 1)
+
+
+_BRANCHES = ("backward_1", "forward_1", "backward_2", "forward_2")
+
+
+class EAVSRP(nn.Module):
+    """EAVSR+ generator, scale 4 (models/eavsrp_model.py:121-364) or 2 (models/eavsrpx2_model.py)."""
+
+    def __init__(self, scale=4, n_feats=64, n_resblock=30, deformable_groups=8):
+        super().__init__()
+        assert scale in (2, 4)
+        self.scale, self.n_feats = scale, n_feats
+        self.spynet = SPyNet()
+        for p in self.spynet.parameters():
+            p.requires_grad = False
+        self.encoder = _Encoder(n_feats)
+        self.deform_align, self.backbone, self.fusion = nn.ModuleDict(), nn.ModuleDict(), nn.ModuleDict()
+        for i, b in enumerate(_BRANCHES):
+            self.deform_align[b] = MultiAdSTN(n_feats, deformable_groups)
+            self.backbone[b] = _ResidualStack((2 + i) * n_feats, n_feats, n_resblock)
+            self.fusion[b] = nn.Conv2d(3 * n_feats, n_feats, 1)
+        self.reconstruction = _ResidualStack(5 * n_feats, n_feats, 5)
+        self.upsample1 = nn.Sequential(nn.Conv2d(n_feats, 4 * n_feats, 3, 1, 1), nn.PixelShuffle(2))
+        if scale == 4:
+            self.upsample2 = nn.Sequential(nn.Conv2d(n_feats, 4 * n_feats, 3, 1, 1), nn.PixelShuffle(2))
+        self.conv_hr = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_last = nn.Conv2d(64, 3, 3, 1, 1)
+        self.compute_dtype = torch.float32
+
+    # -- precision / layout policy ---------------------------------------------------------
+    def prepare(self, dtype=torch.bfloat16):
+        """channels_last everywhere; features in `dtype`; SPyNet stays fp32 (flows are coordinates)."""
+        self.to(memory_format=torch.channels_last)
+        for name, child in self.named_children():
+            if name != "spynet":
+                child.to(dtype)
+        self.compute_dtype = dtype
+        return self
+
+    # -- flows -------------------------------------------------------------------------------
+    def compute_flow(self, lrs):
+        n, t, c, h, w = lrs.shape
+        a = lrs[:, :-1].reshape(-1, c, h, w)
+        b = lrs[:, 1:].reshape(-1, c, h, w)
+        m = a.shape[0]
+        # both directions in one batch: [backward (a<-b); forward (b<-a)]
+        flows = self.spynet(torch.cat([a, b]).float(), torch.cat([b, a]).float())
+        return flows[m:].view(n, t - 1, 2, h, w), flows[:m].view(n, t - 1, 2, h, w)   # forward, backward
+
+    # -- one propagation branch ----------------------------------------------------------------
+    def _propagate(self, feats, flows, branch):
+        n, tm1, _, h, w = flows.shape
+        t = tm1 + 1
+        backward = branch.startswith("backward")
+        order = range(t - 1, -1, -1) if backward else range(t)
+        step = 1 if backward else -1                     # index offset of the previously visited frame
+        align, fuse, body = self.deform_align[branch], self.fusion[branch], self.backbone[branch]
+        others = [k for k in feats if k not in ("spatial", "spatial_d2", "spatial_d4", branch)]
+        pyr = lambda j: [feats["spatial"][j], feats["spatial_d2"][j], feats["spatial_d4"][j]]   # noqa: E731
+        prop = feats["spatial"][0].new_zeros(n, self.n_feats, h, w).contiguous(memory_format=torch.channels_last)
+        outs = []
+        prev_flow = None
+        for i, idx in enumerate(order):
+            cur = feats["spatial"][idx]
+            if i > 0:
+                flow1 = flows[:, idx if backward else idx - 1]
+                cond1 = align(pyr(idx + step), pyr(idx), prop, flow1)
+                if i > 1:
+                    flow2 = flow1 + flow_warp_nhw2(prev_flow, flow1.permute(0, 2, 3, 1))
+                    cond2 = align(pyr(idx + 2 * step), pyr(idx), outs[-2], flow2)
+                else:
+                    cond2 = torch.zeros_like(cond1)
+                prop = fuse(torch.cat([cond1, cur, cond2], 1))
+                prev_flow = flow1
+            x = torch.cat([cur] + [feats[k][idx] for k in others] + [prop], 1)
+            prop = prop + body(x)
+            outs.append(prop)
+        feats[branch] = outs[::-1] if backward else outs
+        return feats
+
+    def _upsample(self, lrs, feats):
+        outs = []
+        for i in range(lrs.shape[1]):
+            x = torch.cat([feats["spatial"][i]] + [feats[b][i] for b in _BRANCHES], 1)
+            x = self.reconstruction(x)
+            x = F.leaky_relu(self.upsample1(x), 0.1)
+            if self.scale == 4:
+                x = F.leaky_relu(self.upsample2(x), 0.1)
+            x = F.leaky_relu(self.conv_hr(x), 0.1)
+            x = self.conv_last(x)
+            base = F.interpolate(lrs[:, i], scale_factor=self.scale, mode="bilinear", align_corners=False)
+            outs.append(x + base)
+        return torch.stack(outs, 1)
+
+    def forward(self, lrs):
+        n, t, c, h, w = lrs.shape
+        assert h >= 64 and w >= 64, f"The height and width of inputs should be at least 64, but got {h} and {w}."
+        if h % 4 or w % 4:
+            raise ValueError(f"EAVSRP needs H and W divisible by 4 (3-level pyramid), got {h}x{w}; "
+                             "replicate-pad the clip (see eavsr_b200.model.pad_clip)")
+        with torch.no_grad():
+            flows_fwd, flows_bwd = self.compute_flow(lrs)
+        x = lrs.reshape(-1, c, h, w).to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
+        f1 = self.encoder(x)
+        f2 = F.interpolate(f1, scale_factor=0.5, mode="bilinear", align_corners=False)
+        f4 = F.interpolate(f1, scale_factor=0.25, mode="bilinear", align_corners=False)
+        split = lambda f: list(f.view(n, t, *f.shape[1:]).unbind(1))      # noqa: E731
+        feats = {"spatial": split(f1), "spatial_d2": split(f2), "spatial_d4": split(f4)}
+        for b in _BRANCHES:
+            feats = self._propagate(feats, flows_bwd if b.startswith("backward") else flows_fwd, b)
+        return self._upsample(lrs.to(self.compute_dtype), feats)
+
+
+def pad_clip(lrs, multiple=4):
+    """Replicate-pad (n,t,c,h,w) so that h, w are multiples of `multiple` (270 -> 272)."""
+    h, w = lrs.shape[-2:]
+    ph, pw = (-h) % multiple, (-w) % multiple
+    if ph == 0 and pw == 0:
+        return lrs
+    n, t, c = lrs.shape[:3]
+    out = F.pad(lrs.reshape(n * t, c, h, w), (0, pw, 0, ph), mode="replicate")
+    return out.view(n, t, c, h + ph, w + pw)
