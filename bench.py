@@ -218,7 +218,7 @@ class ModelWorkload:
 
 def make_workload(name, device):
     if name == "hotpath":
-        return HotpathWorkload(device)
+        return HotpathWorkload(device, t=T_FRAMES)
     if name == "model":
         return ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W)
     raise SystemExit(f"unknown workload {name}")
@@ -305,6 +305,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("EAVSR_BENCH_WORKLOAD", "model"))
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per clip (profiling runs only; default 30)")
+    ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -326,6 +328,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     peaks = load_peaks()
+    global T_FRAMES
+    T_FRAMES = args.frames
     wl = make_workload(args.workload, device)
 
     def barrier():
@@ -377,7 +381,7 @@ def main():
             e2e = {"value": round(world * wl.frames_per_step * args.steps / (ems / 1e3), 3), "unit": "frames/s",
                    "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes}
 
-        roof = dcn_roofline(device, peaks) if rank == 0 else None
+        roof = dcn_roofline(device, peaks) if (rank == 0 and not args.no_roofline) else None
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

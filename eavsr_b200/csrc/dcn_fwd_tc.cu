@@ -154,12 +154,13 @@ dcn_fwd_tc_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
     const int n = tile / tiles_per_img;
     const int pix0 = (tile - n * tiles_per_img) * TILE_M;
     const XT* xn = x + (size_t)n * xs_n;
-    int py_i[NI], px_i[NI];
+    float py_f[NI], px_f[NI];   // un-offset sampling position of tap (0,0): (y-1, x-1)
 #pragma unroll
     for (int j = 0; j < NI; ++j) {
       const int pix = pix0 + rbase + j * Cfg::ROWS_PER_PASS;
-      py_i[j] = pix < HW ? pix / W : -100000;   // sentinel: sample rejected as out of range
-      px_i[j] = pix < HW ? pix - (pix / W) * W : 0;
+      const int yy = pix / W;
+      py_f[j] = pix < HW ? (float)(yy - 1) : -100000.f;   // sentinel: sample rejected as out of range
+      px_f[j] = pix < HW ? (float)(pix - yy * W - 1) : 0.f;
     }
 
     for (int tap = 0; tap < TAPS; ++tap, ++it) {
@@ -187,29 +188,28 @@ dcn_fwd_tc_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
           const float dy = so[(0 * DG + grp) * PL + r];
           const float dx = so[(1 * DG + grp) * PL + r];
           const float m = so[(2 * DG + grp) * PL + r];
-          const float py = (float)(py_i[j] - 1 + ti) + dy;
-          const float px = (float)(px_i[j] - 1 + tj) + dx;
+          const float py = (py_f[j] + (float)ti) + dy;
+          const float px = (px_f[j] + (float)tj) + dx;
           const bool inside = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
           const float fy = floorf(py), fx = floorf(px);
           const int y0 = (int)fy, x0 = (int)fx;
           const float ly = py - fy, lx = px - fx;
           const bool vy0 = inside && y0 >= 0, vy1 = inside && y0 + 1 <= H - 1;
           const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= W - 1;
-          const bool ok[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
-          wgt[jj][0] = ok[0] ? m * (1.f - ly) * (1.f - lx) : 0.f;
-          wgt[jj][1] = ok[1] ? m * (1.f - ly) * lx : 0.f;
-          wgt[jj][2] = ok[2] ? m * ly * (1.f - lx) : 0.f;
-          wgt[jj][3] = ok[3] ? m * ly * lx : 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (ok[q]) {
-              const int yy = y0 + (q >> 1), xx = x0 + (q & 1);
-              RawVec<XT, CPI>::ld(xn + ((size_t)yy * W + xx) * CH + l * CPI, raw[jj][q]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < RawVec<XT, CPI>::NW; ++e) raw[jj][q][e] = 0u;
-            }
-          }
+          wgt[jj][0] = (vy0 && vx0) ? m * (1.f - ly) * (1.f - lx) : 0.f;
+          wgt[jj][1] = (vy0 && vx1) ? m * (1.f - ly) * lx : 0.f;
+          wgt[jj][2] = (vy1 && vx0) ? m * ly * (1.f - lx) : 0.f;
+          wgt[jj][3] = (vy1 && vx1) ? m * ly * lx : 0.f;
+          // Unconditional loads: an out-of-image corner reads a clamped in-image address with
+          // weight 0 (no divergent branches around the four LDGs); 32-bit element offsets.
+          const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+          const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+          const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * CPI;
+          const uint32_t sxo = (uint32_t)(cx1 - cx0) * CH, syo = (uint32_t)((cy1 - cy0) * W) * CH;
+          RawVec<XT, CPI>::ld(xn + b00, raw[jj][0]);
+          RawVec<XT, CPI>::ld(xn + b00 + sxo, raw[jj][1]);
+          RawVec<XT, CPI>::ld(xn + b00 + syo, raw[jj][2]);
+          RawVec<XT, CPI>::ld(xn + b00 + syo + sxo, raw[jj][3]);
         }
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
@@ -403,7 +403,7 @@ extern "C" int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], cons
     tc = nhwc_dense(x_strides, cin, h, w) && nhwc_dense(out_strides, cout, h, w) &&
          ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
          ((x_strides[0] * esz) % 16 == 0) && ((out_strides[0] * esz) % 16 == 0) &&
-         (!bias || (reinterpret_cast<uintptr_t>(bias) & 3u) == 0) && ((long long)h * w < (1ll << 30));
+         (!bias || (reinterpret_cast<uintptr_t>(bias) & 3u) == 0) && ((long long)h * w * CH < (1ll << 31));
   }
   if (tc) {
     const size_t need = eavsr_dcn_forward_workspace(cin, cout, kh, kw, groups, deform_groups, dtype);

@@ -95,11 +95,12 @@ class _Encoder(nn.Module):
 _R = ((-1., -1., -1., 0., 0., 0., 1., 1., 1.), (-1., 0., 1., -1., 0., 1., -1., 0., 1.))
 
 
-def _affine_offsets(T, t, D):
+def _affine_offsets(T, t, D, R=None):
     """offset[n, (g*9+k)*2+i] = sum_j T[n,g,i,j] * R[j,k] - R[i,k] + t[n,g,i]
-    (reference: matmul + 4 permute/reshape copies at models/networks.py:302-310)."""
+    (reference: matmul + 4 permute/reshape copies at models/networks.py:302-310).
+    R is the module's `regular_matrix` buffer (already on the device: no H2D copy, graph-safe)."""
     n, _, h, w = T.shape
-    R = T.new_tensor(_R)                                   # (2, 9)
+    R = T.new_tensor(_R) if R is None else R.to(T.dtype)   # (2, 9)
     T = T.reshape(n, D, 1, 2, 2, h, w)                     # g, -, i, j
     Rk = R.t().reshape(1, 1, 9, 1, 2, 1, 1)                # -, -, k, -, j
     off = (T * Rk).sum(4) - R.t().reshape(1, 1, 9, 2, 1, 1) + t.reshape(n, D, 1, 2, h, w)
@@ -127,7 +128,8 @@ class _AdaptBlock2_3x3(_AdaptBase):
 
     def forward(self, x, ref):
         f = self._mix(x, ref)
-        return _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), 1)
+        return _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), 1,
+                               self.regular_matrix)
 
 
 class _AdaptBlockOffset(_AdaptBase):
@@ -140,7 +142,8 @@ class _AdaptBlockOffset(_AdaptBase):
 
     def forward(self, x, ref):
         f = self._mix(x, ref)
-        off = _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), self.D)
+        off = _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), self.D,
+                              self.regular_matrix)
         return off, torch.sigmoid(self.mask_conv(f).float())
 
 
@@ -242,7 +245,7 @@ class SPyNet(nn.Module):
         ref = F.interpolate(ref, size=(hu, wu), mode="bilinear", align_corners=False)
         supp = F.interpolate(supp, size=(hu, wu), mode="bilinear", align_corners=False)
         flow = F.interpolate(self.compute_flow(ref, supp), size=(h, w), mode="bilinear", align_corners=False)
-        return flow * flow.new_tensor([w / wu, h / hu]).view(1, 2, 1, 1)
+        return torch.cat([flow[:, :1] * (w / wu), flow[:, 1:] * (h / hu)], 1)
 
 
 _BRANCHES = ("backward_1", "forward_1", "backward_2", "forward_2")
@@ -332,9 +335,9 @@ class EAVSRP(nn.Module):
             if self.scale == 4:
                 x = F.leaky_relu(self.upsample2(x), 0.1)
             x = F.leaky_relu(self.conv_hr(x), 0.1)
-            x = self.conv_last(x)
-            base = F.interpolate(lrs[:, i], scale_factor=self.scale, mode="bilinear", align_corners=False)
-            outs.append(x + base)
+            # the image-domain tail is fp32: residual (small) + bilinear base (the [0,1] frame itself)
+            base = F.interpolate(lrs[:, i].float(), scale_factor=self.scale, mode="bilinear", align_corners=False)
+            outs.append(self.conv_last(x).float() + base)
         return torch.stack(outs, 1)
 
     def forward(self, lrs):
@@ -353,7 +356,7 @@ class EAVSRP(nn.Module):
         feats = {"spatial": split(f1), "spatial_d2": split(f2), "spatial_d4": split(f4)}
         for b in _BRANCHES:
             feats = self._propagate(feats, flows_bwd if b.startswith("backward") else flows_fwd, b)
-        return self._upsample(lrs.to(self.compute_dtype), feats)
+        return self._upsample(lrs, feats)
 
 
 def pad_clip(lrs, multiple=4):

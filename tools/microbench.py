@@ -76,7 +76,7 @@ def bench_warp():
             fg = [f.clone().requires_grad_() for f in fl[:m]]
             outs = [E.flow_warp(a, b) for a, b in zip(xg, fg)]
             gs = [torch.randn_like(o) for o in outs]
-            sec = timeit(lambda i: torch.autograd.grad(outs[i % m], [xg[i % m], fg[i % m]], gs[i % m], retain_graph=True), 30)
+            sec = timeit(lambda i: torch.autograd.grad(outs[i % m], [xg[i % m], fg[i % m]], gs[i % m], retain_graph=True), 30, graph=False)
             rec(f"flow_warp bwd(x,flow) {dt} {n}x64x{h}x{w}", sec, n * h * w * (3 * 64 * es + 16))
     x2 = torch.randn(1, 2, 270, 480, device=dev)
     f2 = torch.randn(1, 270, 480, 2, device=dev)
@@ -119,7 +119,7 @@ def bench_dcn():
                     og, mg, wg, bg = offs[0].clone().requires_grad_(), msks[0].clone().requires_grad_(), wgt.clone().requires_grad_(), bias.clone().requires_grad_()
                     out = E.modulated_deform_conv2d(xg, og, mg, wg, bg, 1, 1, 1, 1, dg)
                     go = torch.randn_like(out)
-                    sec = timeit(lambda i: torch.autograd.grad(out, [xg, og, mg, wg, bg], go, retain_graph=True), 3, warm=1)
+                    sec = timeit(lambda i: torch.autograd.grad(out, [xg, og, mg, wg, bg], go, retain_graph=True), 3, warm=1, graph=False)
                     rec(f"dcn bwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by * 2, fl * 2)
                 del xs, offs, msks
                 torch.cuda.empty_cache()
@@ -137,7 +137,7 @@ def bench_corr():
         ag, bg = a[0].clone().requires_grad_(), b[0].clone().requires_grad_()
         out = E.FunctionCorrelation(tenFirst=ag, tenSecond=bg)
         go = torch.randn_like(out)
-        sec = timeit(lambda i: torch.autograd.grad(out, [ag, bg], go, retain_graph=True), 10)
+        sec = timeit(lambda i: torch.autograd.grad(out, [ag, bg], go, retain_graph=True), 10, graph=False)
         rec(f"correlation bwd f32 {n}x{c}x{h}x{w}", sec, n * h * w * (4 * c + 81) * 4, 4.0 * 81 * c * n * h * w)
 
 
