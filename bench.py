@@ -298,6 +298,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    global T_FRAMES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -328,7 +329,6 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     peaks = load_peaks()
-    global T_FRAMES
     T_FRAMES = args.frames
     wl = make_workload(args.workload, device)
 

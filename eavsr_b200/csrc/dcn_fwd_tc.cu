@@ -17,6 +17,7 @@
 // Work decomposition: tile = 128 consecutive pixels of one image, persistent CTAs
 // (2 per SM when shared memory allows) striding over tiles.
 #include "common.cuh"
+#include "dcn_fwd_ws.cuh"
 
 namespace eavsr {
 
@@ -302,7 +303,7 @@ bool nhwc_dense(const int64_t s[4], int c, int h, int w) {
 template <typename XT, bool SPLIT, int DG>
 int launch_tc(const void* x, const int64_t* xs, const float* offset, const float* mask, const void* weight,
               const void* bias, void* out, const int64_t* os, int n, int h, int w, void* workspace,
-              cudaStream_t st) {
+              unsigned flags, cudaStream_t st) {
   using SM = TcSmem<SPLIT, DG>;
   dcn_pack_weight<XT, SPLIT><<<(TAPS * CH * CH + 255) / 256, 256, 0, st>>>((const XT*)weight, (uint8_t*)workspace);
   int rc = check_launch("dcn_forward(pack)");
@@ -317,6 +318,19 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
   const int grid = total < sms * per_sm ? total : sms * per_sm;
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
+  if constexpr (DG <= 8) {
+    if (!(flags & EAVSR_DCN_FORCE_V1)) {       // warp-specialised second-generation kernel
+      using WS = ws::Smem<SPLIT>;
+      auto kv = ws::dcn_fwd_ws_kernel<XT, SPLIT, DG, true>;
+      auto ks = ws::dcn_fwd_ws_kernel<XT, SPLIT, DG, false>;
+      auto k = vec ? kv : ks;
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, WS::DYN_BYTES);
+      if (e != cudaSuccess) { set_error("dcn_forward(ws): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+      k<<<grid, ws::THREADS, WS::DYN_BYTES, st>>>((const XT*)x, offset, mask, (const uint8_t*)workspace,
+                                                   (const XT*)bias, (XT*)out, h, w, xs[0], os[0], tiles_per_img, total);
+      return check_launch("dcn_forward(ws)");
+    }
+  }
   auto kv = dcn_fwd_tc_kernel<XT, SPLIT, DG, true>;
   auto ks = dcn_fwd_tc_kernel<XT, SPLIT, DG, false>;
   auto k = vec ? kv : ks;
@@ -330,13 +344,13 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
 template <typename XT, bool SPLIT>
 int launch_tc_dg(int dg, const void* x, const int64_t* xs, const float* offset, const float* mask,
                  const void* weight, const void* bias, void* out, const int64_t* os, int n, int h, int w,
-                 void* workspace, cudaStream_t st) {
+                 void* workspace, unsigned flags, cudaStream_t st) {
   switch (dg) {
-    case 1: return launch_tc<XT, SPLIT, 1>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, st);
-    case 2: return launch_tc<XT, SPLIT, 2>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, st);
-    case 4: return launch_tc<XT, SPLIT, 4>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, st);
-    case 8: return launch_tc<XT, SPLIT, 8>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, st);
-    case 16: return launch_tc<XT, SPLIT, 16>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, st);
+    case 1: return launch_tc<XT, SPLIT, 1>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
+    case 2: return launch_tc<XT, SPLIT, 2>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
+    case 4: return launch_tc<XT, SPLIT, 4>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
+    case 8: return launch_tc<XT, SPLIT, 8>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
+    case 16: return launch_tc<XT, SPLIT, 16>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
   }
   set_error("dcn_forward(tc): deform_groups %d", dg);
   return EAVSR_ERR_INVALID;
@@ -412,9 +426,9 @@ extern "C" int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], cons
                   workspace_bytes);
     if (dtype == EAVSR_F32)
       return launch_tc_dg<float, true>(deform_groups, x, x_strides, offset, mask, weight, bias, out, out_strides, n, h,
-                                       w, workspace, st);
+                                       w, workspace, flags, st);
     return launch_tc_dg<__nv_bfloat16, false>(deform_groups, x, x_strides, offset, mask, weight, bias, out,
-                                              out_strides, n, h, w, workspace, st);
+                                              out_strides, n, h, w, workspace, flags, st);
   }
   if (dtype == EAVSR_F32)
     return dcn_forward_generic<float>(x, x_strides, offset, mask, weight, bias, out, out_strides, g, st);

@@ -135,29 +135,42 @@ flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* _
   }
   const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
 
-  // phase 2: lane <-> (pixel sub*PPI + lane / CPP, chunk lane % CPP)
+  // phase 2: lane <-> (pixel sub*PPI + lane / CPP, chunk lane % CPP).  UN sub-steps are batched so
+  // that 4*UN 16-byte loads per thread are in flight before the first blend (the un-batched
+  // version serialised CPP round trips to L2/HBM per warp).
   const int chunk = lane % CPP;
-#pragma unroll 4
-  for (int sub = 0; sub < CPP; ++sub) {
-    const int src = sub * PPI + lane / CPP;
-    const uint32_t b = __shfl_sync(0xffffffffu, base, src) + chunk * VEC;
-    const uint32_t sxo = __shfl_sync(0xffffffffu, stepx, src);
-    const uint32_t syo = __shfl_sync(0xffffffffu, stepy, src);
-    const float a00 = __shfl_sync(0xffffffffu, w00, src), a01 = __shfl_sync(0xffffffffu, w01, src);
-    const float a10 = __shfl_sync(0xffffffffu, w10, src), a11 = __shfl_sync(0xffffffffu, w11, src);
-    if (!((live_mask >> src) & 1u)) continue;
-    uint32_t r00[RawVec<T, VEC>::NW], r01[RawVec<T, VEC>::NW], r10[RawVec<T, VEC>::NW], r11[RawVec<T, VEC>::NW];
-    RawVec<T, VEC>::ld(xn + b, r00);
-    RawVec<T, VEC>::ld(xn + b + sxo, r01);
-    RawVec<T, VEC>::ld(xn + b + syo, r10);
-    RawVec<T, VEC>::ld(xn + b + syo + sxo, r11);
-    float r[VEC];
+  constexpr int UN = CPP >= 4 ? 4 : CPP;
+  constexpr int NW = RawVec<T, VEC>::NW;
+#pragma unroll 1
+  for (int sub0 = 0; sub0 < CPP; sub0 += UN) {
+    uint32_t raw[UN][4][NW];
+    float a[UN][4];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j)
-      r[j] = a00 * RawVec<T, VEC>::get(r00, j) + a01 * RawVec<T, VEC>::get(r01, j) +
-             a10 * RawVec<T, VEC>::get(r10, j) + a11 * RawVec<T, VEC>::get(r11, j);
-    const int oy = py0 + (src >> 3), ox = px0 + (src & 7);
-    VecLoad<T, VEC>::st(on + (uint32_t)(oy * W + ox) * C + chunk * VEC, r);
+    for (int u = 0; u < UN; ++u) {
+      const int src = (sub0 + u) * PPI + lane / CPP;
+      const uint32_t b = __shfl_sync(0xffffffffu, base, src) + chunk * VEC;
+      const uint32_t sxo = __shfl_sync(0xffffffffu, stepx, src);
+      const uint32_t syo = __shfl_sync(0xffffffffu, stepy, src);
+      a[u][0] = __shfl_sync(0xffffffffu, w00, src);
+      a[u][1] = __shfl_sync(0xffffffffu, w01, src);
+      a[u][2] = __shfl_sync(0xffffffffu, w10, src);
+      a[u][3] = __shfl_sync(0xffffffffu, w11, src);
+      RawVec<T, VEC>::ld(xn + b, raw[u][0]);              // dead pixels read element 0 with weight 0
+      RawVec<T, VEC>::ld(xn + b + sxo, raw[u][1]);
+      RawVec<T, VEC>::ld(xn + b + syo, raw[u][2]);
+      RawVec<T, VEC>::ld(xn + b + syo + sxo, raw[u][3]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int src = (sub0 + u) * PPI + lane / CPP;
+      float r[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        r[j] = a[u][0] * RawVec<T, VEC>::get(raw[u][0], j) + a[u][1] * RawVec<T, VEC>::get(raw[u][1], j) +
+               a[u][2] * RawVec<T, VEC>::get(raw[u][2], j) + a[u][3] * RawVec<T, VEC>::get(raw[u][3], j);
+      const int oy = py0 + (src >> 3), ox = px0 + (src & 7);
+      if ((live_mask >> src) & 1u) VecLoad<T, VEC>::st(on + (uint32_t)(oy * W + ox) * C + chunk * VEC, r);
+    }
   }
 }
 

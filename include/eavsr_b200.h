@@ -44,6 +44,7 @@ extern "C" {
 #define EAVSR_PAD_BORDER 1
 
 #define EAVSR_DCN_FORCE_GENERIC 1u /* flags bit: skip the tcgen05 path (validation only) */
+#define EAVSR_DCN_FORCE_V1 2u      /* flags bit: first-generation tcgen05 kernel (A/B timing only) */
 
 /* ---- library ------------------------------------------------------------------------ */
 int eavsr_version(void);

@@ -144,12 +144,24 @@ def test_dcn_zero_offset_equals_conv2d(cuda):
     assert max_err(out, ref) < 1e-4
 
 
-def test_dcn_tc_matches_generic(cuda):
-    x, off, mask, wgt, bias = dcn_inputs(1, 64, 40, 72, 64, 8, seed=9)
+@pytest.mark.parametrize("shape", [(1, 40, 72), (3, 67, 121), (1, 270, 480)])
+def test_dcn_tc_kernels_agree(cuda, shape):
+    """warp-specialised tcgen05 kernel == first-generation tcgen05 kernel == generic SIMT kernel,
+    including a multi-image batch with an odd width (scalar cp.async path) and the full bench size
+    (persistent CTAs looping over several tiles, both TMEM accumulators in use)."""
+    n, h, w = shape
+    x, off, mask, wgt, bias = dcn_inputs(n, 64, h, w, 64, 8, seed=9)
     args = (_cl(x.to(cuda)), off.to(cuda), mask.to(cuda), wgt.to(cuda), bias.to(cuda), 1, 1, 1, 1, 8)
     a = _ModulatedDeformConv2dFn.apply(*args, 0)
-    b = _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_GENERIC)
-    assert max_err(a, b) < 1e-4
+    b = _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_V1)
+    c = _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_GENERIC)
+    assert max_err(a, c) < 1e-4
+    assert max_err(b, c) < 1e-4
+    xb = args[0].bfloat16()
+    a16 = _ModulatedDeformConv2dFn.apply(xb, *args[1:3], wgt.to(cuda).bfloat16(), bias.to(cuda).bfloat16(), 1, 1, 1, 1, 8, 0)
+    b16 = _ModulatedDeformConv2dFn.apply(xb, *args[1:3], wgt.to(cuda).bfloat16(), bias.to(cuda).bfloat16(), 1, 1, 1, 1, 8,
+                                         L.DCN_FORCE_V1)
+    assert torch.equal(a16, b16)            # same arithmetic, bit-identical
 
 
 @pytest.mark.parametrize("cfg", [
