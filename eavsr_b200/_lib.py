@@ -46,6 +46,10 @@ _SIGNATURES = {
                                           c_void_p]),
     "eavsr_correlation_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_int, c_int, c_void_p]),
+    "eavsr_adapt_mix_forward": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    "eavsr_affine_offsets_forward": (c_int, [c_void_p, _P64, c_void_p, _P64, c_void_p, _P64, _PF, _PF] + [c_int] * 5 +
+                                     [c_void_p]),
+    "eavsr_ca_residual_forward": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

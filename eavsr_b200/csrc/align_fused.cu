@@ -1,0 +1,346 @@
+// Fused producers / consumers around the alignment hot path (inference, sm_100a).
+//
+// ncu launch list of the full EAVSR+ forward (profiles/): once DCNv2 and the warps run on this
+// library, 75 % of the device time is PyTorch glue between them -- cuDNN's grouped-direct kernel for
+// the two tiny grouped 3x3 convolutions in every AdaptBlock (403 us per call), TensorIterator
+// broadcast kernels for the affine offset expansion, and a reduce + four small launches per channel
+// attention.  These kernels replace that glue:
+//
+//   adapt_mix        concat2(concat(cat[x, ref]))            models/networks.py:289-290,299 / 327-328,334
+//                    = depthwise 3x3 (128 ch) + LeakyReLU(0.2) + grouped 3x3 (2 -> 1, 64 groups) +
+//                    LeakyReLU(0.2) in ONE pass over the two inputs (50 MB instead of ~200 MB + 2 launches)
+//   affine_offsets   T*R - R + t expansion + sigmoid(mask)   models/networks.py:302-313
+//   channel_sum /    CALayer (global mean -> 1x1 -> ReLU -> 1x1 -> sigmoid -> scale) + residual add
+//   ca_scale_residual                                        models/networks.py:449-465 (RCABlock)
+#include "common.cuh"
+
+namespace eavsr {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// adapt_mix
+// ---------------------------------------------------------------------------------------------
+constexpr int MX_TH = 8, MX_TW = 16;            // output tile
+constexpr int MX_IH = MX_TH + 4, MX_IW = MX_TW + 4;
+constexpr int MX_YH = MX_TH + 2, MX_YW = MX_TW + 2;
+constexpr int MX_C = 64;                        // channels of each input
+constexpr int MX_THREADS = 256;
+
+// 8 consecutive channels from shared memory, widened to fp32 (one / two 16-byte LDS)
+__device__ __forceinline__ void lds8(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16lo_to_f32(u.x); f[1] = bf16hi_to_f32(u.x); f[2] = bf16lo_to_f32(u.y); f[3] = bf16hi_to_f32(u.y);
+  f[4] = bf16lo_to_f32(u.z); f[5] = bf16hi_to_f32(u.z); f[6] = bf16lo_to_f32(u.w); f[7] = bf16hi_to_f32(u.w);
+}
+__device__ __forceinline__ void lds8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <typename T> struct MixSmem {
+  T in[MX_IH * MX_IW][MX_C];
+  T y[MX_YH * MX_YW][MX_C];
+  float w1[9][MX_C];
+  float w2[9][MX_C];
+  float b1[MX_C];
+  float b2[MX_C / 2];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(MX_THREADS)
+adapt_mix_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ w1g,
+                 const T* __restrict__ b1g, const T* __restrict__ w2g, const T* __restrict__ b2g,
+                 T* __restrict__ out, int H, int W, float slope) {
+  extern __shared__ __align__(16) uint8_t mix_smem_raw[];
+  MixSmem<T>& S = *reinterpret_cast<MixSmem<T>*>(mix_smem_raw);
+  constexpr int VEC = 16 / sizeof(T);           // channels per 16-byte chunk
+  constexpr int CPP = MX_C / VEC;               // chunks per pixel
+  const int half = blockIdx.z & 1, n = blockIdx.z >> 1;
+  const int y0 = blockIdx.y * MX_TH, x0 = blockIdx.x * MX_TW;
+  const T* src = (half ? b : a) + (size_t)n * H * W * MX_C;
+  const int tid = threadIdx.x;
+
+  // weights of this half: cat channels [half*64, half*64+64) -> out channels [half*32, half*32+32)
+  for (int i = tid; i < 9 * MX_C; i += MX_THREADS) {
+    const int tap = i / MX_C, c = i % MX_C;
+    S.w1[tap][c] = to_f32<T>(w1g[(size_t)(half * MX_C + c) * 9 + tap]);
+    // y channel c feeds out channel half*32 + c/2 as its input (c & 1)
+    S.w2[tap][c] = to_f32<T>(w2g[((size_t)(half * (MX_C / 2) + (c >> 1)) * 2 + (c & 1)) * 9 + tap]);
+  }
+  for (int i = tid; i < MX_C; i += MX_THREADS) S.b1[i] = to_f32<T>(b1g[half * MX_C + i]);
+  for (int i = tid; i < MX_C / 2; i += MX_THREADS) S.b2[i] = to_f32<T>(b2g[half * (MX_C / 2) + i]);
+
+  // input tile with a 2-pixel halo, zero outside the image (conv zero padding)
+  for (int i = tid; i < MX_IH * MX_IW * CPP; i += MX_THREADS) {
+    const int p = i / CPP, ch = i % CPP;
+    const int gy = y0 - 2 + p / MX_IW, gx = x0 - 2 + p % MX_IW;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)gy * W + gx) * MX_C) + ch);
+    *reinterpret_cast<uint4*>(&S.in[p][ch * VEC]) = v;
+  }
+  __syncthreads();
+
+  // phase 1: y = lrelu(depthwise3x3(in) + b1) on the (TH+2)x(TW+2) ring, 0 outside the image
+  for (int i = tid; i < MX_YH * MX_YW * (MX_C / 8); i += MX_THREADS) {
+    const int p = i / (MX_C / 8), c0 = (i % (MX_C / 8)) * 8;
+    const int yy = p / MX_YW, xx = p % MX_YW;
+    const int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = S.b1[c0 + e];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      float v[8];
+      lds8(&S.in[(yy + tap / 3) * MX_IW + xx + tap % 3][c0], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += S.w1[tap][c0 + e] * v[e];
+    }
+    const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = acc[e] > 0.f ? acc[e] : acc[e] * slope;
+      S.y[p][c0 + e] = from_f32<T>(inside ? v : 0.f);
+    }
+  }
+  __syncthreads();
+
+  // phase 2: out[o] = lrelu(b2[o] + sum_tap w2[tap][2o] y[2o] + w2[tap][2o+1] y[2o+1])
+  for (int i = tid; i < MX_TH * MX_TW * (MX_C / 8); i += MX_THREADS) {
+    const int p = i / (MX_C / 8), c0 = (i % (MX_C / 8)) * 8;
+    const int yy = p / MX_TW, xx = p % MX_TW;
+    const int gy = y0 + yy, gx = x0 + xx;
+    if (gy >= H || gx >= W) continue;
+    float acc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = S.b2[(c0 >> 1) + e];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      float v[8];
+      lds8(&S.y[(yy + tap / 3) * MX_YW + xx + tap % 3][c0], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e >> 1] += S.w2[tap][c0 + e] * v[e];
+    }
+    T* op = out + ((size_t)n * H * W + (size_t)gy * W + gx) * MX_C + half * (MX_C / 2) + (c0 >> 1);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = acc[e] > 0.f ? acc[e] : acc[e] * slope;
+      op[e] = from_f32<T>(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// affine offsets + sigmoid mask.  One thread per (pixel, group); outputs are fp32 NCHW planes
+// (lanes along pixels -> coalesced), exactly the layout eavsr_dcn_forward consumes.
+// offset[(g*9+k)*2+i] = T[g][i][0]*R0[k] + T[g][i][1]*R1[k] - R_i[k] + t[g][i]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_offsets_kernel(const T* __restrict__ tm, Strides4 ts, const T* __restrict__ tr, Strides4 rs,
+                      const T* __restrict__ ml, Strides4 ms, float* __restrict__ offset,
+                      float* __restrict__ mask, int N, int D, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W;
+  if (idx >= (long long)N * D * HW) return;
+  const int pix = (int)(idx % HW);
+  const int g = (int)((idx / HW) % D);
+  const int n = (int)(idx / (HW * D));
+  const int y = pix / W, x = pix % W;
+  const T* tp = tm + n * ts.n + y * ts.h + x * ts.w + (long long)(g * 4) * ts.c;
+  const T* rp = tr + n * rs.n + y * rs.h + x * rs.w + (long long)(g * 2) * rs.c;
+  const float a = to_f32<T>(tp[0]), b = to_f32<T>(tp[ts.c]), c = to_f32<T>(tp[2 * ts.c]), d = to_f32<T>(tp[3 * ts.c]);
+  const float t0 = to_f32<T>(rp[0]), t1 = to_f32<T>(rp[rs.c]);
+  float* op = offset + ((size_t)(n * D + g) * 18) * HW + pix;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float r0 = (float)(k / 3 - 1), r1 = (float)(k % 3 - 1);
+    op[(size_t)(2 * k) * HW] = a * r0 + b * r1 - r0 + t0;
+    op[(size_t)(2 * k + 1) * HW] = c * r0 + d * r1 - r1 + t1;
+  }
+  if (mask) {
+    const T* mp = ml + n * ms.n + y * ms.h + x * ms.w + (long long)(g * 9) * ms.c;
+    float* mo = mask + ((size_t)(n * D + g) * 9) * HW + pix;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) mo[(size_t)k * HW] = 1.f / (1.f + __expf(-to_f32<T>(mp[k * ms.c])));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel attention: sums over H*W (NHWC), then out = res * sigmoid(MLP(mean)) + skip
+// ---------------------------------------------------------------------------------------------
+constexpr int CS_THREADS = 256;
+constexpr int CS_PIX = 512;   // pixels per CTA
+
+template <typename T, int C>
+__global__ void __launch_bounds__(CS_THREADS)
+channel_sum_kernel(const T* __restrict__ x, float* __restrict__ sums, int HW) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int CPP = C / VEC;
+  constexpr int PPI = CS_THREADS / CPP;          // pixels per iteration
+  __shared__ float red[PPI][C];
+  const int n = blockIdx.y;
+  const int ch = threadIdx.x % CPP, pl = threadIdx.x / CPP;
+  const int p0 = blockIdx.x * CS_PIX;
+  const int p1 = min(p0 + CS_PIX, HW);
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  const T* xn = x + (size_t)n * HW * C;
+  for (int p = p0 + pl; p < p1; p += PPI) {
+    float v[VEC];
+    VecLoad<T, VEC>::ld(xn + (size_t)p * C + ch * VEC, v);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] += v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) red[pl][ch * VEC + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < PPI; ++i) s += red[i][threadIdx.x];
+    atomicAdd(sums + n * C + threadIdx.x, s);
+  }
+}
+
+template <typename T, int C, int R>
+__global__ void __launch_bounds__(256)
+ca_scale_residual_kernel(const T* __restrict__ res, const T* __restrict__ skip, const float* __restrict__ sums,
+                         const T* __restrict__ w1, const T* __restrict__ b1, const T* __restrict__ w2,
+                         const T* __restrict__ b2, T* __restrict__ out, int HW, float inv_hw, int chunks_per_img) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int CPP = C / VEC;
+  __shared__ float hid[R];
+  __shared__ float scale[C];
+  const int n = blockIdx.y;
+  if (threadIdx.x < R) {
+    float a = to_f32<T>(b1[threadIdx.x]);
+    for (int i = 0; i < C; ++i) a += to_f32<T>(w1[threadIdx.x * C + i]) * (sums[n * C + i] * inv_hw);
+    hid[threadIdx.x] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = to_f32<T>(b2[threadIdx.x]);
+#pragma unroll
+    for (int j = 0; j < R; ++j) a += to_f32<T>(w2[threadIdx.x * R + j]) * hid[j];
+    scale[threadIdx.x] = 1.f / (1.f + __expf(-a));
+  }
+  __syncthreads();
+  const size_t base = (size_t)n * HW * C;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < chunks_per_img; i += gridDim.x * 256) {
+    const int ch = i % CPP;
+    float r[VEC], s[VEC], o[VEC];
+    VecLoad<T, VEC>::ld(res + base + (size_t)i * VEC, r);
+    VecLoad<T, VEC>::ld(skip + base + (size_t)i * VEC, s);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o[e] = r[e] * scale[ch * VEC + e] + s[e];
+    VecLoad<T, VEC>::st(out + base + (size_t)i * VEC, o);
+  }
+}
+
+bool dense_nhwc(const int64_t s[4], int c, int h, int w) {
+  return s[1] == 1 && s[3] == c && s[2] == (int64_t)w * c && s[0] == (int64_t)h * w * c;
+}
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+int mix_launch(const void* a, const void* b, const void* w1, const void* b1, const void* w2, const void* b2,
+               void* out, int n, int h, int w, float slope, cudaStream_t st) {
+  auto k = adapt_mix_kernel<T>;
+  const int smem = (int)sizeof(MixSmem<T>);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("adapt_mix: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  dim3 grid(ceil_div(w, MX_TW), ceil_div(h, MX_TH), n * 2);
+  k<<<grid, MX_THREADS, smem, st>>>((const T*)a, (const T*)b, (const T*)w1, (const T*)b1, (const T*)w2,
+                                    (const T*)b2, (T*)out, h, w, slope);
+  return check_launch("adapt_mix");
+}
+
+}  // namespace
+}  // namespace eavsr
+
+using namespace eavsr;
+
+extern "C" int eavsr_adapt_mix_forward(const void* a, const void* b, const void* w1, const void* b1,
+                                       const void* w2, const void* b2, void* out, int n, int c, int h, int w,
+                                       float negative_slope, int dtype, void* stream) {
+  EAVSR_REQUIRE(a && b && w1 && b1 && w2 && b2 && out, "adapt_mix: null pointer");
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "adapt_mix: empty tensor");
+  if (c != MX_C) { set_error("adapt_mix: only %d-channel inputs are fused (got %d)", MX_C, c); return EAVSR_ERR_UNSUPPORTED; }
+  EAVSR_REQUIRE(al16(a) && al16(b) && al16(out), "adapt_mix: tensors must be 16-byte aligned dense NHWC");
+  EAVSR_REQUIRE(2 * n <= 65535 && ceil_div(h, MX_TH) <= 65535, "adapt_mix: batch/height too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == EAVSR_F32) return mix_launch<float>(a, b, w1, b1, w2, b2, out, n, h, w, negative_slope, st);
+  if (dtype == EAVSR_BF16) return mix_launch<__nv_bfloat16>(a, b, w1, b1, w2, b2, out, n, h, w, negative_slope, st);
+  set_error("adapt_mix: bad dtype %d", dtype);
+  return EAVSR_ERR_INVALID;
+}
+
+extern "C" int eavsr_affine_offsets_forward(const void* transform, const int64_t transform_strides[4],
+                                            const void* translation, const int64_t translation_strides[4],
+                                            const void* mask_logits, const int64_t mask_strides[4], float* offset,
+                                            float* mask, int n, int deform_groups, int h, int w, int dtype,
+                                            void* stream) {
+  EAVSR_REQUIRE(transform && translation && offset && transform_strides && translation_strides,
+                "affine_offsets: null pointer");
+  EAVSR_REQUIRE(!mask || (mask_logits && mask_strides), "affine_offsets: mask output without logits");
+  EAVSR_REQUIRE(n > 0 && deform_groups > 0 && h > 0 && w > 0, "affine_offsets: empty tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  Strides4 ts{transform_strides[0], transform_strides[1], transform_strides[2], transform_strides[3]};
+  Strides4 rs{translation_strides[0], translation_strides[1], translation_strides[2], translation_strides[3]};
+  Strides4 ms{0, 0, 0, 0};
+  if (mask) ms = Strides4{mask_strides[0], mask_strides[1], mask_strides[2], mask_strides[3]};
+  const long long total = (long long)n * deform_groups * h * w;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dtype == EAVSR_F32)
+    affine_offsets_kernel<float><<<blocks, 256, 0, st>>>((const float*)transform, ts, (const float*)translation, rs,
+                                                         (const float*)mask_logits, ms, offset, mask, n,
+                                                         deform_groups, h, w);
+  else if (dtype == EAVSR_BF16)
+    affine_offsets_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)transform, ts, (const __nv_bfloat16*)translation, rs,
+        (const __nv_bfloat16*)mask_logits, ms, offset, mask, n, deform_groups, h, w);
+  else { set_error("affine_offsets: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("affine_offsets");
+}
+
+extern "C" int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1, const void* b1,
+                                         const void* w2, const void* b2, void* out, float* sums_workspace, int n,
+                                         int c, int h, int w, int reduction, int dtype, void* stream) {
+  EAVSR_REQUIRE(res && skip && w1 && b1 && w2 && b2 && out && sums_workspace, "ca_residual: null pointer");
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "ca_residual: empty tensor");
+  if (c != 64 || reduction != 16) {
+    set_error("ca_residual: only C=64, reduction=16 is fused (got C=%d, r=%d)", c, reduction);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  EAVSR_REQUIRE(al16(res) && al16(skip) && al16(out), "ca_residual: tensors must be 16-byte aligned dense NHWC");
+  EAVSR_REQUIRE(n <= 65535, "ca_residual: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = h * w;
+  cudaError_t e = cudaMemsetAsync(sums_workspace, 0, (size_t)n * c * sizeof(float), st);
+  if (e != cudaSuccess) { set_error("ca_residual: memset: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  dim3 g1(ceil_div(HW, CS_PIX), n);
+  int rc;
+  if (dtype == EAVSR_F32) {
+    channel_sum_kernel<float, 64><<<g1, CS_THREADS, 0, st>>>((const float*)res, sums_workspace, HW);
+    rc = check_launch("ca_residual(sum)");
+    if (rc) return rc;
+    const int chunks = HW * 64 / 4;
+    dim3 g2(min(ceil_div(chunks, 256 * 4), 148 * 8), n);
+    ca_scale_residual_kernel<float, 64, 4><<<g2, 256, 0, st>>>((const float*)res, (const float*)skip, sums_workspace,
+                                                             (const float*)w1, (const float*)b1, (const float*)w2,
+                                                             (const float*)b2, (float*)out, HW, 1.f / (float)HW, chunks);
+  } else if (dtype == EAVSR_BF16) {
+    using B = __nv_bfloat16;
+    channel_sum_kernel<B, 64><<<g1, CS_THREADS, 0, st>>>((const B*)res, sums_workspace, HW);
+    rc = check_launch("ca_residual(sum)");
+    if (rc) return rc;
+    const int chunks = HW * 64 / 8;
+    dim3 g2(min(ceil_div(chunks, 256 * 4), 148 * 8), n);
+    ca_scale_residual_kernel<B, 64, 4><<<g2, 256, 0, st>>>((const B*)res, (const B*)skip, sums_workspace, (const B*)w1,
+                                                         (const B*)b1, (const B*)w2, (const B*)b2, (B*)out, HW,
+                                                         1.f / (float)HW, chunks);
+  } else { set_error("ca_residual: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("ca_residual(scale)");
+}

@@ -153,6 +153,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
+    __nanosleep(64);   // polling warps must not steal issue slots from the warps they wait for
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }

@@ -193,7 +193,7 @@ dcn_fwd_tc_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
           const float px = (px_f[j] + (float)tj) + dx;
           const bool inside = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
           const float fy = floorf(py), fx = floorf(px);
-          const int y0 = (int)fy, x0 = (int)fx;
+          const int y0 = (int)fminf(fmaxf(fy, -2.f), 1.0e6f), x0 = (int)fminf(fmaxf(fx, -2.f), 1.0e6f);
           const float ly = py - fy, lx = px - fx;
           const bool vy0 = inside && y0 >= 0, vy1 = inside && y0 + 1 <= H - 1;
           const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= W - 1;
@@ -208,9 +208,9 @@ dcn_fwd_tc_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
           const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * CPI;
           const uint32_t sxo = (uint32_t)(cx1 - cx0) * CH, syo = (uint32_t)((cy1 - cy0) * W) * CH;
           RawVec<XT, CPI>::ld(xn + b00, raw[jj][0]);
-          RawVec<XT, CPI>::ld(xn + b00 + sxo, raw[jj][1]);
-          RawVec<XT, CPI>::ld(xn + b00 + syo, raw[jj][2]);
-          RawVec<XT, CPI>::ld(xn + b00 + syo + sxo, raw[jj][3]);
+          RawVec<XT, CPI>::ld(xn + (uint32_t)(b00 + sxo), raw[jj][1]);
+          RawVec<XT, CPI>::ld(xn + (uint32_t)(b00 + syo), raw[jj][2]);
+          RawVec<XT, CPI>::ld(xn + (uint32_t)(b00 + syo + sxo), raw[jj][3]);
         }
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {

@@ -197,25 +197,29 @@ dcn_fwd_ws_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
         const float m = so[(2 * DG + grp) * PLW + lr];
         const float py = (py_f[j] + (float)ti) + dy;
         const float px = (px_f[j] + (float)tj) + dx;
-        const bool inside = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
         const float fy = floorf(py), fx = floorf(px);
-        const int y0 = (int)fy, x0 = (int)fx;
         const float ly = py - fy, lx = px - fx;
-        const bool vy0 = inside && y0 >= 0, vy1 = inside && y0 + 1 <= H - 1;
-        const bool vx0 = x0 >= 0, vx1 = x0 + 1 <= W - 1;
-        const float hy = m * (1.f - ly), ly_m = m * ly;
-        wgt[pb][jj][0] = (vy0 && vx0) ? hy * (1.f - lx) : 0.f;
-        wgt[pb][jj][1] = (vy0 && vx1) ? hy * lx : 0.f;
-        wgt[pb][jj][2] = (vy1 && vx0) ? ly_m * (1.f - lx) : 0.f;
-        wgt[pb][jj][3] = (vy1 && vx1) ? ly_m * lx : 0.f;
+        // cell index, saturated so that wild / NaN offsets land on "all corners outside"
+        const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)H), x0 = (int)fminf(fmaxf(fx, -2.f), (float)W);
+        // separable weights with the mask folded into the row weights.  A row / column outside the
+        // image gets weight 0, which also implements DCNv2's "p <= -1 or p >= size -> 0" rule
+        // (exactly on p == -1 the only in-image corner has weight l == 0).
+        const float wy0 = ((unsigned)y0 < (unsigned)H) ? m * (1.f - ly) : 0.f;
+        const float wy1 = ((unsigned)(y0 + 1) < (unsigned)H) ? m * ly : 0.f;
+        const float wx0 = ((unsigned)x0 < (unsigned)W) ? (1.f - lx) : 0.f;
+        const float wx1 = ((unsigned)(x0 + 1) < (unsigned)W) ? lx : 0.f;
+        wgt[pb][jj][0] = wy0 * wx0;
+        wgt[pb][jj][1] = wy0 * wx1;
+        wgt[pb][jj][2] = wy1 * wx0;
+        wgt[pb][jj][3] = wy1 * wx1;
         const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
         const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
         const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * CPI;
         const uint32_t sxo = (uint32_t)(cx1 - cx0) * CH, syo = (uint32_t)((cy1 - cy0) * W) * CH;
         RawVec<XT, CPI>::ld(xn + b00, raw[pb][jj][0]);
-        RawVec<XT, CPI>::ld(xn + b00 + sxo, raw[pb][jj][1]);
-        RawVec<XT, CPI>::ld(xn + b00 + syo, raw[pb][jj][2]);
-        RawVec<XT, CPI>::ld(xn + b00 + syo + sxo, raw[pb][jj][3]);
+        RawVec<XT, CPI>::ld(xn + (uint32_t)(b00 + sxo), raw[pb][jj][1]);
+        RawVec<XT, CPI>::ld(xn + (uint32_t)(b00 + syo), raw[pb][jj][2]);
+        RawVec<XT, CPI>::ld(xn + (uint32_t)(b00 + syo + sxo), raw[pb][jj][3]);
       }
     };
 

@@ -156,9 +156,9 @@ flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* _
       a[u][2] = __shfl_sync(0xffffffffu, w10, src);
       a[u][3] = __shfl_sync(0xffffffffu, w11, src);
       RawVec<T, VEC>::ld(xn + b, raw[u][0]);              // dead pixels read element 0 with weight 0
-      RawVec<T, VEC>::ld(xn + b + sxo, raw[u][1]);
-      RawVec<T, VEC>::ld(xn + b + syo, raw[u][2]);
-      RawVec<T, VEC>::ld(xn + b + syo + sxo, raw[u][3]);
+      RawVec<T, VEC>::ld(xn + (uint32_t)(b + sxo), raw[u][1]);
+      RawVec<T, VEC>::ld(xn + (uint32_t)(b + syo), raw[u][2]);
+      RawVec<T, VEC>::ld(xn + (uint32_t)(b + syo + sxo), raw[u][3]);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {

@@ -23,7 +23,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import ModulatedDeformConv2d, flow_warp, flow_warp_nhw2, modulated_deform_conv2d
+from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, flow_warp, flow_warp_nhw2,
+                  fused_inference_ok, modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
 
@@ -48,7 +49,11 @@ class _RCABlock(nn.Module):
         self.ca = _CALayer(ch)
 
     def forward(self, x):
-        return self.ca(self.res(x)) + x
+        res = self.res(x)
+        du = self.ca.conv_du
+        if res.shape[1] == 64 and fused_inference_ok(res, x):    # reduce + MLP + scale + add: 2 kernels
+            return ca_residual(res, x, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16)
+        return self.ca(res) + x
 
 
 class _RCAGroup(nn.Module):
@@ -117,6 +122,9 @@ class _AdaptBase(nn.Module):
         self.translation_conv = nn.Conv2d(ch, n_trans, k, 1, k // 2)
 
     def _mix(self, x, ref):
+        if x.shape[1] == 64 and fused_inference_ok(x, ref):      # both grouped convs in one pass
+            return adapt_mix(x, ref, self.concat[0].weight, self.concat[0].bias, self.concat2[0].weight,
+                             self.concat2[0].bias, 0.2)
         return self.concat2(self.concat(torch.cat([x, ref], 1)))
 
 
@@ -128,8 +136,10 @@ class _AdaptBlock2_3x3(_AdaptBase):
 
     def forward(self, x, ref):
         f = self._mix(x, ref)
-        return _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), 1,
-                               self.regular_matrix)
+        T, t = self.transform_matrix_conv(f), self.translation_conv(f)
+        if fused_inference_ok(T, t):
+            return affine_offsets_mask(T, t, None, 1)[0]
+        return _affine_offsets(T.float(), t.float(), 1, self.regular_matrix)
 
 
 class _AdaptBlockOffset(_AdaptBase):
@@ -142,9 +152,11 @@ class _AdaptBlockOffset(_AdaptBase):
 
     def forward(self, x, ref):
         f = self._mix(x, ref)
-        off = _affine_offsets(self.transform_matrix_conv(f).float(), self.translation_conv(f).float(), self.D,
-                              self.regular_matrix)
-        return off, torch.sigmoid(self.mask_conv(f).float())
+        T, t, m = self.transform_matrix_conv(f), self.translation_conv(f), self.mask_conv(f)
+        if fused_inference_ok(T, t, m):
+            return affine_offsets_mask(T, t, m, self.D)
+        off = _affine_offsets(T.float(), t.float(), self.D, self.regular_matrix)
+        return off, torch.sigmoid(m.float())
 
 
 class _TransOffset(nn.Module):

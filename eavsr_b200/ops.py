@@ -34,6 +34,7 @@ from . import _lib as L
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "flow_warp", "flow_warp_nhw2",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
+    "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok",
 ]
 
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
@@ -368,3 +369,78 @@ def FunctionCorrelation(tenFirst, tenSecond):
 class ModuleCorrelation(nn.Module):
     def forward(self, tenFirst, tenSecond):
         return _FunctionCorrelation.apply(tenFirst, tenSecond)
+
+
+# ------------------------------------------------------------------------------------------
+# fused inference-only producers / consumers around the hot path (no autograd: the callers in
+# eavsr_b200.model use the PyTorch modules whenever a gradient is required)
+# ------------------------------------------------------------------------------------------
+def fused_inference_ok(*tensors) -> bool:
+    """True when the fused (non-differentiable) kernels may be used for these tensors."""
+    ts = [t for t in tensors if t is not None]
+    if not all(t.is_cuda for t in ts):
+        return False
+    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+        return False
+    return all(t.dtype in _DTYPES for t in ts)
+
+
+def adapt_mix(a, b, w1, b1, w2, b2, negative_slope: float = 0.2):
+    """``concat2(concat(cat[a, b]))`` of the reference's AdaptBlocks (models/networks.py:289-290,299):
+    depthwise 3x3 + LeakyReLU + grouped (2->1) 3x3 + LeakyReLU in one pass.  a, b: (n,64,h,w)."""
+    _require_cuda("adapt_mix", a, b, w1, b1, w2, b2)
+    lib = L.load()
+    n, c, h, w = a.shape
+    with torch.cuda.device(a.device):
+        ad = a.contiguous(memory_format=torch.channels_last)
+        bd = b.to(a.dtype).contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(ad)
+        dt = a.dtype
+        L.check(lib.eavsr_adapt_mix_forward(ad.data_ptr(), bd.data_ptr(), w1.to(dt).contiguous().data_ptr(),
+                                            b1.to(dt).contiguous().data_ptr(), w2.to(dt).contiguous().data_ptr(),
+                                            b2.to(dt).contiguous().data_ptr(), out.data_ptr(), n, c, h, w,
+                                            float(negative_slope), _dtype_code("adapt_mix", ad), _stream(ad)),
+                "adapt_mix")
+    return out
+
+
+def affine_offsets_mask(transform, translation, mask_logits, deform_groups: int):
+    """Per-group affine offset expansion ``T*R - R + t`` and ``sigmoid(mask_logits)``
+    (models/networks.py:302-313) -> fp32 NCHW (offset (n,18D,h,w), mask (n,9D,h,w) or None)."""
+    _require_cuda("affine_offsets_mask", transform, translation, mask_logits)
+    lib = L.load()
+    n, _, h, w = transform.shape
+    D = deform_groups
+    with torch.cuda.device(transform.device):
+        translation = translation.to(transform.dtype)
+        offset = torch.empty((n, 18 * D, h, w), dtype=torch.float32, device=transform.device)
+        mask = None
+        if mask_logits is not None:
+            mask_logits = mask_logits.to(transform.dtype)
+            mask = torch.empty((n, 9 * D, h, w), dtype=torch.float32, device=transform.device)
+        L.check(lib.eavsr_affine_offsets_forward(
+            transform.data_ptr(), _strides(transform), translation.data_ptr(), _strides(translation),
+            _ptr(mask_logits), _strides(mask_logits) if mask_logits is not None else None, offset.data_ptr(),
+            _ptr(mask), n, D, h, w, _dtype_code("affine_offsets_mask", transform), _stream(transform)),
+            "affine_offsets")
+    return offset, mask
+
+
+def ca_residual(res, skip, w1, b1, w2, b2, reduction: int = 16):
+    """``res * CALayer(res) + skip`` of the reference's RCABlock (models/networks.py:449-465) with two
+    kernels (channel sums; MLP + scale + residual).  res, skip: (n,64,h,w)."""
+    _require_cuda("ca_residual", res, skip, w1, b1, w2, b2)
+    lib = L.load()
+    n, c, h, w = res.shape
+    with torch.cuda.device(res.device):
+        rd = res.contiguous(memory_format=torch.channels_last)
+        sd = skip.to(res.dtype).contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(rd)
+        sums = torch.empty((n, c), dtype=torch.float32, device=res.device)
+        dt = res.dtype
+        L.check(lib.eavsr_ca_residual_forward(rd.data_ptr(), sd.data_ptr(), w1.to(dt).contiguous().data_ptr(),
+                                              b1.to(dt).contiguous().data_ptr(), w2.to(dt).contiguous().data_ptr(),
+                                              b2.to(dt).contiguous().data_ptr(), out.data_ptr(), sums.data_ptr(),
+                                              n, c, h, w, reduction, _dtype_code("ca_residual", rd), _stream(rd)),
+                "ca_residual")
+    return out

@@ -117,6 +117,32 @@ int eavsr_correlation_forward(const void* first, const void* second, void* out, 
 int eavsr_correlation_backward(const void* first, const void* second, const void* gout, void* gfirst,
                                void* gsecond, int n, int c, int h, int w, int dtype, void* stream);
 
+/* ---- fused producers / consumers around the hot path (inference) -----------------------------
+ * The offset/mask generator that feeds the DCN and the channel
+ * attention of the residual backbone (row f3), as single passes instead of PyTorch glue.
+ *
+ * adapt_mix: concat2(concat(cat[a, b])) of AdaptBlockOffset / AdaptBlock2_3x3
+ *   (models/networks.py:289-290,299 and :327-328,334): depthwise 3x3 on the 128 concatenated
+ *   channels + LeakyReLU, then grouped 3x3 (groups=64, 2 -> 1) + LeakyReLU.
+ *   a, b, out: (n,64,h,w) dense NHWC;  w1 (128,1,3,3), b1 (128), w2 (64,2,3,3), b2 (64); all `dtype`. */
+int eavsr_adapt_mix_forward(const void* a, const void* b, const void* w1, const void* b1, const void* w2,
+                            const void* b2, void* out, int n, int c, int h, int w, float negative_slope,
+                            int dtype, void* stream);
+/* affine_offsets: offset = T*R - R + t per deformable group and mask = sigmoid(logits)
+ *   (models/networks.py:302-313).  transform (n,4D,h,w), translation (n,2D,h,w), mask_logits (n,9D,h,w)
+ *   are `dtype` with arbitrary strides; offset (n,18D,h,w) / mask (n,9D,h,w) are fp32 NCHW contiguous,
+ *   the layout eavsr_dcn_forward consumes.  mask (and mask_logits) may be NULL. */
+int eavsr_affine_offsets_forward(const void* transform, const int64_t transform_strides[4],
+                                 const void* translation, const int64_t translation_strides[4],
+                                 const void* mask_logits, const int64_t mask_strides[4], float* offset, float* mask,
+                                 int n, int deform_groups, int h, int w, int dtype, void* stream);
+/* ca_residual: out = res * sigmoid(W2 relu(W1 mean_hw(res) + b1) + b2) + skip  (CALayer + residual of
+ *   RCABlock, models/networks.py:449-465).  res, skip, out: (n,64,h,w) dense NHWC; w1 (4,64), w2 (64,4);
+ *   sums_workspace: n*64 floats. */
+int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1, const void* b1, const void* w2,
+                              const void* b2, void* out, float* sums_workspace, int n, int c, int h, int w,
+                              int reduction, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

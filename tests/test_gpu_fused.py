@@ -1,0 +1,92 @@
+"""GPU parity of the fused producer/consumer kernels against the PyTorch modules they replace
+(the reference's own definitions: nn.Conv2d groups / LeakyReLU, matmul expansion, CALayer)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import eavsr_b200.model as M
+from eavsr_b200 import ops
+from oracle import alignment as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("shape", [(1, 17, 23), (2, 8, 16), (1, 67, 120), (1, 5, 3)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 3e-2)])
+def test_adapt_mix_matches_grouped_convs(cuda, shape, dtype, tol):
+    n, h, w = shape
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(n, 64, h, w, generator=g), torch.randn(n, 64, h, w, generator=g)
+    w1, b1 = torch.randn(128, 1, 3, 3, generator=g) * 0.3, torch.randn(128, generator=g) * 0.1
+    w2, b2 = torch.randn(64, 2, 3, 3, generator=g) * 0.3, torch.randn(64, generator=g) * 0.1
+    cast = lambda t: t.to(dtype).double()        # noqa: E731  reference in fp64 on the dtype-rounded inputs
+    y = F.leaky_relu(F.conv2d(torch.cat([cast(a), cast(b)], 1), cast(w1), cast(b1), padding=1, groups=128), 0.2)
+    ref = F.leaky_relu(F.conv2d(y, cast(w2), cast(b2), padding=1, groups=64), 0.2)
+    out = ops.adapt_mix(_cl(a.to(cuda, dtype)), _cl(b.to(cuda, dtype)), w1.to(cuda, dtype), b1.to(cuda, dtype),
+                        w2.to(cuda, dtype), b2.to(cuda, dtype), 0.2)
+    assert out.shape == ref.shape and out.dtype == dtype
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("D", [1, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cl", [True, False])
+def test_affine_offsets_mask_matches_oracle(cuda, D, dtype, cl):
+    g = torch.Generator().manual_seed(2)
+    n, h, w = 2, 13, 19
+    T = torch.randn(n, 4 * D, h, w, generator=g).to(dtype)
+    t = torch.randn(n, 2 * D, h, w, generator=g).to(dtype)
+    m = torch.randn(n, 9 * D, h, w, generator=g).to(dtype)
+    ref_off = O.affine_offsets(T.double(), t.double(), D)
+    ref_mask = torch.sigmoid(m.double())
+    f = _cl if cl else (lambda z: z)
+    off, mask = ops.affine_offsets_mask(f(T.to(cuda)), f(t.to(cuda)), f(m.to(cuda)), D)
+    assert off.dtype == torch.float32 and off.is_contiguous() and mask.is_contiguous()
+    assert (off.double().cpu() - ref_off).abs().max() < 1e-5
+    assert (mask.double().cpu() - ref_mask).abs().max() < 1e-5
+    off2, none = ops.affine_offsets_mask(f(T.to(cuda)), f(t.to(cuda)), None, D)
+    assert none is None and torch.equal(off2, off)
+
+
+@pytest.mark.parametrize("shape", [(1, 20, 30), (3, 7, 9), (1, 67, 120)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_ca_residual_matches_rcablock_tail(cuda, shape, dtype, tol):
+    n, h, w = shape
+    g = torch.Generator().manual_seed(3)
+    res, skip = torch.randn(n, 64, h, w, generator=g), torch.randn(n, 64, h, w, generator=g)
+    ca = M._CALayer(64).double()
+    for p in ca.parameters():
+        p.data = (torch.randn(p.shape, generator=g) * 0.5).to(dtype).double()
+    ref = ca(res.to(dtype).double()) + skip.to(dtype).double()
+    du = ca.conv_du
+    out = ops.ca_residual(_cl(res.to(cuda, dtype)), _cl(skip.to(cuda, dtype)), du[0].weight.to(cuda, dtype),
+                          du[0].bias.to(cuda, dtype), du[2].weight.to(cuda, dtype), du[2].bias.to(cuda, dtype), 16)
+    assert (out.double().cpu() - ref).abs().max() < tol * max(1.0, ref.abs().max().item())
+
+
+def test_model_uses_fused_path_only_without_grad(cuda):
+    blk = M._RCABlock(64).to(cuda)
+    x = _cl(torch.randn(1, 64, 12, 12, device=cuda))
+    from eavsr_b200 import _lib
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        y_fused = blk(x)
+    assert _lib.launch_count() - n0 == 2
+    n1 = _lib.launch_count()
+    y_torch = blk(x.requires_grad_())
+    assert _lib.launch_count() == n1 and y_torch.requires_grad
+    assert (y_fused - y_torch.detach()).abs().max() < 1e-4
