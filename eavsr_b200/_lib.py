@@ -47,9 +47,10 @@ _SIGNATURES = {
     "eavsr_correlation_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_int, c_int, c_void_p]),
     "eavsr_adapt_mix_forward": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_float, c_int, c_void_p]),
-    "eavsr_affine_offsets_forward": (c_int, [c_void_p, _P64, c_void_p, _P64, c_void_p, _P64, _PF, _PF] + [c_int] * 5 +
-                                     [c_void_p]),
-    "eavsr_ca_residual_forward": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_void_p]),
+    "eavsr_affine_offsets_forward": (c_int, [c_void_p, _P64, c_void_p, _P64, c_void_p, _P64, c_void_p, c_void_p,
+                                             c_void_p, _PF, _PF] + [c_int] * 5 + [c_void_p]),
+    "eavsr_ca_residual_forward": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_void_p]),
+    "eavsr_bias_act_forward": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_float, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

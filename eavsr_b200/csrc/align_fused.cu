@@ -138,7 +138,8 @@ adapt_mix_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __re
 template <typename T>
 __global__ void __launch_bounds__(256)
 affine_offsets_kernel(const T* __restrict__ tm, Strides4 ts, const T* __restrict__ tr, Strides4 rs,
-                      const T* __restrict__ ml, Strides4 ms, float* __restrict__ offset,
+                      const T* __restrict__ ml, Strides4 ms, const T* __restrict__ tm_bias,
+                      const T* __restrict__ tr_bias, const T* __restrict__ ml_bias, float* __restrict__ offset,
                       float* __restrict__ mask, int N, int D, int H, int W) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W;
@@ -149,8 +150,13 @@ affine_offsets_kernel(const T* __restrict__ tm, Strides4 ts, const T* __restrict
   const int y = pix / W, x = pix % W;
   const T* tp = tm + n * ts.n + y * ts.h + x * ts.w + (long long)(g * 4) * ts.c;
   const T* rp = tr + n * rs.n + y * rs.h + x * rs.w + (long long)(g * 2) * rs.c;
-  const float a = to_f32<T>(tp[0]), b = to_f32<T>(tp[ts.c]), c = to_f32<T>(tp[2 * ts.c]), d = to_f32<T>(tp[3 * ts.c]);
-  const float t0 = to_f32<T>(rp[0]), t1 = to_f32<T>(rp[rs.c]);
+  float a = to_f32<T>(tp[0]), b = to_f32<T>(tp[ts.c]), c = to_f32<T>(tp[2 * ts.c]), d = to_f32<T>(tp[3 * ts.c]);
+  float t0 = to_f32<T>(rp[0]), t1 = to_f32<T>(rp[rs.c]);
+  if (tm_bias) {   // biases of the bias-free convolutions that produced T / t / logits
+    a += to_f32<T>(tm_bias[g * 4]); b += to_f32<T>(tm_bias[g * 4 + 1]);
+    c += to_f32<T>(tm_bias[g * 4 + 2]); d += to_f32<T>(tm_bias[g * 4 + 3]);
+  }
+  if (tr_bias) { t0 += to_f32<T>(tr_bias[g * 2]); t1 += to_f32<T>(tr_bias[g * 2 + 1]); }
   float* op = offset + ((size_t)(n * D + g) * 18) * HW + pix;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -162,7 +168,10 @@ affine_offsets_kernel(const T* __restrict__ tm, Strides4 ts, const T* __restrict
     const T* mp = ml + n * ms.n + y * ms.h + x * ms.w + (long long)(g * 9) * ms.c;
     float* mo = mask + ((size_t)(n * D + g) * 9) * HW + pix;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) mo[(size_t)k * HW] = 1.f / (1.f + __expf(-to_f32<T>(mp[k * ms.c])));
+    for (int k = 0; k < 9; ++k) {
+      const float lg = to_f32<T>(mp[k * ms.c]) + (ml_bias ? to_f32<T>(ml_bias[g * 9 + k]) : 0.f);
+      mo[(size_t)k * HW] = 1.f / (1.f + __expf(-lg));
+    }
   }
 }
 
@@ -208,15 +217,19 @@ template <typename T, int C, int R>
 __global__ void __launch_bounds__(256)
 ca_scale_residual_kernel(const T* __restrict__ res, const T* __restrict__ skip, const float* __restrict__ sums,
                          const T* __restrict__ w1, const T* __restrict__ b1, const T* __restrict__ w2,
-                         const T* __restrict__ b2, T* __restrict__ out, int HW, float inv_hw, int chunks_per_img) {
+                         const T* __restrict__ b2, const T* __restrict__ res_bias, T* __restrict__ out, int HW,
+                         float inv_hw, int chunks_per_img) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int CPP = C / VEC;
   __shared__ float hid[R];
   __shared__ float scale[C];
+  __shared__ float rb[C];                       // bias of the conv that produced `res` (0 if none)
   const int n = blockIdx.y;
+  if (threadIdx.x < C) rb[threadIdx.x] = res_bias ? to_f32<T>(res_bias[threadIdx.x]) : 0.f;
+  __syncthreads();
   if (threadIdx.x < R) {
     float a = to_f32<T>(b1[threadIdx.x]);
-    for (int i = 0; i < C; ++i) a += to_f32<T>(w1[threadIdx.x * C + i]) * (sums[n * C + i] * inv_hw);
+    for (int i = 0; i < C; ++i) a += to_f32<T>(w1[threadIdx.x * C + i]) * (sums[n * C + i] * inv_hw + rb[i]);
     hid[threadIdx.x] = fmaxf(a, 0.f);
   }
   __syncthreads();
@@ -234,8 +247,31 @@ ca_scale_residual_kernel(const T* __restrict__ res, const T* __restrict__ skip, 
     VecLoad<T, VEC>::ld(res + base + (size_t)i * VEC, r);
     VecLoad<T, VEC>::ld(skip + base + (size_t)i * VEC, s);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) o[e] = r[e] * scale[ch * VEC + e] + s[e];
+    for (int e = 0; e < VEC; ++e) o[e] = (r[e] + rb[ch * VEC + e]) * scale[ch * VEC + e] + s[e];
     VecLoad<T, VEC>::st(out + base + (size_t)i * VEC, o);
+  }
+}
+
+// x[p][c] = act(x[p][c] + bias[c]) in place on a dense NHWC tensor; act = LeakyReLU(slope)
+// (slope 1 = identity, 0 = ReLU).  PyTorch adds a cuDNN convolution's bias with a broadcast
+// TensorIterator kernel (not vectorised for channels_last: 17.6 us on a 64x272x480 bf16 map) and the
+// activation with another launch; this is one 16-byte-vectorised pass.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(T* __restrict__ x, const T* __restrict__ bias, int C, long long nchunks, float slope) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int cpp = C / VEC;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nchunks; i += (long long)gridDim.x * 256) {
+    const int ch = (int)(i % cpp);
+    float v[VEC], b[VEC];
+    VecLoad<T, VEC>::ld(x + i * VEC, v);
+    VecLoad<T, VEC>::ld(bias + ch * VEC, b);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float t = v[e] + b[e];
+      v[e] = t > 0.f ? t : t * slope;
+    }
+    VecLoad<T, VEC>::st(x + i * VEC, v);
   }
 }
 
@@ -279,9 +315,10 @@ extern "C" int eavsr_adapt_mix_forward(const void* a, const void* b, const void*
 
 extern "C" int eavsr_affine_offsets_forward(const void* transform, const int64_t transform_strides[4],
                                             const void* translation, const int64_t translation_strides[4],
-                                            const void* mask_logits, const int64_t mask_strides[4], float* offset,
-                                            float* mask, int n, int deform_groups, int h, int w, int dtype,
-                                            void* stream) {
+                                            const void* mask_logits, const int64_t mask_strides[4],
+                                            const void* transform_bias, const void* translation_bias,
+                                            const void* mask_bias, float* offset, float* mask, int n,
+                                            int deform_groups, int h, int w, int dtype, void* stream) {
   EAVSR_REQUIRE(transform && translation && offset && transform_strides && translation_strides,
                 "affine_offsets: null pointer");
   EAVSR_REQUIRE(!mask || (mask_logits && mask_strides), "affine_offsets: mask output without logits");
@@ -295,19 +332,22 @@ extern "C" int eavsr_affine_offsets_forward(const void* transform, const int64_t
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (dtype == EAVSR_F32)
     affine_offsets_kernel<float><<<blocks, 256, 0, st>>>((const float*)transform, ts, (const float*)translation, rs,
-                                                         (const float*)mask_logits, ms, offset, mask, n,
-                                                         deform_groups, h, w);
+                                                         (const float*)mask_logits, ms, (const float*)transform_bias,
+                                                         (const float*)translation_bias, (const float*)mask_bias,
+                                                         offset, mask, n, deform_groups, h, w);
   else if (dtype == EAVSR_BF16)
     affine_offsets_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         (const __nv_bfloat16*)transform, ts, (const __nv_bfloat16*)translation, rs,
-        (const __nv_bfloat16*)mask_logits, ms, offset, mask, n, deform_groups, h, w);
+        (const __nv_bfloat16*)mask_logits, ms, (const __nv_bfloat16*)transform_bias,
+        (const __nv_bfloat16*)translation_bias, (const __nv_bfloat16*)mask_bias, offset, mask, n, deform_groups, h, w);
   else { set_error("affine_offsets: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
   return check_launch("affine_offsets");
 }
 
 extern "C" int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1, const void* b1,
-                                         const void* w2, const void* b2, void* out, float* sums_workspace, int n,
-                                         int c, int h, int w, int reduction, int dtype, void* stream) {
+                                         const void* w2, const void* b2, const void* res_bias, void* out,
+                                         float* sums_workspace, int n, int c, int h, int w, int reduction, int dtype,
+                                         void* stream) {
   EAVSR_REQUIRE(res && skip && w1 && b1 && w2 && b2 && out && sums_workspace, "ca_residual: null pointer");
   EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "ca_residual: empty tensor");
   if (c != 64 || reduction != 16) {
@@ -330,7 +370,8 @@ extern "C" int eavsr_ca_residual_forward(const void* res, const void* skip, cons
     dim3 g2(min(ceil_div(chunks, 256 * 4), 148 * 8), n);
     ca_scale_residual_kernel<float, 64, 4><<<g2, 256, 0, st>>>((const float*)res, (const float*)skip, sums_workspace,
                                                              (const float*)w1, (const float*)b1, (const float*)w2,
-                                                             (const float*)b2, (float*)out, HW, 1.f / (float)HW, chunks);
+                                                             (const float*)b2, (const float*)res_bias, (float*)out, HW,
+                                                             1.f / (float)HW, chunks);
   } else if (dtype == EAVSR_BF16) {
     using B = __nv_bfloat16;
     channel_sum_kernel<B, 64><<<g1, CS_THREADS, 0, st>>>((const B*)res, sums_workspace, HW);
@@ -339,8 +380,30 @@ extern "C" int eavsr_ca_residual_forward(const void* res, const void* skip, cons
     const int chunks = HW * 64 / 8;
     dim3 g2(min(ceil_div(chunks, 256 * 4), 148 * 8), n);
     ca_scale_residual_kernel<B, 64, 4><<<g2, 256, 0, st>>>((const B*)res, (const B*)skip, sums_workspace, (const B*)w1,
-                                                         (const B*)b1, (const B*)w2, (const B*)b2, (B*)out, HW,
-                                                         1.f / (float)HW, chunks);
+                                                         (const B*)b1, (const B*)w2, (const B*)b2, (const B*)res_bias,
+                                                         (B*)out, HW, 1.f / (float)HW, chunks);
   } else { set_error("ca_residual: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
   return check_launch("ca_residual(scale)");
+}
+
+extern "C" int eavsr_bias_act_forward(void* x, const void* bias, int c, long long pixels, float negative_slope,
+                                      int dtype, void* stream) {
+  EAVSR_REQUIRE(x && bias, "bias_act: null pointer");
+  EAVSR_REQUIRE(c > 0 && pixels > 0, "bias_act: empty tensor");
+  const int vec = dtype == EAVSR_F32 ? 4 : 8;
+  if (c % vec != 0 || !al16(x) || !al16(bias)) {
+    set_error("bias_act: needs C %% %d == 0 and 16-byte aligned dense NHWC data (C=%d)", vec, c);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nchunks = pixels * (c / vec);
+  long long blocks = (nchunks + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == EAVSR_F32)
+    bias_act_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)x, (const float*)bias, c, nchunks, negative_slope);
+  else if (dtype == EAVSR_BF16)
+    bias_act_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)bias, c,
+                                                                    nchunks, negative_slope);
+  else { set_error("bias_act: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("bias_act");
 }

@@ -100,6 +100,131 @@ corr_fwd(const T* __restrict__ f1, const T* __restrict__ f2, T* __restrict__ out
     }
 }
 
+// ---- fp32 fast path: cp.async double-buffered staging (zero-fill outside the image) --------------
+// The first version staged with scalar loads + stores between two __syncthreads() and reached 7 % of
+// HBM on the 30x32x80x128 level (382 us): the FMA work (81*C per pixel, ~25 us at the FP32 pipe's
+// peak) was serialised behind the staging.  Here channel chunk k+1 streams into the second buffer
+// with 16-byte cp.async (src-size 0 => zero fill for the padding) while chunk k is consumed.
+struct CorrStage {
+  float s1[CKC][TH][TW];
+  float s2[CKC][HH][HW_];
+};
+
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_4_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(CORR_THREADS, 2)
+corr_fwd_f32(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, int C, int H,
+             int W) {
+  extern __shared__ __align__(16) uint8_t corr_smem[];
+  CorrStage* st = reinterpret_cast<CorrStage*>(corr_smem);
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const int tid = threadIdx.x;
+  const int tq = tid & 7, ty = (tid >> 3) & 7, dgrp = tid >> 6;
+  const size_t plane = (size_t)H * W;
+  const float* f1n = f1 + (size_t)n * C * plane;
+  const float* f2n = f2 + (size_t)n * C * plane;
+
+  auto stage_in = [&](int c0, int buf) {
+    CorrStage& S = st[buf];
+    if (VEC4) {
+      for (int i = tid; i < CKC * TH * (TW / 4); i += CORR_THREADS) {
+        const int xx = (i % (TW / 4)) * 4, yy = (i / (TW / 4)) % TH, cc = i / ((TW / 4) * TH);
+        const int gy = y0 + yy, gx = x0 + xx, gc = c0 + cc;
+        const bool ok = gc < C && gy < H && gx < W;
+        cp_async_16_zfill(smem_u32(&S.s1[cc][yy][xx]), ok ? f1n + (size_t)gc * plane + (size_t)gy * W + gx : f1n, ok);
+      }
+      for (int i = tid; i < CKC * HH * (HW_ / 4); i += CORR_THREADS) {
+        const int xx = (i % (HW_ / 4)) * 4, yy = (i / (HW_ / 4)) % HH, cc = i / ((HW_ / 4) * HH);
+        const int gy = y0 + yy - D, gx = x0 + xx - D, gc = c0 + cc;
+        const bool ok = gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        cp_async_16_zfill(smem_u32(&S.s2[cc][yy][xx]), ok ? f2n + (size_t)gc * plane + (size_t)gy * W + gx : f2n, ok);
+      }
+    } else {
+      for (int i = tid; i < CKC * TH * TW; i += CORR_THREADS) {
+        const int xx = i % TW, yy = (i / TW) % TH, cc = i / (TW * TH);
+        const int gy = y0 + yy, gx = x0 + xx, gc = c0 + cc;
+        const bool ok = gc < C && gy < H && gx < W;
+        cp_async_4_zfill(smem_u32(&S.s1[cc][yy][xx]), ok ? f1n + (size_t)gc * plane + (size_t)gy * W + gx : f1n, ok);
+      }
+      for (int i = tid; i < CKC * HH * HW_; i += CORR_THREADS) {
+        const int xx = i % HW_, yy = (i / HW_) % HH, cc = i / (HW_ * HH);
+        const int gy = y0 + yy - D, gx = x0 + xx - D, gc = c0 + cc;
+        const bool ok = gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        cp_async_4_zfill(smem_u32(&S.s2[cc][yy][xx]), ok ? f2n + (size_t)gc * plane + (size_t)gy * W + gx : f2n, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+  float acc[3][ND][4];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < ND; ++b)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[a][b][p] = 0.f;
+
+  const int nchunks = (C + CKC - 1) / CKC;
+  stage_in(0, 0);
+  for (int k = 0; k < nchunks; ++k) {
+    if (k + 1 < nchunks) {
+      stage_in((k + 1) * CKC, (k + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const CorrStage& S = st[k & 1];
+#pragma unroll 2
+    for (int cc = 0; cc < CKC; ++cc) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&S.s1[cc][ty][4 * tq]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int dyi = 0; dyi < 3; ++dyi) {
+        const float* row = &S.s2[cc][ty + dgrp * 3 + dyi][4 * tq];
+        const float4 b0 = *reinterpret_cast<const float4*>(row);
+        const float4 b1 = *reinterpret_cast<const float4*>(row + 4);
+        const float4 b2 = *reinterpret_cast<const float4*>(row + 8);
+        const float b[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+        for (int dxi = 0; dxi < ND; ++dxi)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) acc[dyi][dxi][p] += a[p] * b[p + dxi];
+      }
+    }
+    __syncthreads();   // everyone is done with buffer k&1 before chunk k+2 streams into it
+  }
+
+  const int gy = y0 + ty, gx = x0 + 4 * tq;
+  if (gy >= H || gx >= W) return;
+  const float inv = 1.f / (float)C;
+  float* on = out + (size_t)n * (ND * ND) * plane + (size_t)gy * W + gx;
+#pragma unroll
+  for (int dyi = 0; dyi < 3; ++dyi)
+#pragma unroll
+    for (int dxi = 0; dxi < ND; ++dxi) {
+      const int kk = (dgrp * 3 + dyi) * ND + dxi;
+      float* op = on + (size_t)kk * plane;
+      if (VEC4) {
+        *reinterpret_cast<float4*>(op) = make_float4(acc[dyi][dxi][0] * inv, acc[dyi][dxi][1] * inv,
+                                                     acc[dyi][dxi][2] * inv, acc[dyi][dxi][3] * inv);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (gx + p < W) op[p] = acc[dyi][dxi][p] * inv;
+      }
+    }
+}
+
 // Backward, one thread per input-gradient element; reads are coalesced along x and hit L1/L2.
 // gfirst[n,c,y,x]  = 1/C sum_k gout[n,k,y,x]       * second[n,c,y+dy,x+dx]
 // gsecond[n,c,y,x] = 1/C sum_k gout[n,k,y-dy,x-dx] * first[n,c,y-dy,x-dx]
@@ -134,6 +259,18 @@ corr_bwd(const T* __restrict__ other, const T* __restrict__ gout, T* __restrict_
 template <typename T>
 int corr_forward_t(const void* f1, const void* f2, void* out, int n, int c, int h, int w, cudaStream_t st) {
   dim3 grid(ceil_div(w, TW), ceil_div(h, TH), n);
+  if (sizeof(T) == 4) {
+    const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(f2) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    const int smem = 2 * (int)sizeof(CorrStage);
+    auto kv = corr_fwd_f32<true>;
+    auto ks = corr_fwd_f32<false>;
+    auto k = vec ? kv : ks;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("correlation_forward: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+    k<<<grid, CORR_THREADS, smem, st>>>((const float*)f1, (const float*)f2, (float*)out, c, h, w);
+    return check_launch("correlation_forward");
+  }
   corr_fwd<T><<<grid, CORR_THREADS, 0, st>>>((const T*)f1, (const T*)f2, (T*)out, c, h, w);
   return check_launch("correlation_forward");
 }

@@ -23,8 +23,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, flow_warp, flow_warp_nhw2,
-                  fused_inference_ok, modulated_deform_conv2d)
+from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, conv2d_bias_act, flow_warp,
+                  flow_warp_nhw2, fused_inference_ok, modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
 
@@ -49,11 +49,15 @@ class _RCABlock(nn.Module):
         self.ca = _CALayer(ch)
 
     def forward(self, x):
-        res = self.res(x)
         du = self.ca.conv_du
-        if res.shape[1] == 64 and fused_inference_ok(res, x):    # reduce + MLP + scale + add: 2 kernels
-            return ca_residual(res, x, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16)
-        return self.ca(res) + x
+        if x.shape[1] == 64 and fused_inference_ok(x, self.res[0].weight):
+            # conv+bias+ReLU epilogue in one pass, second conv bias-free (its bias is folded into the
+            # channel-attention kernels), then reduce + MLP + scale + residual add in 2 kernels
+            h = conv2d_bias_act(self.res[0], x, 0.0)
+            c2 = self.res[2]
+            res = F.conv2d(h, c2.weight, None, c2.stride, c2.padding)
+            return ca_residual(res, x, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16, res_bias=c2.bias)
+        return self.ca(self.res(x)) + x
 
 
 class _RCAGroup(nn.Module):
@@ -62,7 +66,10 @@ class _RCAGroup(nn.Module):
         self.rg = nn.Sequential(*[_RCABlock(ch) for _ in range(nb)], nn.Conv2d(ch, ch, 3, 1, 1))
 
     def forward(self, x):
-        return self.rg(x) + x
+        y = x
+        for blk in self.rg[:-1]:
+            y = blk(y)
+        return conv2d_bias_act(self.rg[-1], y, 1.0) + x
 
 
 class _ResidualStack(nn.Module):
@@ -73,7 +80,7 @@ class _ResidualStack(nn.Module):
         self.main = nn.Sequential(nn.Conv2d(cin, ch, 3, 1, 1), nn.LeakyReLU(0.1, inplace=True), _RCAGroup(ch, nb))
 
     def forward(self, x):
-        return self.main(x)
+        return self.main[2](conv2d_bias_act(self.main[0], x, 0.1))
 
 
 class _Encoder(nn.Module):
@@ -94,7 +101,11 @@ class _Encoder(nn.Module):
         self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
 
     def forward(self, x):
-        return self.tail(self.model((x - self.mean) / self.std))
+        x = (x - self.mean) / self.std
+        convs = [m for m in self.model if isinstance(m, nn.Conv2d)]
+        for i, conv in enumerate(convs):
+            x = conv2d_bias_act(conv, x, 0.0 if i + 1 < len(convs) else 1.0)   # no ReLU after conv3_1
+        return conv2d_bias_act(self.tail, x, 1.0)
 
 
 _R = ((-1., -1., -1., 0., 0., 0., 1., 1., 1.), (-1., 0., 1., -1., 0., 1., -1., 0., 1.))
@@ -136,9 +147,12 @@ class _AdaptBlock2_3x3(_AdaptBase):
 
     def forward(self, x, ref):
         f = self._mix(x, ref)
+        if fused_inference_ok(f, self.transform_matrix_conv.weight):
+            ct, cr = self.transform_matrix_conv, self.translation_conv      # bias-free; biases added in-kernel
+            T = F.conv2d(f, ct.weight, None, 1, ct.padding)
+            t = F.conv2d(f, cr.weight, None, 1, cr.padding)
+            return affine_offsets_mask(T, t, None, 1, ct.bias, cr.bias)[0]
         T, t = self.transform_matrix_conv(f), self.translation_conv(f)
-        if fused_inference_ok(T, t):
-            return affine_offsets_mask(T, t, None, 1)[0]
         return _affine_offsets(T.float(), t.float(), 1, self.regular_matrix)
 
 
@@ -152,9 +166,13 @@ class _AdaptBlockOffset(_AdaptBase):
 
     def forward(self, x, ref):
         f = self._mix(x, ref)
+        if fused_inference_ok(f, self.mask_conv.weight):
+            ct, cr, cm = self.transform_matrix_conv, self.translation_conv, self.mask_conv
+            T = F.conv2d(f, ct.weight, None, 1, ct.padding)
+            t = F.conv2d(f, cr.weight, None, 1, cr.padding)
+            m = F.conv2d(f, cm.weight, None, 1, cm.padding)
+            return affine_offsets_mask(T, t, m, self.D, ct.bias, cr.bias, cm.bias)
         T, t, m = self.transform_matrix_conv(f), self.translation_conv(f), self.mask_conv(f)
-        if fused_inference_ok(T, t, m):
-            return affine_offsets_mask(T, t, m, self.D)
         off = _affine_offsets(T.float(), t.float(), self.D, self.regular_matrix)
         return off, torch.sigmoid(m.float())
 
@@ -213,8 +231,7 @@ class _ConvModule(nn.Module):
         self.activate = nn.ReLU(inplace=True) if act else None
 
     def forward(self, x):
-        x = self.conv(x)
-        return self.activate(x) if self.activate is not None else x
+        return conv2d_bias_act(self.conv, x, 0.0 if self.activate is not None else 1.0)
 
 
 class _SPyNetLevel(nn.Module):
@@ -330,7 +347,7 @@ class EAVSRP(nn.Module):
                     cond2 = align(pyr(idx + 2 * step), pyr(idx), outs[-2], flow2)
                 else:
                     cond2 = torch.zeros_like(cond1)
-                prop = fuse(torch.cat([cond1, cur, cond2], 1))
+                prop = conv2d_bias_act(fuse, torch.cat([cond1, cur, cond2], 1), 1.0)
                 prev_flow = flow1
             x = torch.cat([cur] + [feats[k][idx] for k in others] + [prop], 1)
             prop = prop + body(x)
@@ -343,10 +360,11 @@ class EAVSRP(nn.Module):
         for i in range(lrs.shape[1]):
             x = torch.cat([feats["spatial"][i]] + [feats[b][i] for b in _BRANCHES], 1)
             x = self.reconstruction(x)
-            x = F.leaky_relu(self.upsample1(x), 0.1)
+            # LeakyReLU commutes with PixelShuffle: fold it into the conv epilogue
+            x = self.upsample1[1](conv2d_bias_act(self.upsample1[0], x, 0.1))
             if self.scale == 4:
-                x = F.leaky_relu(self.upsample2(x), 0.1)
-            x = F.leaky_relu(self.conv_hr(x), 0.1)
+                x = self.upsample2[1](conv2d_bias_act(self.upsample2[0], x, 0.1))
+            x = conv2d_bias_act(self.conv_hr, x, 0.1)
             # the image-domain tail is fp32: residual (small) + bilinear base (the [0,1] frame itself)
             base = F.interpolate(lrs[:, i].float(), scale_factor=self.scale, mode="bilinear", align_corners=False)
             outs.append(self.conv_last(x).float() + base)

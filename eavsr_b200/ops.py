@@ -34,7 +34,7 @@ from . import _lib as L
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "flow_warp", "flow_warp_nhw2",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
-    "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok",
+    "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
 ]
 
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
@@ -375,6 +375,10 @@ class ModuleCorrelation(nn.Module):
 # fused inference-only producers / consumers around the hot path (no autograd: the callers in
 # eavsr_b200.model use the PyTorch modules whenever a gradient is required)
 # ------------------------------------------------------------------------------------------
+def _b(bias, like):
+    return None if bias is None else bias.detach().to(like.dtype).contiguous()
+
+
 def fused_inference_ok(*tensors) -> bool:
     """True when the fused (non-differentiable) kernels may be used for these tensors."""
     ts = [t for t in tensors if t is not None]
@@ -404,9 +408,11 @@ def adapt_mix(a, b, w1, b1, w2, b2, negative_slope: float = 0.2):
     return out
 
 
-def affine_offsets_mask(transform, translation, mask_logits, deform_groups: int):
+def affine_offsets_mask(transform, translation, mask_logits, deform_groups: int, transform_bias=None,
+                        translation_bias=None, mask_bias=None):
     """Per-group affine offset expansion ``T*R - R + t`` and ``sigmoid(mask_logits)``
-    (models/networks.py:302-313) -> fp32 NCHW (offset (n,18D,h,w), mask (n,9D,h,w) or None)."""
+    (models/networks.py:302-313) -> fp32 NCHW (offset (n,18D,h,w), mask (n,9D,h,w) or None).
+    The optional biases are added to T / t / logits first (bias-free producing convolutions)."""
     _require_cuda("affine_offsets_mask", transform, translation, mask_logits)
     lib = L.load()
     n, _, h, w = transform.shape
@@ -420,15 +426,18 @@ def affine_offsets_mask(transform, translation, mask_logits, deform_groups: int)
             mask = torch.empty((n, 9 * D, h, w), dtype=torch.float32, device=transform.device)
         L.check(lib.eavsr_affine_offsets_forward(
             transform.data_ptr(), _strides(transform), translation.data_ptr(), _strides(translation),
-            _ptr(mask_logits), _strides(mask_logits) if mask_logits is not None else None, offset.data_ptr(),
+            _ptr(mask_logits), _strides(mask_logits) if mask_logits is not None else None,
+            _ptr(_b(transform_bias, transform)), _ptr(_b(translation_bias, transform)),
+            _ptr(_b(mask_bias, transform)), offset.data_ptr(),
             _ptr(mask), n, D, h, w, _dtype_code("affine_offsets_mask", transform), _stream(transform)),
             "affine_offsets")
     return offset, mask
 
 
-def ca_residual(res, skip, w1, b1, w2, b2, reduction: int = 16):
-    """``res * CALayer(res) + skip`` of the reference's RCABlock (models/networks.py:449-465) with two
-    kernels (channel sums; MLP + scale + residual).  res, skip: (n,64,h,w)."""
+def ca_residual(res, skip, w1, b1, w2, b2, reduction: int = 16, res_bias=None):
+    """``r * CALayer(r) + skip`` with ``r = res + res_bias`` -- the tail of the reference's RCABlock
+    (models/networks.py:449-465) with two kernels (channel sums; MLP + scale + residual).
+    ``res_bias`` lets the producing convolution run bias-free.  res, skip: (n,64,h,w)."""
     _require_cuda("ca_residual", res, skip, w1, b1, w2, b2)
     lib = L.load()
     n, c, h, w = res.shape
@@ -440,7 +449,41 @@ def ca_residual(res, skip, w1, b1, w2, b2, reduction: int = 16):
         dt = res.dtype
         L.check(lib.eavsr_ca_residual_forward(rd.data_ptr(), sd.data_ptr(), w1.to(dt).contiguous().data_ptr(),
                                               b1.to(dt).contiguous().data_ptr(), w2.to(dt).contiguous().data_ptr(),
-                                              b2.to(dt).contiguous().data_ptr(), out.data_ptr(), sums.data_ptr(),
+                                              b2.to(dt).contiguous().data_ptr(),
+                                              _ptr(res_bias.to(dt).contiguous()) if res_bias is not None else None,
+                                              out.data_ptr(), sums.data_ptr(),
                                               n, c, h, w, reduction, _dtype_code("ca_residual", rd), _stream(rd)),
                 "ca_residual")
     return out
+
+
+def bias_act_(x, bias, negative_slope: float = 1.0):
+    """In place ``x = LeakyReLU_slope(x + bias[c])`` on a channels_last tensor (slope 1: bias only,
+    0: ReLU).  Returns x."""
+    _require_cuda("bias_act_", x, bias)
+    lib = L.load()
+    n, c, h, w = x.shape
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("bias_act_: x must be dense channels_last")
+    with torch.cuda.device(x.device):
+        L.check(lib.eavsr_bias_act_forward(x.data_ptr(), bias.to(x.dtype).contiguous().data_ptr(), c, n * h * w,
+                                           float(negative_slope), _dtype_code("bias_act_", x), _stream(x)),
+                "bias_act")
+    return x
+
+
+def conv2d_bias_act(conv: nn.Conv2d, x, negative_slope: float = 1.0):
+    """cuDNN convolution with its bias add and (Leaky)ReLU folded into one vectorised epilogue pass
+    (inference).  Falls back to ``act(conv(x))`` whenever a gradient is needed or the layout does
+    not allow the fused epilogue."""
+    vec = 16 // x.element_size()
+    if (conv.bias is None or conv.out_channels % vec != 0 or not fused_inference_ok(x, conv.weight)
+            or not x.is_contiguous(memory_format=torch.channels_last)):
+        y = conv(x)
+        if negative_slope == 1.0:
+            return y
+        return torch.relu_(y) if negative_slope == 0.0 else torch.nn.functional.leaky_relu_(y, negative_slope)
+    y = torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if not y.is_contiguous(memory_format=torch.channels_last):
+        y = y.contiguous(memory_format=torch.channels_last)
+    return bias_act_(y, conv.bias, negative_slope)

@@ -131,17 +131,27 @@ int eavsr_adapt_mix_forward(const void* a, const void* b, const void* w1, const 
 /* affine_offsets: offset = T*R - R + t per deformable group and mask = sigmoid(logits)
  *   (models/networks.py:302-313).  transform (n,4D,h,w), translation (n,2D,h,w), mask_logits (n,9D,h,w)
  *   are `dtype` with arbitrary strides; offset (n,18D,h,w) / mask (n,9D,h,w) are fp32 NCHW contiguous,
- *   the layout eavsr_dcn_forward consumes.  mask (and mask_logits) may be NULL. */
+ *   the layout eavsr_dcn_forward consumes.  mask (and mask_logits) may be NULL.  The optional *_bias
+ *   vectors are added to the inputs first, so the three producing convolutions can run bias-free. */
 int eavsr_affine_offsets_forward(const void* transform, const int64_t transform_strides[4],
                                  const void* translation, const int64_t translation_strides[4],
-                                 const void* mask_logits, const int64_t mask_strides[4], float* offset, float* mask,
-                                 int n, int deform_groups, int h, int w, int dtype, void* stream);
+                                 const void* mask_logits, const int64_t mask_strides[4],
+                                 const void* transform_bias /* (4D) or NULL */,
+                                 const void* translation_bias /* (2D) or NULL */,
+                                 const void* mask_bias /* (9D) or NULL */, float* offset, float* mask, int n,
+                                 int deform_groups, int h, int w, int dtype, void* stream);
 /* ca_residual: out = res * sigmoid(W2 relu(W1 mean_hw(res) + b1) + b2) + skip  (CALayer + residual of
  *   RCABlock, models/networks.py:449-465).  res, skip, out: (n,64,h,w) dense NHWC; w1 (4,64), w2 (64,4);
  *   sums_workspace: n*64 floats. */
 int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1, const void* b1, const void* w2,
-                              const void* b2, void* out, float* sums_workspace, int n, int c, int h, int w,
-                              int reduction, int dtype, void* stream);
+                              const void* b2, const void* res_bias /* bias of the conv that produced res, or NULL */,
+                              void* out, float* sums_workspace, int n, int c, int h, int w, int reduction, int dtype,
+                              void* stream);
+/* bias_act: x = LeakyReLU_slope(x + bias[c]) in place on a dense NHWC tensor of `pixels` x c elements
+ *   (slope 1 = plain bias add, 0 = ReLU): the bias/activation epilogue of the cuDNN convolutions around
+ *   the hot path in one vectorised pass.  c must be a multiple of 16 bytes / sizeof(dtype). */
+int eavsr_bias_act_forward(void* x, const void* bias, int c, long long pixels, float negative_slope, int dtype,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,57 @@ def test_ca_residual_matches_rcablock_tail(cuda, shape, dtype, tol):
     assert (out.double().cpu() - ref).abs().max() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_ca_residual_with_folded_conv_bias(cuda, dtype, tol):
+    g = torch.Generator().manual_seed(4)
+    res, skip = torch.randn(2, 64, 9, 14, generator=g), torch.randn(2, 64, 9, 14, generator=g)
+    rb = torch.randn(64, generator=g) * 0.5
+    ca = M._CALayer(64).double()
+    for p in ca.parameters():
+        p.data = (torch.randn(p.shape, generator=g) * 0.5).to(dtype).double()
+    r = res.to(dtype).double() + rb.to(dtype).double().view(1, -1, 1, 1)
+    ref = ca(r) + skip.to(dtype).double()
+    du = ca.conv_du
+    out = ops.ca_residual(_cl(res.to(cuda, dtype)), _cl(skip.to(cuda, dtype)), du[0].weight.to(cuda, dtype),
+                          du[0].bias.to(cuda, dtype), du[2].weight.to(cuda, dtype), du[2].bias.to(cuda, dtype), 16,
+                          res_bias=rb.to(cuda, dtype))
+    assert (out.double().cpu() - ref).abs().max() < tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("slope", [1.0, 0.0, 0.1])
+@pytest.mark.parametrize("dtype,c", [(torch.float32, 64), (torch.bfloat16, 72), (torch.float32, 4), (torch.bfloat16, 256)])
+def test_bias_act_and_conv_epilogue(cuda, slope, dtype, c):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, c, 11, 13, generator=g).to(dtype)
+    b = torch.randn(c, generator=g).to(dtype)
+    t = x.double() + b.double().view(1, -1, 1, 1)
+    ref = torch.where(t > 0, t, t * slope)
+    out = ops.bias_act_(_cl(x.to(cuda)).clone(memory_format=torch.channels_last), b.to(cuda), slope)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert (out.double().cpu() - ref).abs().max() < tol * max(1.0, ref.abs().max().item())
+    conv = torch.nn.Conv2d(16, c, 3, 1, 1).to(cuda, dtype).to(memory_format=torch.channels_last)
+    xin = _cl(torch.randn(1, 16, 10, 12, generator=g).to(cuda, dtype))
+    with torch.no_grad():
+        fused = ops.conv2d_bias_act(conv, xin, slope)
+        y = conv(xin)
+        plain = y if slope == 1.0 else F.leaky_relu(y, slope)
+    assert (fused.float() - plain.float()).abs().max() < (1e-5 if dtype == torch.float32 else 5e-2)
+
+
+def test_affine_offsets_with_folded_biases(cuda):
+    g = torch.Generator().manual_seed(6)
+    D, n, h, w = 8, 1, 9, 11
+    T, t, m = (torch.randn(n, k * D, h, w, generator=g) for k in (4, 2, 9))
+    bT, bt, bm = (torch.randn(k * D, generator=g) for k in (4, 2, 9))
+    v = lambda z, b: z.double() + b.double().view(1, -1, 1, 1)      # noqa: E731
+    ref_off = O.affine_offsets(v(T, bT), v(t, bt), D)
+    ref_mask = torch.sigmoid(v(m, bm))
+    off, mask = ops.affine_offsets_mask(_cl(T.to(cuda)), _cl(t.to(cuda)), _cl(m.to(cuda)), D, bT.to(cuda), bt.to(cuda),
+                                        bm.to(cuda))
+    assert (off.double().cpu() - ref_off).abs().max() < 1e-5
+    assert (mask.double().cpu() - ref_mask).abs().max() < 1e-5
+
+
 def test_model_uses_fused_path_only_without_grad(cuda):
     blk = M._RCABlock(64).to(cuda)
     x = _cl(torch.randn(1, 64, 12, 12, device=cuda))
@@ -85,7 +136,7 @@ def test_model_uses_fused_path_only_without_grad(cuda):
     n0 = _lib.launch_count()
     with torch.no_grad():
         y_fused = blk(x)
-    assert _lib.launch_count() - n0 == 2
+    assert _lib.launch_count() - n0 == 3        # bias+ReLU epilogue, channel sums, scale+residual
     n1 = _lib.launch_count()
     y_torch = blk(x.requires_grad_())
     assert _lib.launch_count() == n1 and y_torch.requires_grad
