@@ -353,11 +353,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.time()
+        torch.cuda.profiler.start()          # no-op unless run under `ncu --profile-from-start off`
         e0.record()
         for _ in range(args.steps):
             wl.step()
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
         t1 = time.time()
         launches = _lib.launch_count() - l0
         if getattr(wl, "launches_per_step", None):   # CUDA-graph replay: the counter only sees the capture
