@@ -407,3 +407,35 @@ extern "C" int eavsr_bias_act_forward(void* x, const void* bias, int c, long lon
   else { set_error("bias_act: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
   return check_launch("bias_act");
 }
+
+// Scale + residual only, with channel sums that were produced elsewhere (the epilogue of
+// eavsr_conv3x3_forward): out = (res + res_bias) * sigmoid(MLP(sums / HW + res_bias)) + skip.
+extern "C" int eavsr_ca_scale_forward(const void* res, const void* skip, const float* sums, const void* w1,
+                                      const void* b1, const void* w2, const void* b2, const void* res_bias, void* out,
+                                      int n, int c, int h, int w, int reduction, int dtype, void* stream) {
+  EAVSR_REQUIRE(res && skip && sums && w1 && b1 && w2 && b2 && out, "ca_scale: null pointer");
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0 && n <= 65535, "ca_scale: bad shape");
+  if (c != 64 || reduction != 16) {
+    set_error("ca_scale: only C=64, reduction=16 is fused (got C=%d, r=%d)", c, reduction);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  EAVSR_REQUIRE(al16(res) && al16(skip) && al16(out), "ca_scale: tensors must be 16-byte aligned dense NHWC");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = h * w;
+  if (dtype == EAVSR_F32) {
+    const int chunks = HW * 64 / 4;
+    dim3 g2(min(ceil_div(chunks, 256 * 4), 148 * 8), n);
+    ca_scale_residual_kernel<float, 64, 4><<<g2, 256, 0, st>>>((const float*)res, (const float*)skip, sums,
+                                                             (const float*)w1, (const float*)b1, (const float*)w2,
+                                                             (const float*)b2, (const float*)res_bias, (float*)out, HW,
+                                                             1.f / (float)HW, chunks);
+  } else if (dtype == EAVSR_BF16) {
+    using B = __nv_bfloat16;
+    const int chunks = HW * 64 / 8;
+    dim3 g2(min(ceil_div(chunks, 256 * 4), 148 * 8), n);
+    ca_scale_residual_kernel<B, 64, 4><<<g2, 256, 0, st>>>((const B*)res, (const B*)skip, sums, (const B*)w1,
+                                                         (const B*)b1, (const B*)w2, (const B*)b2, (const B*)res_bias,
+                                                         (B*)out, HW, 1.f / (float)HW, chunks);
+  } else { set_error("ca_scale: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("ca_scale");
+}

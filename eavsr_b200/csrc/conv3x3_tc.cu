@@ -1,0 +1,299 @@
+// 3x3 convolution 64 -> 64 channels (NHWC bf16, stride 1, pad 1) as an implicit GEMM on
+// tcgen05 / TMEM, with bias + (Leaky)ReLU and the channel sums of the channel-attention layer
+// fused into the epilogue.  This is SURVEY.md section 8 row f3: the RCAB residual backbone
+// (models/networks.py:449-482, models/eavsrp_model.py:366-400) is 65 % of EAVSR+'s FLOPs and,
+// once the alignment path is native, 7 700 of these convolutions per 30-frame clip.
+//
+// D[128 positions x 64 cout] = sum_{tap} A_tap[128 x 64 cin] * W_tap[64 x 64]
+//
+// The trick that makes the nine A_tap operands free: the CTA stages ONE halo tile of the input
+// (6 rows x 32 columns of pixels) in the *non-swizzled* K-major UMMA layout
+// [16-byte channel chunk][pixel row][16 B].  In that layout consecutive pixels of one channel
+// chunk are 16 bytes apart, so the A operand of tap (r, s) is the same buffer with the descriptor
+// start address advanced by (r*32 + s) * 16 bytes -- no im2col, no re-staging, no second copy.
+// One MMA covers 128 consecutive halo positions = a 4 x 32 block of which 4 x 30 are real outputs
+// (the 2 wrap-around columns per row are computed and dropped: 6 % waste).
+//
+// Warp roles (288 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0-3  producers: cp.async (zero-fill outside the image = conv padding) into a 3-stage ring
+//   warp  4    one lane issues 36 tcgen05.mma per tile (A: no-swizzle descriptors, B: 9 resident
+//              128B-swizzled 64x64 weight tiles) and commits to mbarriers
+//   warps 5-8  epilogue: tcgen05.ld -> +bias -> activation -> bf16 NHWC store, channel sums kept in
+//              registers across the CTA's tiles and flushed with one atomicAdd per channel
+// Two TMEM accumulators (2 x 64 columns) decouple the epilogue from the next tile's MMAs.
+#include "common.cuh"
+
+namespace eavsr {
+namespace {
+
+constexpr int CV_CH = 64;
+constexpr int CV_TR = 4, CV_TC = 30;            // real outputs per tile
+constexpr int CV_PW = 32;                       // halo pitch in pixels (= MMA rows per output row)
+constexpr int CV_HROWS = (CV_TR + 2) * CV_PW;   // 192 staged halo positions
+constexpr int CV_ROWS = 200;                    // + padding rows read by the wrap-around outputs
+constexpr int CV_PLANE = CV_ROWS * 16 + 16;     // bytes per 16-byte-chunk plane (+16: bank spread)
+constexpr int CV_ASTAGE = 8 * CV_PLANE;         // 8 chunks of 8 bf16 = 64 channels
+constexpr int CV_NS = 3;
+constexpr int CV_BTILE = CV_CH * CV_CH * 2;     // 8 KB per tap
+constexpr int CV_PRODUCERS = 128;
+constexpr int CV_THREADS = 288;
+constexpr int CV_TMEM = 128;
+
+struct CvSmem {
+  static constexpr int B_OFF = 0;                                  // 9 x 8 KB, 1024-aligned
+  static constexpr int A_OFF = B_OFF + 9 * CV_BTILE;               // 3 stages
+  static constexpr int BAR_OFF = ((A_OFF + CV_NS * CV_ASTAGE + 15) / 16) * 16;
+  // full[NS], empty[NS], accf[2], acce[2], wbar, tmem slot
+  static constexpr int TOTAL = BAR_OFF + (2 * CV_NS + 5) * 8 + 16;
+  static constexpr int DYN = TOTAL + 1024;
+};
+
+// no-swizzle K-major descriptor: core matrix = 8 rows x 16 B contiguous; SBO = 128 B between
+// 8-row groups (rows are 16 B apart), LBO = distance between the two 16-byte K chunks of one MMA.
+__device__ __forceinline__ uint64_t umma_desc_nosw_kmajor(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+
+__global__ void conv_pack_weight(const __nv_bfloat16* __restrict__ w, uint8_t* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tap, o, c)
+  if (idx >= 9 * CV_CH * CV_CH) return;
+  const int c = idx % CV_CH, o = (idx / CV_CH) % CV_CH, t = idx / (CV_CH * CV_CH);
+  *reinterpret_cast<__nv_bfloat16*>(packed + (size_t)t * CV_BTILE + sw128_offset(o, c * 2)) =
+      w[((size_t)o * CV_CH + c) * 9 + t];
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ wpacked,
+                  const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                  float* __restrict__ chan_sums, int H, int W, int tiles_x, int tiles_per_img, int total_tiles,
+                  float slope) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sB = base + CvSmem::B_OFF, sA = base + CvSmem::A_OFF, bars = base + CvSmem::BAR_OFF;
+  const uint32_t bar_full = bars, bar_empty = bars + CV_NS * 8, bar_accf = bars + 2 * CV_NS * 8;
+  const uint32_t bar_acce = bar_accf + 16, bar_w = bar_acce + 16, tmem_slot_addr = bar_w + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CvSmem::BAR_OFF + (2 * CV_NS + 5) * 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < CV_NS; ++s) {
+      mbar_init(bar_full + 8 * s, CV_PRODUCERS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf + 8 * b, 1);
+      mbar_init(bar_acce + 8 * b, 4);
+    }
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+  }
+  // zero the padding rows of every stage once (they only feed dropped wrap-around outputs)
+  for (int i = tid; i < CV_NS * 8 * (CV_ROWS - CV_HROWS + 1); i += CV_THREADS) {
+    const int s = i / (8 * (CV_ROWS - CV_HROWS + 1)), r = i % (8 * (CV_ROWS - CV_HROWS + 1));
+    const int ch = r / (CV_ROWS - CV_HROWS + 1), row = CV_HROWS + r % (CV_ROWS - CV_HROWS + 1);
+    *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + s * CV_ASTAGE + ch * CV_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 4) tmem_alloc<CV_TMEM>(tmem_slot_addr);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int first = blockIdx.x;
+  const int my_tiles = (total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int s = tl % CV_NS;
+      if (tl >= CV_NS) mbar_wait(bar_empty + 8 * s, ((tl / CV_NS) - 1) & 1);
+      const int tile = first + tl * (int)gridDim.x;
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+      const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
+      const uint32_t stage = sA + s * CV_ASTAGE;
+      for (int i = tid; i < CV_HROWS * 8; i += CV_PRODUCERS) {
+        const int p = i >> 3, ch = i & 7;
+        const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+        const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const __nv_bfloat16* src = ok ? xn + ((size_t)gy * W + gx) * CV_CH + ch * 8 : xn;
+        cp_async_16_zfill(stage + ch * CV_PLANE + p * 16, src, ok);
+      }
+      cp_async_commit();
+      if (tl >= 1) {                       // tile tl-1 has landed: publish it (keeps one stage in flight)
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full + 8 * ((tl - 1) % CV_NS));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    mbar_arrive(bar_full + 8 * ((my_tiles - 1) % CV_NS));
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, 9 * CV_BTILE);
+      for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
+      mbar_wait(bar_w, 0);
+      constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_CH);
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int s = tl % CV_NS, buf = tl & 1;
+        if (tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, (tl / CV_NS) & 1);
+        tc_fence_after();
+        const uint32_t stage = sA + s * CV_ASTAGE;
+        const uint32_t d = tmem_d + buf * CV_CH;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t a0 = stage + ((t / 3) * CV_PW + (t % 3)) * 16;
+          const uint64_t bdesc = umma_desc_sw128_kmajor(sB + t * CV_BTILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = umma_desc_nosw_kmajor(a0 + 2 * k * CV_PLANE, CV_PLANE);
+            umma_bf16(d, adesc, bdesc + 2 * k, IDESC, (t | k) != 0);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);
+        umma_commit(bar_accf + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 5..8 -> TMEM lane quadrants 1,2,3,0) =====================
+    const int q = warp & 3;                       // output row of the tile handled by this warp
+    float bsum0 = 0.f, bsum1 = 0.f;               // channel sums of channels 2*lane, 2*lane+1
+    float bv[CV_CH];
+#pragma unroll
+    for (int c = 0; c < CV_CH; ++c) bv[c] = bias ? __bfloat162float(bias[c]) : 0.f;
+    int cur_n = -1;
+    auto flush = [&]() {
+      if (chan_sums && cur_n >= 0) {
+        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane, bsum0);
+        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane + 1, bsum1);
+      }
+      bsum0 = bsum1 = 0.f;
+    };
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int buf = tl & 1;
+      const int tile = first + tl * (int)gridDim.x;
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      if (n != cur_n) { flush(); cur_n = n; }
+      const int oy = (rem / tiles_x) * CV_TR + q, ox = (rem % tiles_x) * CV_TC + lane;
+      const bool valid = lane < CV_TC && oy < H && ox < W;
+      mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[CV_CH];
+      tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH, acc);
+      tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH + 32, acc + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+      float f[CV_CH];
+#pragma unroll
+      for (int c = 0; c < CV_CH; ++c) {
+        const float t = __uint_as_float(acc[c]) + bv[c];
+        f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
+      }
+      if (valid) {
+        __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH;
+#pragma unroll
+        for (int c = 0; c < CV_CH; c += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(f[c], f[c + 1]); u.y = pack_bf16x2(f[c + 2], f[c + 3]);
+          u.z = pack_bf16x2(f[c + 4], f[c + 5]); u.w = pack_bf16x2(f[c + 6], f[c + 7]);
+          *reinterpret_cast<uint4*>(op + c) = u;
+        }
+      }
+      if (chan_sums) {
+        // transpose-reduce over the 32 lanes: 62 shuffles leave lane l with the sums of channels 2l, 2l+1
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+          const int m = 16 >> step, len = 32 >> step;     // lanes with bit m keep the upper half
+          const bool up = (lane & m) != 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < len) {
+              const float send = up ? f[i] : f[i + len];
+              const float keep = up ? f[i + len] : f[i];
+              f[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+          }
+        }
+        // step k adds (32 >> k) to the channel base when lane bit (16 >> k) is set: base = 2 * lane
+        bsum0 += f[0];
+        bsum1 += f[1];
+      }
+    }
+    flush();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<CV_TMEM>(tmem_d);
+}
+
+}  // namespace
+}  // namespace eavsr
+
+using namespace eavsr;
+
+extern "C" size_t eavsr_conv3x3_packed_weight_bytes(void) { return (size_t)9 * CV_BTILE; }
+
+extern "C" int eavsr_conv3x3_pack_weight(const void* weight, void* packed, int cin, int cout, int dtype,
+                                         void* stream) {
+  EAVSR_REQUIRE(weight && packed, "conv3x3_pack_weight: null pointer");
+  if (cin != CV_CH || cout != CV_CH || dtype != EAVSR_BF16) {
+    set_error("conv3x3: only 64->64 bf16 is implemented (got %d->%d, dtype %d)", cin, cout, dtype);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  conv_pack_weight<<<(9 * CV_CH * CV_CH + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)weight,
+                                                                                   (uint8_t*)packed);
+  return check_launch("conv3x3_pack_weight");
+}
+
+extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
+                                     float* channel_sums, int n, int cin, int cout, int h, int w,
+                                     float negative_slope, int dtype, void* stream) {
+  EAVSR_REQUIRE(x && packed_weight && out, "conv3x3_forward: null pointer");
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_forward: empty tensor");
+  if (cin != CV_CH || cout != CV_CH || dtype != EAVSR_BF16) {
+    set_error("conv3x3: only 64->64 bf16 is implemented (got %d->%d, dtype %d)", cin, cout, dtype);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                  reinterpret_cast<uintptr_t>(packed_weight)) & 15u) == 0,
+                "conv3x3_forward: x / out / packed weights must be 16-byte aligned dense NHWC");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_x = ceil_div(w, CV_TC), tiles_y = ceil_div(h, CV_TR);
+  const int tiles_per_img = tiles_x * tiles_y;
+  const long long total = (long long)tiles_per_img * n;
+  EAVSR_REQUIRE(total < (1ll << 30), "conv3x3_forward: too many tiles");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(total < sms ? total : sms);
+  if (channel_sums) {
+    cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
+    if (em != cudaSuccess) { set_error("conv3x3_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
+  }
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem::DYN);
+  if (e != cudaSuccess) { set_error("conv3x3_forward: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  conv3x3_tc_kernel<<<grid, CV_THREADS, CvSmem::DYN, st>>>((const __nv_bfloat16*)x, (const uint8_t*)packed_weight,
+                                                          (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
+                                                          channel_sums, h, w, tiles_x, tiles_per_img, (int)total,
+                                                          negative_slope);
+  return check_launch("conv3x3_forward");
+}

@@ -23,8 +23,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, conv2d_bias_act, flow_warp,
-                  flow_warp_nhw2, fused_inference_ok, modulated_deform_conv2d)
+from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act,
+                  conv3x3_64, conv3x3_64_eligible, flow_warp, flow_warp_nhw2, fused_inference_ok,
+                  modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
 
@@ -50,6 +51,12 @@ class _RCABlock(nn.Module):
 
     def forward(self, x):
         du = self.ca.conv_du
+        if conv3x3_64_eligible(self.res[0], x):
+            # both convolutions on tcgen05: bias+ReLU in the first epilogue, bias + the channel sums of
+            # the attention layer in the second; then one scale+residual pass.  3 kernels per block.
+            h = conv3x3_64(self.res[0], x, 0.0)
+            res, sums = conv3x3_64(self.res[2], h, 1.0, want_sums=True)
+            return ca_scale(res, x, sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16)
         if x.shape[1] == 64 and fused_inference_ok(x, self.res[0].weight):
             # conv+bias+ReLU epilogue in one pass, second conv bias-free (its bias is folded into the
             # channel-attention kernels), then reduce + MLP + scale + residual add in 2 kernels
@@ -69,6 +76,8 @@ class _RCAGroup(nn.Module):
         y = x
         for blk in self.rg[:-1]:
             y = blk(y)
+        if conv3x3_64_eligible(self.rg[-1], y):
+            return conv3x3_64(self.rg[-1], y, 1.0) + x
         return conv2d_bias_act(self.rg[-1], y, 1.0) + x
 
 
@@ -364,7 +373,8 @@ class EAVSRP(nn.Module):
             x = self.upsample1[1](conv2d_bias_act(self.upsample1[0], x, 0.1))
             if self.scale == 4:
                 x = self.upsample2[1](conv2d_bias_act(self.upsample2[0], x, 0.1))
-            x = conv2d_bias_act(self.conv_hr, x, 0.1)
+            x = conv3x3_64(self.conv_hr, x, 0.1) if conv3x3_64_eligible(self.conv_hr, x) else \
+                conv2d_bias_act(self.conv_hr, x, 0.1)
             # the image-domain tail is fp32: residual (small) + bilinear base (the [0,1] frame itself)
             base = F.interpolate(lrs[:, i].float(), scale_factor=self.scale, mode="bilinear", align_corners=False)
             outs.append(self.conv_last(x).float() + base)

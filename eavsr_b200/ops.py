@@ -35,6 +35,7 @@ __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "flow_warp", "flow_warp_nhw2",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
+    "conv3x3_64", "conv3x3_64_eligible", "ca_scale",
 ]
 
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
@@ -487,3 +488,67 @@ def conv2d_bias_act(conv: nn.Conv2d, x, negative_slope: float = 1.0):
     if not y.is_contiguous(memory_format=torch.channels_last):
         y = y.contiguous(memory_format=torch.channels_last)
     return bias_act_(y, conv.bias, negative_slope)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 3x3 convolution 64 -> 64 (bf16 NHWC) with fused bias / activation / channel sums
+# ------------------------------------------------------------------------------------------
+def conv3x3_64_eligible(conv: nn.Conv2d, x) -> bool:
+    return (isinstance(conv, nn.Conv2d) and conv.in_channels == 64 and conv.out_channels == 64
+            and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
+            and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 64
+            and fused_inference_ok(x, conv.weight))
+
+
+def _packed_conv_weight(conv: nn.Conv2d, device) -> torch.Tensor:
+    """Weights re-packed once into the 9 swizzled 64x64 bf16 tiles the MMA reads (cached on the module,
+    invalidated by the parameter's version counter / storage)."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version, str(device))
+    hit = getattr(conv, "_eavsr_packed", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    lib = L.load()
+    packed = torch.empty(lib.eavsr_conv3x3_packed_weight_bytes(), dtype=torch.uint8, device=device)
+    wb = w.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+    L.check(lib.eavsr_conv3x3_pack_weight(wb.data_ptr(), packed.data_ptr(), 64, 64, L.BF16,
+                                          torch.cuda.current_stream(device).cuda_stream), "conv3x3_pack_weight")
+    conv._eavsr_packed = (key, packed)
+    return packed
+
+
+def conv3x3_64(conv: nn.Conv2d, x, negative_slope: float = 1.0, want_sums: bool = False):
+    """``LeakyReLU_slope(conv(x))`` for a 64->64 3x3 stride-1 pad-1 convolution on tcgen05 (bf16
+    channels_last, inference).  With ``want_sums`` also returns the per-(n, channel) sums of the
+    output over (h, w) in fp32, computed in the epilogue.  Check `conv3x3_64_eligible` first."""
+    lib = L.load()
+    n, c, h, w = x.shape
+    with torch.cuda.device(x.device):
+        xd = x.contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(xd)
+        sums = torch.empty((n, 64), dtype=torch.float32, device=x.device) if want_sums else None
+        packed = _packed_conv_weight(conv, x.device)
+        bias = conv.bias.detach().to(torch.bfloat16).contiguous() if conv.bias is not None else None
+        L.check(lib.eavsr_conv3x3_forward(xd.data_ptr(), packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(sums),
+                                          n, 64, 64, h, w, float(negative_slope), L.BF16, _stream(xd)),
+                "conv3x3_forward")
+    return (out, sums) if want_sums else out
+
+
+def ca_scale(res, skip, sums, w1, b1, w2, b2, reduction: int = 16, res_bias=None):
+    """``(res + res_bias) * sigmoid(MLP(sums / HW + res_bias)) + skip`` with channel sums that were
+    produced by the convolution's epilogue (see `conv3x3_64`)."""
+    lib = L.load()
+    n, c, h, w = res.shape
+    with torch.cuda.device(res.device):
+        rd = res.contiguous(memory_format=torch.channels_last)
+        sd = skip.to(res.dtype).contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(rd)
+        dt = res.dtype
+        L.check(lib.eavsr_ca_scale_forward(rd.data_ptr(), sd.data_ptr(), sums.data_ptr(),
+                                           w1.to(dt).contiguous().data_ptr(), b1.to(dt).contiguous().data_ptr(),
+                                           w2.to(dt).contiguous().data_ptr(), b2.to(dt).contiguous().data_ptr(),
+                                           _ptr(_b(res_bias, res)), out.data_ptr(), n, c, h, w, reduction,
+                                           _dtype_code("ca_scale", rd), _stream(rd)), "ca_scale")
+    return out

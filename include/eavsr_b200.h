@@ -153,6 +153,25 @@ int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1,
 int eavsr_bias_act_forward(void* x, const void* bias, int c, long long pixels, float negative_slope, int dtype,
                            void* stream);
 
+/* Second half of ca_residual with channel sums produced elsewhere (eavsr_conv3x3_forward). */
+int eavsr_ca_scale_forward(const void* res, const void* skip, const float* sums, const void* w1, const void* b1,
+                           const void* w2, const void* b2, const void* res_bias, void* out, int n, int c, int h,
+                           int w, int reduction, int dtype, void* stream);
+
+/* ---- 3x3 convolution 64 -> 64 on tcgen05 (the RCAB backbone convs,
+ * models/networks.py:449-482) -------------------------------------------------------------------
+ * x, out: (n,64,h,w) dense NHWC bf16, stride 1, pad 1.  out = LeakyReLU_slope(conv(x) + bias)
+ * (slope 1 = none, 0 = ReLU).  If channel_sums != NULL it receives sum over (h,w) of `out` per
+ * (n, channel) in fp32 (zero-filled by the call) -- the global average pool of CALayer for free.
+ * Weights are packed once with eavsr_conv3x3_pack_weight into eavsr_conv3x3_packed_weight_bytes()
+ * bytes (16-byte aligned). */
+size_t eavsr_conv3x3_packed_weight_bytes(void);
+int eavsr_conv3x3_pack_weight(const void* weight /* (64,64,3,3) */, void* packed, int cin, int cout, int dtype,
+                              void* stream);
+int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
+                          float* channel_sums, int n, int cin, int cout, int h, int w, float negative_slope,
+                          int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

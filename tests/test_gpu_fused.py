@@ -129,6 +129,44 @@ def test_affine_offsets_with_folded_biases(cuda):
     assert (mask.double().cpu() - ref_mask).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(1, 12, 30), (2, 7, 33), (1, 67, 120), (1, 272, 480), (3, 4, 5)])
+@pytest.mark.parametrize("slope", [1.0, 0.0, 0.1])
+def test_conv3x3_tcgen05_matches_conv2d(cuda, shape, slope):
+    n, h, w = shape
+    g = torch.Generator().manual_seed(7)
+    conv = torch.nn.Conv2d(64, 64, 3, 1, 1)
+    with torch.no_grad():
+        conv.weight.copy_((torch.rand(conv.weight.shape, generator=g) * 2 - 1) / 24)
+        conv.bias.copy_(torch.randn(64, generator=g) * 0.1)
+    conv = conv.to(cuda, torch.bfloat16)
+    x = _cl(torch.randn(n, 64, h, w, generator=g).to(cuda, torch.bfloat16))
+    assert ops.conv3x3_64_eligible(conv, x)
+    y = F.conv2d(x.double().cpu(), conv.weight.double().cpu(), conv.bias.double().cpu(), padding=1)
+    ref = torch.where(y > 0, y, y * slope)
+    with torch.no_grad():
+        out, sums = ops.conv3x3_64(conv, x, slope, want_sums=True)
+        out2 = ops.conv3x3_64(conv, x, slope)
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16 and torch.equal(out, out2)
+    assert (out.double().cpu() - ref).abs().max() < 2e-2 * max(1.0, ref.abs().max().item())
+    ref_sums = ref.sum((2, 3))
+    assert (sums.double().cpu() - ref_sums).abs().max() < 1e-3 * max(1.0, ref_sums.abs().max().item()) + 0.02 * (h * w) ** 0.5
+    assert not ops.conv3x3_64_eligible(conv, x.float())
+
+
+def test_rcablock_tcgen05_path_matches_torch_path(cuda):
+    g = torch.Generator().manual_seed(8)
+    blk = M._RCABlock(64)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * (0.05 if p.dim() > 1 else 0.1))
+    blk = blk.to(cuda, torch.bfloat16).to(memory_format=torch.channels_last)
+    x = _cl(torch.randn(2, 64, 21, 37, generator=g).to(cuda, torch.bfloat16))
+    with torch.no_grad():
+        fused = blk(x)
+    ref = blk.double().cpu()(x.double().cpu())
+    assert (fused.double().cpu() - ref).abs().max() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
 def test_model_uses_fused_path_only_without_grad(cuda):
     blk = M._RCABlock(64).to(cuda)
     x = _cl(torch.randn(1, 64, 12, 12, device=cuda))

@@ -141,8 +141,28 @@ def bench_corr():
         rec(f"correlation bwd f32 {n}x{c}x{h}x{w}", sec, n * h * w * (4 * c + 81) * 4, 4.0 * 81 * c * n * h * w)
 
 
+def bench_conv():
+    from eavsr_b200 import ops
+    import torch.nn.functional as F
+    for n, h, w in ((1, 272, 480), (1, 1088, 1920)):
+        k = 6 if h < 1000 else 2
+        conv = torch.nn.Conv2d(64, 64, 3, 1, 1).to(dev, torch.bfloat16).to(memory_format=torch.channels_last)
+        xs = [torch.randn(n, 64, h, w, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(k)]
+        px = n * h * w
+        by, fl = px * 256, 2.0 * px * 64 * 64 * 9
+        with torch.no_grad():
+            sec = timeit(lambda i: ops.conv3x3_64(conv, xs[i % k], 0.0), 40)
+            rec(f"conv3x3 64->64 tcgen05 +bias+relu bf16 {n}x64x{h}x{w}", sec, by, fl)
+            sec = timeit(lambda i: ops.conv3x3_64(conv, xs[i % k], 1.0, want_sums=True), 40)
+            rec(f"conv3x3 64->64 tcgen05 +bias+chan-sums bf16 {n}x64x{h}x{w}", sec, by, fl)
+            sec = timeit(lambda i: F.relu(conv(xs[i % k])), 40)
+            rec(f"cuDNN conv3x3 + bias + relu (torch) bf16 {n}x64x{h}x{w}", sec, by, fl)
+            sec = timeit(lambda i: F.conv2d(xs[i % k], conv.weight, None, 1, 1), 40)
+            rec(f"cuDNN conv3x3 only (torch) bf16 {n}x64x{h}x{w}", sec, by, fl)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["warp", "dcn", "corr"]
+    which = sys.argv[1:] or ["warp", "dcn", "corr", "conv"]
     for wname in which:
         globals()["bench_" + wname]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

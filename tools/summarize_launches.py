@@ -27,7 +27,8 @@ def main(path, skip=0):
         short = re.sub(r"\(.*", "", name)
         short = re.sub(r"<.*", "", short)[-70:]
         if "eavsr" in name:
-            m = re.search(r"(dcn_\w+|flow_warp_\w+|corr_\w+)", name)
+            m = re.search(r"(dcn_\w+|flow_warp_\w+|corr_\w+|conv3x3_\w+|conv_pack\w+|adapt_mix\w+|affine_offsets\w+|"
+                          r"channel_sum\w+|ca_scale\w+|bias_act\w+)", name)
             short = "eavsr::" + (m.group(1) if m else short)
         c, t = agg.get(short, (0, 0.0))
         agg[short] = (c + 1, t + us)
