@@ -21,6 +21,8 @@
 //   warps 5-8  epilogue: tcgen05.ld -> +bias -> activation -> bf16 NHWC store, channel sums kept in
 //              registers across the CTA's tiles and flushed with one atomicAdd per channel
 // Two TMEM accumulators (2 x 64 columns) decouple the epilogue from the next tile's MMAs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eavsr {
@@ -42,7 +44,8 @@ constexpr int CV_TMEM = 128;
 struct CvSmem {
   static constexpr int B_OFF = 0;                                  // 9 x 8 KB, 1024-aligned
   static constexpr int A_OFF = B_OFF + 9 * CV_BTILE;               // 3 stages
-  static constexpr int BAR_OFF = ((A_OFF + CV_NS * CV_ASTAGE + 15) / 16) * 16;
+  static constexpr int BIAS_OFF = ((A_OFF + CV_NS * CV_ASTAGE + 15) / 16) * 16;   // 64 fp32
+  static constexpr int BAR_OFF = BIAS_OFF + CV_CH * 4;
   // full[NS], empty[NS], accf[2], acce[2], wbar, tmem slot
   static constexpr int TOTAL = BAR_OFF + (2 * CV_NS + 5) * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ wpacked,
                   const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                   float* __restrict__ chan_sums, int H, int W, int tiles_x, int tiles_per_img, int total_tiles,
-                  float slope) {
+                  float slope, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -98,6 +101,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     mbar_init(bar_w, 1);
     fence_mbar_init();
   }
+  if (tid < CV_CH) reinterpret_cast<float*>(smem + CvSmem::BIAS_OFF)[tid] = bias ? __bfloat162float(bias[tid]) : 0.f;
   // zero the padding rows of every stage once (they only feed dropped wrap-around outputs)
   for (int i = tid; i < CV_NS * 8 * (CV_ROWS - CV_HROWS + 1); i += CV_THREADS) {
     const int s = i / (8 * (CV_ROWS - CV_HROWS + 1)), r = i % (8 * (CV_ROWS - CV_HROWS + 1));
@@ -157,12 +161,12 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
         const uint32_t d = tmem_d + buf * CV_CH;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const uint32_t a0 = stage + ((t / 3) * CV_PW + (t % 3)) * 16;
+          const uint32_t a0 = stage + (dbg == 2 ? 0 : ((t / 3) * CV_PW + (t % 3)) * 16);
           const uint64_t bdesc = umma_desc_sw128_kmajor(sB + t * CV_BTILE);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adesc = umma_desc_nosw_kmajor(a0 + 2 * k * CV_PLANE, CV_PLANE);
-            umma_bf16(d, adesc, bdesc + 2 * k, IDESC, (t | k) != 0);
+            if (dbg != 1 || (t | k) == 0) umma_bf16(d, adesc, bdesc + 2 * k, IDESC, (t | k) != 0);
           }
         }
         umma_commit(bar_empty + 8 * s);
@@ -173,17 +177,33 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   } else {
     // ===================== epilogue (warps 5..8 -> TMEM lane quadrants 1,2,3,0) =====================
     const int q = warp & 3;                       // output row of the tile handled by this warp
-    float bsum0 = 0.f, bsum1 = 0.f;               // channel sums of channels 2*lane, 2*lane+1
-    float bv[CV_CH];
+    float csum[CV_CH];                            // this thread's running channel sums (its pixels)
 #pragma unroll
-    for (int c = 0; c < CV_CH; ++c) bv[c] = bias ? __bfloat162float(bias[c]) : 0.f;
+    for (int c = 0; c < CV_CH; ++c) csum[c] = 0.f;
+    const float* bsm = reinterpret_cast<const float*>(smem + CvSmem::BIAS_OFF);
     int cur_n = -1;
     auto flush = [&]() {
       if (chan_sums && cur_n >= 0) {
-        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane, bsum0);
-        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane + 1, bsum1);
+        // transpose-reduce over the 32 lanes: 62 shuffles leave lane l with the sums of channels 2l, 2l+1
+        // (step k adds (32 >> k) to the channel base when lane bit (16 >> k) is set: base = 2 * lane)
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+          const int m = 16 >> step, len = 32 >> step;
+          const bool up = (lane & m) != 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < len) {
+              const float send = up ? csum[i] : csum[i + len];
+              const float keep = up ? csum[i + len] : csum[i];
+              csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+          }
+        }
+        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane, csum[0]);
+        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane + 1, csum[1]);
       }
-      bsum0 = bsum1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CV_CH; ++c) csum[c] = 0.f;
     };
     for (int tl = 0; tl < my_tiles; ++tl) {
       const int buf = tl & 1;
@@ -204,7 +224,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       float f[CV_CH];
 #pragma unroll
       for (int c = 0; c < CV_CH; ++c) {
-        const float t = __uint_as_float(acc[c]) + bv[c];
+        const float t = __uint_as_float(acc[c]) + bsm[c];
         f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
       }
       if (valid) {
@@ -218,23 +238,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
         }
       }
       if (chan_sums) {
-        // transpose-reduce over the 32 lanes: 62 shuffles leave lane l with the sums of channels 2l, 2l+1
 #pragma unroll
-        for (int step = 0; step < 5; ++step) {
-          const int m = 16 >> step, len = 32 >> step;     // lanes with bit m keep the upper half
-          const bool up = (lane & m) != 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < len) {
-              const float send = up ? f[i] : f[i + len];
-              const float keep = up ? f[i + len] : f[i];
-              f[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-            }
-          }
-        }
-        // step k adds (32 >> k) to the channel base when lane bit (16 >> k) is set: base = 2 * lane
-        bsum0 += f[0];
-        bsum1 += f[1];
+        for (int c = 0; c < CV_CH; ++c) csum[c] += f[c];
       }
     }
     flush();
@@ -285,6 +290,8 @@ extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(total < sms ? total : sms);
+  const char* dbg_env = getenv("EAVSR_CONV_DBG");      // timing experiments only (results are wrong when set)
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   if (channel_sums) {
     cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
     if (em != cudaSuccess) { set_error("conv3x3_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
@@ -294,6 +301,6 @@ extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, c
   conv3x3_tc_kernel<<<grid, CV_THREADS, CvSmem::DYN, st>>>((const __nv_bfloat16*)x, (const uint8_t*)packed_weight,
                                                           (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
                                                           channel_sums, h, w, tiles_x, tiles_per_img, (int)total,
-                                                          negative_slope);
+                                                          negative_slope, dbg);
   return check_launch("conv3x3_forward");
 }

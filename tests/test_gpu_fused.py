@@ -140,7 +140,9 @@ def test_conv3x3_tcgen05_matches_conv2d(cuda, shape, slope):
         conv.bias.copy_(torch.randn(64, generator=g) * 0.1)
     conv = conv.to(cuda, torch.bfloat16)
     x = _cl(torch.randn(n, 64, h, w, generator=g).to(cuda, torch.bfloat16))
-    assert ops.conv3x3_64_eligible(conv, x)
+    with torch.no_grad():
+        assert ops.conv3x3_64_eligible(conv, x)
+    assert not ops.conv3x3_64_eligible(conv, x)          # gradients enabled: PyTorch path
     y = F.conv2d(x.double().cpu(), conv.weight.double().cpu(), conv.bias.double().cpu(), padding=1)
     ref = torch.where(y > 0, y, y * slope)
     with torch.no_grad():
@@ -150,7 +152,8 @@ def test_conv3x3_tcgen05_matches_conv2d(cuda, shape, slope):
     assert (out.double().cpu() - ref).abs().max() < 2e-2 * max(1.0, ref.abs().max().item())
     ref_sums = ref.sum((2, 3))
     assert (sums.double().cpu() - ref_sums).abs().max() < 1e-3 * max(1.0, ref_sums.abs().max().item()) + 0.02 * (h * w) ** 0.5
-    assert not ops.conv3x3_64_eligible(conv, x.float())
+    with torch.no_grad():
+        assert not ops.conv3x3_64_eligible(conv, x.float())
 
 
 def test_rcablock_tcgen05_path_matches_torch_path(cuda):
