@@ -35,7 +35,7 @@ constexpr int CV_HROWS = (CV_TR + 2) * CV_PW;   // 192 staged halo positions
 constexpr int CV_ROWS = 200;                    // + padding rows read by the wrap-around outputs
 constexpr int CV_PLANE = CV_ROWS * 16 + 16;     // bytes per 16-byte-chunk plane (+16: bank spread)
 constexpr int CV_ASTAGE = 8 * CV_PLANE;         // 8 chunks of 8 bf16 = 64 channels
-constexpr int CV_NS = 3;
+constexpr int CV_NS = 4;                        // one stage per producer warp
 constexpr int CV_BTILE = CV_CH * CV_CH * 2;     // 8 KB per tap
 constexpr int CV_PRODUCERS = 128;
 constexpr int CV_THREADS = 288;
@@ -91,7 +91,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < CV_NS; ++s) {
-      mbar_init(bar_full + 8 * s, CV_PRODUCERS);
+      mbar_init(bar_full + 8 * s, 32);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -120,15 +120,19 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
 
   if (warp < 4) {
     // ===================== producers =====================
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      const int s = tl % CV_NS;
-      if (tl >= CV_NS) mbar_wait(bar_empty + 8 * s, ((tl / CV_NS) - 1) & 1);
+    // Warp w owns stage w and the tiles tl == w (mod 4): it waits for its stage to drain, streams the
+    // halo tile in, waits for ITS copies only and publishes.  The four warps are independent, so up
+    // to four tiles are in flight and a late MMA never delays the publication of a landed tile.
+    for (int tl = warp; tl < my_tiles; tl += CV_NS) {
+      const int u = tl / CV_NS;
+      if (u >= 1) mbar_wait(bar_empty + 8 * warp, (u - 1) & 1);
       const int tile = first + tl * (int)gridDim.x;
       const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
       const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
       const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
-      const uint32_t stage = sA + s * CV_ASTAGE;
-      for (int i = tid; i < CV_HROWS * 8; i += CV_PRODUCERS) {
+      const uint32_t stage = sA + warp * CV_ASTAGE;
+#pragma unroll 4
+      for (int i = lane; i < CV_HROWS * 8; i += 32) {
         const int p = i >> 3, ch = i & 7;
         const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
         const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
@@ -136,15 +140,11 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
         cp_async_16_zfill(stage + ch * CV_PLANE + p * 16, src, ok);
       }
       cp_async_commit();
-      if (tl >= 1) {                       // tile tl-1 has landed: publish it (keeps one stage in flight)
-        cp_async_wait<1>();
-        fence_proxy_async_smem();
-        mbar_arrive(bar_full + 8 * ((tl - 1) % CV_NS));
-      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      mbar_arrive(bar_full + 8 * warp);
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    mbar_arrive(bar_full + 8 * ((my_tiles - 1) % CV_NS));
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -152,21 +152,22 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_CH);
+      const uint64_t b_base = umma_desc_sw128_kmajor(sB);
       for (int tl = 0; tl < my_tiles; ++tl) {
         const int s = tl % CV_NS, buf = tl & 1;
         if (tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
         mbar_wait(bar_full + 8 * s, (tl / CV_NS) & 1);
         tc_fence_after();
-        const uint32_t stage = sA + s * CV_ASTAGE;
+        const uint64_t a_base = umma_desc_nosw_kmajor(sA + s * CV_ASTAGE, CV_PLANE);
         const uint32_t d = tmem_d + buf * CV_CH;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const uint32_t a0 = stage + (dbg == 2 ? 0 : ((t / 3) * CV_PW + (t % 3)) * 16);
-          const uint64_t bdesc = umma_desc_sw128_kmajor(sB + t * CV_BTILE);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_desc_nosw_kmajor(a0 + 2 * k * CV_PLANE, CV_PLANE);
-            if (dbg != 1 || (t | k) == 0) umma_bf16(d, adesc, bdesc + 2 * k, IDESC, (t | k) != 0);
+            // descriptors differ from the bases only in the 16-byte-granular start address field
+            const uint64_t adesc = a_base + (uint64_t)(((dbg == 2 ? 0 : ((t / 3) * CV_PW + (t % 3)) * 16) + 2 * k * CV_PLANE) >> 4);
+            const uint64_t bdesc = b_base + (uint64_t)((t * CV_BTILE) >> 4) + 2 * k;
+            if (dbg != 1 || (t | k) == 0) umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
           }
         }
         umma_commit(bar_empty + 8 * s);
