@@ -18,6 +18,8 @@ FLOW_N2HW, FLOW_NHW2 = 0, 1
 PAD_ZEROS, PAD_BORDER = 0, 1
 DCN_FORCE_GENERIC = 1
 DCN_FORCE_V1 = 2
+DCN_FORCE_WS = 4
+DCN_BLEND_FP32 = 8
 
 Strides = c_int64 * 4
 _P64 = POINTER(c_int64)

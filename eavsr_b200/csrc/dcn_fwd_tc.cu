@@ -18,6 +18,7 @@
 // (2 per SM when shared memory allows) striding over tiles.
 #include "common.cuh"
 #include "dcn_fwd_ws.cuh"
+#include "dcn_fwd_win.cuh"
 
 namespace eavsr {
 
@@ -318,6 +319,27 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
   const int grid = total < sms * per_sm ? total : sms * per_sm;
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
+  if constexpr (DG <= 8 && !SPLIT) {
+    if (!(flags & (EAVSR_DCN_FORCE_V1 | EAVSR_DCN_FORCE_WS)) && (long long)h * w * CH < (1ll << 31)) {
+      // third generation: shared-memory window gather (bf16)
+      const bool vecw = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
+      const int tiles_x = (w + win::TW - 1) / win::TW, tiles_y = (h + win::TH - 1) / win::TH;
+      const int tpi = tiles_x * tiles_y, tot = tpi * n;
+      const int g3 = tot < sms ? tot : sms;
+      const bool b16 = !(flags & EAVSR_DCN_BLEND_FP32);
+      void (*k)(const __nv_bfloat16*, const float*, const float*, const uint8_t*, const __nv_bfloat16*,
+                __nv_bfloat16*, int, int, long long, long long, int, int, int) =
+          vecw ? (b16 ? win::dcn_fwd_win_kernel<DG, true, true> : win::dcn_fwd_win_kernel<DG, true, false>)
+               : (b16 ? win::dcn_fwd_win_kernel<DG, false, true> : win::dcn_fwd_win_kernel<DG, false, false>);
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, win::Smem::DYN);
+      if (e != cudaSuccess) { set_error("dcn_forward(win): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+      k<<<g3, win::THREADS, win::Smem::DYN, st>>>((const __nv_bfloat16*)x, offset, mask, (const uint8_t*)workspace,
+                                                 (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0], os[0],
+                                                 tiles_x, tpi, tot);
+      return check_launch("dcn_forward(win)");
+    }
+  }
   if constexpr (DG <= 8) {
     if (!(flags & EAVSR_DCN_FORCE_V1)) {       // warp-specialised second-generation kernel
       using WS = ws::Smem<SPLIT>;

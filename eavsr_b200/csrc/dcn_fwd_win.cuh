@@ -1,0 +1,344 @@
+// Third-generation tcgen05 DCNv2 forward (bf16 features, deform_groups <= 8): the gather reads a
+// shared-memory WINDOW of x instead of going through L1.
+//
+// Why (ncu, profiles/r1_dcn_fwd_ws_ncu.txt): with per-group offsets every lane of a gather request
+// touches its own 128-byte line but uses 16 bytes of it -- 23 sectors per request, L1 throughput
+// 55-70 %, L1 hit rate 14-38 %.  The 4 608 gathered bytes per output pixel are 36x the 128 bytes of x
+// that pixel owns, i.e. the reuse is there, L1 just cannot serve it at 16-byte granularity.
+// Shared memory can: with pixel-major rows of 128 B the 8 lanes of a quarter-warp are the 8 channel
+// chunks, i.e. 8 distinct 16-byte bank groups whatever pixels they hit -> conflict-free LDS.128.
+//
+//   * tile = 8 x 16 output pixels (M = 128); window = the tile plus a 5-pixel apron (18 x 26 pixels,
+//     58.5 KB), double buffered, filled by one lane with cp.async.bulk row copies (TMA engine) for the
+//     NEXT tile while this one is gathered.  Out-of-image rows/columns are never loaded: corners
+//     outside the image have weight 0 and their clamped address is inside the loaded part.
+//   * a sample whose four corners are not all inside the window (|offset| > ~3 px) falls back to the
+//     global-memory gather of the previous kernel -- correct for any offset, fast for real ones.
+//   * 16 producer warps (2 items per thread per tap) + 1 MMA/loader warp; bf16x2 HFMA2 blend
+//     (template BLEND16) or fp32 blend; per-warp cp.async staging of offsets/masks; A ring of 2
+//     stages; per-tap weight tiles through a 3-stage bulk-copy ring; 2 TMEM accumulators.
+#pragma once
+#include "common.cuh"
+
+namespace eavsr {
+namespace win {
+
+constexpr int PWARPS = 16;
+constexpr int THREADS = (PWARPS + 1) * 32;   // 544
+constexpr int TH = 8, TW = 16;               // tile
+constexpr int PAD = 5;
+constexpr int WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 18 x 26 window
+constexpr int WIN_BYTES = WH * WW * 128;     // 59 904
+constexpr int CH = 64, TAPS = 9;
+constexpr int A_TILE = 128 * CH * 2;         // 16 KB
+constexpr int B_TILE = CH * CH * 2;          // 8 KB
+constexpr int NSA = 2, NSB = 3;
+constexpr int PLW = 12;                      // staged offset plane: 8 rows + 4 pad words
+constexpr int MAX_PLANES = 24;
+constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 1152 B
+constexpr int TMEM_COLS = 128;
+
+struct Smem {
+  static constexpr int WIN_OFF = 0;
+  static constexpr int A_OFF = WIN_OFF + 2 * WIN_BYTES;                    // 119 808 (1024-aligned: 117 KB)
+  static constexpr int B_OFF = A_OFF + NSA * A_TILE;
+  static constexpr int OFFS_OFF = B_OFF + NSB * B_TILE;
+  static constexpr int BAR_OFF = OFFS_OFF + PWARPS * 2 * OFF_WARP_BUF;
+  // full[NSA], empty[NSA], bfull[NSB], accf[2], acce[2], winf[2], wine[2]; tmem slot
+  static constexpr int NBARS = 2 * NSA + NSB + 8;
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+  static constexpr int DYN = TOTAL + 1024;
+};
+static_assert(Smem::A_OFF % 1024 == 0, "A stages must be 1024-byte aligned for the 128B swizzle");
+
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;\n" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t hfma2_bf16(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;\n" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int DG, bool VEC_OFF, bool BLEND16>
+__global__ void __launch_bounds__(THREADS, 1)
+dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ offset,
+                   const float* __restrict__ mask, const uint8_t* __restrict__ wpacked,
+                   const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
+                   long long xs_n, long long os_n, int tiles_x, int tiles_per_img, int total_tiles) {
+  static_assert(DG <= 8, "window kernel: deform_groups <= 8");
+  constexpr int NPLANES = 3 * DG;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t sWin = sbase + Smem::WIN_OFF, sA = sbase + Smem::A_OFF, sB = sbase + Smem::B_OFF;
+  const uint32_t bars = sbase + Smem::BAR_OFF;
+  const uint32_t bar_full = bars, bar_empty = bar_full + NSA * 8, bar_bfull = bar_empty + NSA * 8;
+  const uint32_t bar_accf = bar_bfull + NSB * 8, bar_acce = bar_accf + 16;
+  const uint32_t bar_winf = bar_acce + 16, bar_wine = bar_winf + 16;
+  const uint32_t tmem_slot_addr = bar_wine + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::BAR_OFF + Smem::NBARS * 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W;
+  if (tid == 0) {
+    for (int s = 0; s < NSA; ++s) { mbar_init(bar_full + 8 * s, PWARPS); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < NSB; ++s) mbar_init(bar_bfull + 8 * s, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf + 8 * b, 1);
+      mbar_init(bar_acce + 8 * b, PWARPS);
+      mbar_init(bar_winf + 8 * b, 1);
+      mbar_init(bar_wine + 8 * b, PWARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == PWARPS) tmem_alloc<TMEM_COLS>(tmem_slot_addr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int first = blockIdx.x;
+  const int my_tiles = (total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_iters = my_tiles * TAPS;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, CH);
+
+  auto tile_coords = [&](int tl, int& n, int& ty0, int& tx0) {
+    const int tile = first + tl * (int)gridDim.x;
+    n = tile / tiles_per_img;
+    const int rem = tile - n * tiles_per_img;
+    ty0 = (rem / tiles_x) * TH;
+    tx0 = (rem % tiles_x) * TW;
+  };
+
+  if (warp == PWARPS) {
+    // ============ MMA issuer + weight-tile loader + window loader (one lane) ============
+    if (lane == 0) {
+      auto issue_b = [&](int j) {
+        const uint32_t bar = bar_bfull + 8 * (j % NSB);
+        mbar_arrive_expect_tx(bar, B_TILE);
+        bulk_g2s(sB + (j % NSB) * B_TILE, wpacked + (size_t)(j % TAPS) * B_TILE, B_TILE, bar);
+      };
+      auto load_window = [&](int tl) {
+        int n, ty0, tx0;
+        tile_coords(tl, n, ty0, tx0);
+        const int wy0 = ty0 - PAD, wx0 = tx0 - PAD;
+        const int gx0 = max(wx0, 0), gx1 = min(wx0 + WW, W);
+        const int gy0 = max(wy0, 0), gy1 = min(wy0 + WH, H);
+        const uint32_t bar = bar_winf + 8 * (tl & 1);
+        const uint32_t row_bytes = (uint32_t)(gx1 - gx0) * 128u;
+        mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)(gy1 - gy0));
+        const __nv_bfloat16* xn = x + (size_t)n * xs_n;
+        const uint32_t dst0 = sWin + (tl & 1) * WIN_BYTES;
+        for (int gy = gy0; gy < gy1; ++gy)
+          bulk_g2s(dst0 + ((gy - wy0) * WW + (gx0 - wx0)) * 128, xn + ((size_t)gy * W + gx0) * CH, row_bytes, bar);
+      };
+      load_window(0);
+      for (int j = 0; j < NSB && j < n_iters; ++j) issue_b(j);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % NSA, sb = it % NSB;
+        const int tap = it % TAPS, tl = it / TAPS, buf = tl & 1;
+        if (it >= 1 && it - 1 + NSB < n_iters) {           // B stage of it-1 is free once MMA(it-1) retired
+          mbar_wait(bar_empty + 8 * ((it - 1) % NSA), ((it - 1) / NSA) & 1);
+          issue_b(it - 1 + NSB);
+        }
+        if (tap == 0 && tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, (it / NSA) & 1);
+        if (tap == 0 && tl + 1 < my_tiles) {               // producers have left tile tl-1: refill its window
+          if (tl >= 1) mbar_wait(bar_wine + 8 * ((tl + 1) & 1), (((tl + 1) >> 1) - 1) & 1);
+          load_window(tl + 1);
+        }
+        mbar_wait(bar_bfull + 8 * sb, (it / NSB) & 1);
+        tc_fence_after();
+        const uint64_t a_d = umma_desc_sw128_kmajor(sA + s * A_TILE), b_d = umma_desc_sw128_kmajor(sB + sb * B_TILE);
+        const uint32_t d = tmem_d + buf * CH;
+#pragma unroll
+        for (int k = 0; k < CH / 16; ++k) umma_bf16(d, a_d + 2 * k, b_d + 2 * k, IDESC, (tap | k) != 0);
+        umma_commit(bar_empty + 8 * s);
+        if (tap == TAPS - 1) umma_commit(bar_accf + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============ producers: window gather -> blend -> swizzled A stage ============
+    const int q = lane >> 3, l = lane & 7;
+    const int grp = (l * DG) / 8;
+    const int wrow = warp >> 1, wcol = (warp & 1) * 8;       // this warp: tile row wrow, columns wcol..wcol+7
+    const uint32_t offBase = sbase + Smem::OFFS_OFF + warp * 2 * OFF_WARP_BUF;
+    const float* offF = reinterpret_cast<const float*>(smem + Smem::OFFS_OFF + warp * 2 * OFF_WARP_BUF);
+
+    auto prefetch_offsets = [&](int it) {
+      if (it < n_iters) {
+        int n, ty0, tx0;
+        tile_coords(it / TAPS, n, ty0, tx0);
+        const int tap = it % TAPS;
+        const int gy = ty0 + wrow, gx = tx0 + wcol;
+        const uint32_t dst0 = offBase + (it & 1) * OFF_WARP_BUF;
+        if (gy < H) {
+          constexpr int PER_PLANE = VEC_OFF ? 2 : 8;
+          for (int i = lane; i < NPLANES * PER_PLANE; i += 32) {
+            const int plane = i / PER_PLANE, e = i - plane * PER_PLANE;
+            const int comp = plane / DG, g = plane - comp * DG;
+            const int col = VEC_OFF ? e * 4 : e;
+            if (gx + col < W) {
+              const size_t pix = (size_t)gy * W + gx + col;
+              const float* src = (comp < 2)
+                  ? offset + ((size_t)(n * DG + g) * TAPS + tap) * 2 * HW + (size_t)comp * HW + pix
+                  : mask + ((size_t)(n * DG + g) * TAPS + tap) * HW + pix;
+              const uint32_t dst = dst0 + (plane * PLW + col) * 4;
+              if (VEC_OFF) cp_async_16(dst, src); else cp_async_4(dst, src);
+            }
+          }
+        }
+      }
+      cp_async_commit();
+    };
+
+    auto epilogue = [&](int tl) {
+      const int buf = tl & 1;
+      mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
+      tc_fence_after();
+      const int qd = warp & 3, cq = warp >> 2;                // TMEM lane quadrant, 16-column quarter
+      uint32_t acc[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+          : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+            "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+            "=r"(acc[14]), "=r"(acc[15])
+          : "r"(tmem_d + ((uint32_t)(qd * 32) << 16) + buf * CH + cq * 16)
+          : "memory");
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+      int n, ty0, tx0;
+      tile_coords(tl, n, ty0, tx0);
+      const int m = qd * 32 + lane;
+      const int gy = ty0 + (m >> 4), gx = tx0 + (m & 15);
+      if (gy < H && gx < W) {
+        __nv_bfloat16* op = out + (size_t)n * os_n + ((size_t)gy * W + gx) * CH + cq * 16;
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(acc[e]) + (bias ? __bfloat162float(bias[cq * 16 + e]) : 0.f);
+#pragma unroll
+        for (int e = 0; e < 16; e += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(f[e], f[e + 1]); u.y = pack_bf16x2(f[e + 2], f[e + 3]);
+          u.z = pack_bf16x2(f[e + 4], f[e + 5]); u.w = pack_bf16x2(f[e + 6], f[e + 7]);
+          *reinterpret_cast<uint4*>(op + e) = u;
+        }
+      }
+    };
+
+    prefetch_offsets(0);
+    prefetch_offsets(1);
+    int n = 0, ty0 = 0, tx0 = 0;
+    const __nv_bfloat16* xn = x;
+    for (int it = 0; it < n_iters; ++it) {
+      const int tap = it % TAPS, tl = it / TAPS;
+      if (tap == 0) {
+        tile_coords(tl, n, ty0, tx0);
+        xn = x + (size_t)n * xs_n;
+        mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);     // this tile's window has landed
+      }
+      cp_async_wait<1>();                                      // offsets of `it` have landed
+      __syncwarp();
+      const float* so = offF + (it & 1) * (OFF_WARP_BUF / 4);
+      const int ti = tap / 3, tj = tap - ti * 3;
+      const int wy0 = ty0 - PAD, wx0 = tx0 - PAD;
+      const uint32_t win = sWin + (tl & 1) * WIN_BYTES + l * 16;
+      const int gy = ty0 + wrow;
+      uint32_t res[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = j * 4 + q;
+        const int gx = tx0 + wcol + col;
+        const float dy = so[(0 * DG + grp) * PLW + col];
+        const float dx = so[(1 * DG + grp) * PLW + col];
+        const float mk = so[(2 * DG + grp) * PLW + col];
+        const bool live = gy < H && gx < W;
+        const float py = live ? (float)(gy - 1 + ti) + dy : -100000.f;
+        const float px = (float)(gx - 1 + tj) + dx;
+        const float fy = floorf(py), fx = floorf(px);
+        const float ly = py - fy, lx = px - fx;
+        const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)H), x0 = (int)fminf(fmaxf(fx, -2.f), (float)W);
+        const float wy0f = ((unsigned)y0 < (unsigned)H) ? mk * (1.f - ly) : 0.f;
+        const float wy1f = ((unsigned)(y0 + 1) < (unsigned)H) ? mk * ly : 0.f;
+        const float wx0f = ((unsigned)x0 < (unsigned)W) ? (1.f - lx) : 0.f;
+        const float wx1f = ((unsigned)(x0 + 1) < (unsigned)W) ? lx : 0.f;
+        const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
+        const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+        const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+        const int ry0 = cy0 - wy0, ry1 = cy1 - wy0, rx0 = cx0 - wx0, rx1 = cx1 - wx0;
+        const bool inwin = (unsigned)ry0 < (unsigned)WH && (unsigned)ry1 < (unsigned)WH &&
+                           (unsigned)rx0 < (unsigned)WW && (unsigned)rx1 < (unsigned)WW;
+        uint4 v00, v01, v10, v11;
+        if (inwin) {
+          const uint32_t a00 = win + (uint32_t)(ry0 * WW + rx0) * 128u;
+          const uint32_t sx = (uint32_t)(rx1 - rx0) * 128u, sy = (uint32_t)(ry1 - ry0) * (WW * 128u);
+          v00 = lds128(a00); v01 = lds128(a00 + sx); v10 = lds128(a00 + sy); v11 = lds128(a00 + sy + sx);
+        } else {                                               // far sample: global gather (rare)
+          const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
+          const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
+          v00 = __ldg(reinterpret_cast<const uint4*>(xn + b00));
+          v01 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
+          v10 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
+          v11 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
+        }
+        const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
+        const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+        if (BLEND16) {
+          const uint32_t p00 = pack_bf16x2(w00, w00), p01 = pack_bf16x2(w01, w01);
+          const uint32_t p10 = pack_bf16x2(w10, w10), p11 = pack_bf16x2(w11, w11);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            res[j][e] = hfma2_bf16(p11, d[e], hfma2_bf16(p10, c[e], hfma2_bf16(p01, b[e], hmul2_bf16(p00, a[e]))));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = w00 * bf16lo_to_f32(a[e]) + w01 * bf16lo_to_f32(b[e]) + w10 * bf16lo_to_f32(c[e]) +
+                             w11 * bf16lo_to_f32(d[e]);
+            const float hi = w00 * bf16hi_to_f32(a[e]) + w01 * bf16hi_to_f32(b[e]) + w10 * bf16hi_to_f32(c[e]) +
+                             w11 * bf16hi_to_f32(d[e]);
+            res[j][e] = pack_bf16x2(lo, hi);
+          }
+        }
+      }
+      __syncwarp();                                            // all lanes are done with offset buffer it&1
+      prefetch_offsets(it + 2);
+      if (it >= NSA) mbar_wait(bar_empty + 8 * (it % NSA), ((it / NSA) - 1) & 1);
+      const uint32_t aStage = sA + (it % NSA) * A_TILE;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int m = wrow * 16 + wcol + j * 4 + q;
+        const uint32_t dst = aStage + sw128_offset(m, l * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(res[j][0]), "r"(res[j][1]),
+                     "r"(res[j][2]), "r"(res[j][3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_full + 8 * (it % NSA));
+        if (tap == TAPS - 1) mbar_arrive(bar_wine + 8 * (tl & 1));   // this warp is done with the window
+      }
+      if (tap == 1 && tl >= 1) epilogue(tl - 1);
+    }
+    cp_async_wait<0>();
+    epilogue(my_tiles - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PWARPS) tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+}  // namespace win
+}  // namespace eavsr

@@ -45,6 +45,8 @@ extern "C" {
 
 #define EAVSR_DCN_FORCE_GENERIC 1u /* flags bit: skip the tcgen05 path (validation only) */
 #define EAVSR_DCN_FORCE_V1 2u      /* flags bit: first-generation tcgen05 kernel (A/B timing only) */
+#define EAVSR_DCN_FORCE_WS 4u      /* flags bit: second-generation (warp-specialised, L1 gather) kernel */
+#define EAVSR_DCN_BLEND_FP32 8u    /* flags bit: window kernel with fp32 blend instead of bf16x2 HFMA2 */
 
 /* ---- library ------------------------------------------------------------------------ */
 int eavsr_version(void);

@@ -157,11 +157,16 @@ def test_dcn_tc_kernels_agree(cuda, shape):
     c = _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_GENERIC)
     assert max_err(a, c) < 1e-4
     assert max_err(b, c) < 1e-4
-    xb = args[0].bfloat16()
-    a16 = _ModulatedDeformConv2dFn.apply(xb, *args[1:3], wgt.to(cuda).bfloat16(), bias.to(cuda).bfloat16(), 1, 1, 1, 1, 8, 0)
-    b16 = _ModulatedDeformConv2dFn.apply(xb, *args[1:3], wgt.to(cuda).bfloat16(), bias.to(cuda).bfloat16(), 1, 1, 1, 1, 8,
-                                         L.DCN_FORCE_V1)
-    assert torch.equal(a16, b16)            # same arithmetic, bit-identical
+    # bf16: window kernel (bf16x2 blend / fp32 blend), warp-specialised L1 kernel, first-generation kernel
+    xb, wb, bb = args[0].bfloat16(), wgt.to(cuda).bfloat16(), bias.to(cuda).bfloat16()
+    run = lambda fl: _ModulatedDeformConv2dFn.apply(xb, *args[1:3], wb, bb, 1, 1, 1, 1, 8, fl)     # noqa: E731
+    w16, w32, ws, v1 = run(0), run(L.DCN_BLEND_FP32), run(L.DCN_FORCE_WS), run(L.DCN_FORCE_V1)
+    assert torch.equal(ws, v1)              # same arithmetic, bit-identical
+    assert torch.equal(w32, v1)             # the window only changes where the corners are read from
+    ref = _dcn_ref(xb, off, mask, wb, bb, dg=8)
+    assert rel_err(w32, ref) < BF16_REL
+    assert rel_err(w16, ref) < BF16_REL     # bf16x2 HFMA2 blend: a few more roundings, same tolerance
+    print(f"dcn bf16 rel err: fp32-blend {rel_err(w32, ref):.2e}  bf16x2-blend {rel_err(w16, ref):.2e}")
 
 
 @pytest.mark.parametrize("cfg", [
