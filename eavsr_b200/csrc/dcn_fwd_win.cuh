@@ -32,10 +32,14 @@ constexpr int WIN_BYTES = WH * WW * 128;     // 59 904
 constexpr int CH = 64, TAPS = 9;
 constexpr int A_TILE = 128 * CH * 2;         // 16 KB
 constexpr int B_TILE = CH * CH * 2;          // 8 KB
-constexpr int NSA = 2, NSB = 3;
-constexpr int PLW = 12;                      // staged offset plane: 8 rows + 4 pad words
+constexpr int NSA = 2, NSB = 2;
+constexpr int PLW = 8;                       // staged offset plane: 8 pixels, XOR-swizzled (no padding)
 constexpr int MAX_PLANES = 24;
-constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 1152 B
+constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 768 B
+// Offsets/masks come from HBM with ~1.5 us latency and each (tile, tap) needs 12 KB of them; with a
+// prefetch distance of 2 taps the first versions had only ~24 KB per SM in flight (Little: 2.4 TB/s
+// for the whole chip = the ~100 us floor every earlier kernel hit).  4 buffers -> distance 3.
+constexpr int NOB = 4;
 constexpr int TMEM_COLS = 128;
 
 struct Smem {
@@ -43,7 +47,7 @@ struct Smem {
   static constexpr int A_OFF = WIN_OFF + 2 * WIN_BYTES;                    // 119 808 (1024-aligned: 117 KB)
   static constexpr int B_OFF = A_OFF + NSA * A_TILE;
   static constexpr int OFFS_OFF = B_OFF + NSB * B_TILE;
-  static constexpr int BAR_OFF = OFFS_OFF + PWARPS * 2 * OFF_WARP_BUF;
+  static constexpr int BAR_OFF = OFFS_OFF + PWARPS * NOB * OFF_WARP_BUF;
   // full[NSA], empty[NSA], bfull[NSB], accf[2], acce[2], winf[2], wine[2]; tmem slot
   static constexpr int NBARS = 2 * NSA + NSB + 8;
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
@@ -171,8 +175,11 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     const int q = lane >> 3, l = lane & 7;
     const int grp = (l * DG) / 8;
     const int wrow = warp >> 1, wcol = (warp & 1) * 8;       // this warp: tile row wrow, columns wcol..wcol+7
-    const uint32_t offBase = sbase + Smem::OFFS_OFF + warp * 2 * OFF_WARP_BUF;
-    const float* offF = reinterpret_cast<const float*>(smem + Smem::OFFS_OFF + warp * 2 * OFF_WARP_BUF);
+    const uint32_t offBase = sbase + Smem::OFFS_OFF + warp * NOB * OFF_WARP_BUF;
+    const float* offF = reinterpret_cast<const float*>(smem + Smem::OFFS_OFF + warp * NOB * OFF_WARP_BUF);
+    // column swizzle of the staged planes: groups 4..7 swap the two 4-pixel halves, which makes the
+    // 32 lanes (8 groups x 4 pixels) of one load hit 32 distinct banks without padding
+    const int colx = (grp >> 2) << 2;
 
     auto prefetch_offsets = [&](int it) {
       if (it < n_iters) {
@@ -180,7 +187,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         tile_coords(it / TAPS, n, ty0, tx0);
         const int tap = it % TAPS;
         const int gy = ty0 + wrow, gx = tx0 + wcol;
-        const uint32_t dst0 = offBase + (it & 1) * OFF_WARP_BUF;
+        const uint32_t dst0 = offBase + (it % NOB) * OFF_WARP_BUF;
         if (gy < H) {
           constexpr int PER_PLANE = VEC_OFF ? 2 : 8;
           for (int i = lane; i < NPLANES * PER_PLANE; i += 32) {
@@ -192,7 +199,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
               const float* src = (comp < 2)
                   ? offset + ((size_t)(n * DG + g) * TAPS + tap) * 2 * HW + (size_t)comp * HW + pix
                   : mask + ((size_t)(n * DG + g) * TAPS + tap) * HW + pix;
-              const uint32_t dst = dst0 + (plane * PLW + col) * 4;
+              const uint32_t dst = dst0 + (plane * PLW + (col ^ ((g >> 2) << 2))) * 4;
               if (VEC_OFF) cp_async_16(dst, src); else cp_async_4(dst, src);
             }
           }
@@ -240,6 +247,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
     prefetch_offsets(0);
     prefetch_offsets(1);
+    prefetch_offsets(2);
     int n = 0, ty0 = 0, tx0 = 0;
     const __nv_bfloat16* xn = x;
     for (int it = 0; it < n_iters; ++it) {
@@ -249,9 +257,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         xn = x + (size_t)n * xs_n;
         mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);     // this tile's window has landed
       }
-      cp_async_wait<1>();                                      // offsets of `it` have landed
-      __syncwarp();
-      const float* so = offF + (it & 1) * (OFF_WARP_BUF / 4);
+      cp_async_wait<2>();                                      // offsets of `it` have landed
+      __syncwarp();                                            // ... and everyone left buffer (it-1) % NOB
+      prefetch_offsets(it + 3);
+      const float* so = offF + (it % NOB) * (OFF_WARP_BUF / 4);
       const int ti = tap / 3, tj = tap - ti * 3;
       const int wy0 = ty0 - PAD, wx0 = tx0 - PAD;
       const uint32_t win = sWin + (tl & 1) * WIN_BYTES + l * 16;
@@ -261,9 +270,9 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       for (int j = 0; j < 2; ++j) {
         const int col = j * 4 + q;
         const int gx = tx0 + wcol + col;
-        const float dy = so[(0 * DG + grp) * PLW + col];
-        const float dx = so[(1 * DG + grp) * PLW + col];
-        const float mk = so[(2 * DG + grp) * PLW + col];
+        const float dy = so[(0 * DG + grp) * PLW + (col ^ colx)];
+        const float dx = so[(1 * DG + grp) * PLW + (col ^ colx)];
+        const float mk = so[(2 * DG + grp) * PLW + (col ^ colx)];
         const bool live = gy < H && gx < W;
         const float py = live ? (float)(gy - 1 + ti) + dy : -100000.f;
         const float px = (float)(gx - 1 + tj) + dx;
@@ -312,8 +321,6 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
           }
         }
       }
-      __syncwarp();                                            // all lanes are done with offset buffer it&1
-      prefetch_offsets(it + 2);
       if (it >= NSA) mbar_wait(bar_empty + 8 * (it % NSA), ((it / NSA) - 1) & 1);
       const uint32_t aStage = sA + (it % NSA) * A_TILE;
 #pragma unroll

@@ -163,7 +163,7 @@ def test_dcn_tc_kernels_agree(cuda, shape):
     w16, w32, ws, v1 = run(0), run(L.DCN_BLEND_FP32), run(L.DCN_FORCE_WS), run(L.DCN_FORCE_V1)
     assert torch.equal(ws, v1)              # same arithmetic, bit-identical
     assert torch.equal(w32, v1)             # the window only changes where the corners are read from
-    ref = _dcn_ref(xb, off, mask, wb, bb, dg=8)
+    ref = _dcn_ref(xb.cpu(), off, mask, wb.cpu(), bb.cpu(), dg=8)
     assert rel_err(w32, ref) < BF16_REL
     assert rel_err(w16, ref) < BF16_REL     # bf16x2 HFMA2 blend: a few more roundings, same tolerance
     print(f"dcn bf16 rel err: fp32-blend {rel_err(w32, ref):.2e}  bf16x2-blend {rel_err(w16, ref):.2e}")
