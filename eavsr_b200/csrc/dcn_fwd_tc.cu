@@ -320,7 +320,7 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
   if constexpr (DG <= 8 && !SPLIT) {
-    if (!(flags & (EAVSR_DCN_FORCE_V1 | EAVSR_DCN_FORCE_WS)) && (long long)h * w * CH < (1ll << 31)) {
+    if (!(flags & (EAVSR_DCN_FORCE_V1 | EAVSR_DCN_FORCE_WS)) && (long long)h * w <= (1ll << 24)) {
       // third generation: shared-memory window gather (bf16)
       const bool vecw = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
                         ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);

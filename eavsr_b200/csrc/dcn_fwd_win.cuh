@@ -32,7 +32,7 @@ constexpr int WIN_BYTES = WH * WW * 128;     // 59 904
 constexpr int CH = 64, TAPS = 9;
 constexpr int A_TILE = 128 * CH * 2;         // 16 KB
 constexpr int B_TILE = CH * CH * 2;          // 8 KB
-constexpr int NSA = 2, NSB = 2;
+constexpr int NSA = 2, NSB = 3;
 constexpr int PLW = 8;                       // staged offset plane: 8 pixels, XOR-swizzled (no padding)
 constexpr int MAX_PLANES = 24;
 constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 768 B
@@ -103,6 +103,11 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     }
     fence_mbar_init();
   }
+  // window cells that lie outside the image are never loaded; zero both buffers once so that whatever
+  // they hold later (stale x) is finite and their 0 weights really give 0
+  for (int i = tid; i < 2 * WIN_BYTES / 16; i += THREADS)
+    *reinterpret_cast<uint4*>(smem + Smem::WIN_OFF + i * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   if (warp == PWARPS) tmem_alloc<TMEM_COLS>(tmem_slot_addr);
   tc_fence_before();
   __syncthreads();
@@ -146,13 +151,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       };
       load_window(0);
       for (int j = 0; j < NSB && j < n_iters; ++j) issue_b(j);
+      const uint64_t a_base = umma_desc_sw128_kmajor(sA), b_base = umma_desc_sw128_kmajor(sB);
+      int tap = 0, tl = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % NSA, sb = it % NSB;
-        const int tap = it % TAPS, tl = it / TAPS, buf = tl & 1;
-        if (it >= 1 && it - 1 + NSB < n_iters) {           // B stage of it-1 is free once MMA(it-1) retired
-          mbar_wait(bar_empty + 8 * ((it - 1) % NSA), ((it - 1) / NSA) & 1);
-          issue_b(it - 1 + NSB);
-        }
+        const int s = it % NSA, sb = it % NSB, buf = tl & 1;
         if (tap == 0 && tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
         mbar_wait(bar_full + 8 * s, (it / NSA) & 1);
         if (tap == 0 && tl + 1 < my_tiles) {               // producers have left tile tl-1: refill its window
@@ -161,12 +163,20 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         }
         mbar_wait(bar_bfull + 8 * sb, (it / NSB) & 1);
         tc_fence_after();
-        const uint64_t a_d = umma_desc_sw128_kmajor(sA + s * A_TILE), b_d = umma_desc_sw128_kmajor(sB + sb * B_TILE);
+        // descriptors differ from the stage-0 ones only in the 16-byte-granular start address field
+        const uint64_t a_d = a_base + (uint64_t)((s * A_TILE) >> 4), b_d = b_base + (uint64_t)((sb * B_TILE) >> 4);
         const uint32_t d = tmem_d + buf * CH;
 #pragma unroll
         for (int k = 0; k < CH / 16; ++k) umma_bf16(d, a_d + 2 * k, b_d + 2 * k, IDESC, (tap | k) != 0);
         umma_commit(bar_empty + 8 * s);
         if (tap == TAPS - 1) umma_commit(bar_accf + 8 * buf);
+        // refill the weight ring behind the MMAs: the stage of it-1 is free once MMA(it-1) retired, and
+        // MMA(it) is already queued, so the tensor pipe never waits for this thread
+        if (it >= 1 && it - 1 + NSB < n_iters) {
+          mbar_wait(bar_empty + 8 * ((it - 1) % NSA), ((it - 1) / NSA) & 1);
+          issue_b(it - 1 + NSB);
+        }
+        if (++tap == TAPS) { tap = 0; ++tl; }
       }
     }
     __syncwarp();
@@ -181,28 +191,45 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     // 32 lanes (8 groups x 4 pixels) of one load hit 32 distinct banks without padding
     const int colx = (grp >> 2) << 2;
 
-    auto prefetch_offsets = [&](int it) {
-      if (it < n_iters) {
-        int n, ty0, tx0;
-        tile_coords(it / TAPS, n, ty0, tx0);
-        const int tap = it % TAPS;
-        const int gy = ty0 + wrow, gx = tx0 + wcol;
-        const uint32_t dst0 = offBase + (it % NOB) * OFF_WARP_BUF;
-        if (gy < H) {
+    // Offset/mask prefetch stream, 3 taps ahead of the gather.  Everything that needs an integer
+    // division (tile -> image / row / column) is done once per tile, not once per tap.
+    struct TileRef { int n, ty0, tx0; const float* ob; const float* mb; bool row_ok; };
+    auto make_ref = [&](int tl) {
+      TileRef r;
+      tile_coords(tl, r.n, r.ty0, r.tx0);
+      const int gy = r.ty0 + wrow, gx = r.tx0 + wcol;
+      r.row_ok = gy < H;
+      const size_t pix = (size_t)gy * W + gx;
+      r.ob = offset + (size_t)r.n * DG * TAPS * 2 * HW + pix;
+      r.mb = mask + (size_t)r.n * DG * TAPS * HW + pix;
+      return r;
+    };
+    TileRef pref = make_ref(0);          // tile of the prefetch stream
+    int p_tl = 0, p_tap = 0;
+    auto prefetch_next = [&]() {         // stages (p_tl, p_tap) into buffer (p_tl*9 + p_tap) % NOB, then advances
+      if (p_tl < my_tiles) {
+        const uint32_t dst0 = offBase + ((p_tl * TAPS + p_tap) % NOB) * OFF_WARP_BUF;
+        if (pref.row_ok) {
+          const int gx = pref.tx0 + wcol;
           constexpr int PER_PLANE = VEC_OFF ? 2 : 8;
-          for (int i = lane; i < NPLANES * PER_PLANE; i += 32) {
+#pragma unroll
+          for (int k = 0; k < (NPLANES * PER_PLANE + 31) / 32; ++k) {
+            const int i = lane + 32 * k;
             const int plane = i / PER_PLANE, e = i - plane * PER_PLANE;
             const int comp = plane / DG, g = plane - comp * DG;
             const int col = VEC_OFF ? e * 4 : e;
-            if (gx + col < W) {
-              const size_t pix = (size_t)gy * W + gx + col;
-              const float* src = (comp < 2)
-                  ? offset + ((size_t)(n * DG + g) * TAPS + tap) * 2 * HW + (size_t)comp * HW + pix
-                  : mask + ((size_t)(n * DG + g) * TAPS + tap) * HW + pix;
+            if (i < NPLANES * PER_PLANE && gx + col < W) {
+              const uint32_t rel = (comp < 2) ? (uint32_t)((g * TAPS + p_tap) * 2 + comp) * (uint32_t)HW
+                                              : (uint32_t)(g * TAPS + p_tap) * (uint32_t)HW;
+              const float* src = ((comp < 2) ? pref.ob : pref.mb) + rel + col;
               const uint32_t dst = dst0 + (plane * PLW + (col ^ ((g >> 2) << 2))) * 4;
               if (VEC_OFF) cp_async_16(dst, src); else cp_async_4(dst, src);
             }
           }
+        }
+        if (++p_tap == TAPS) {
+          p_tap = 0;
+          if (++p_tl < my_tiles) pref = make_ref(p_tl);
         }
       }
       cp_async_commit();
@@ -245,98 +272,107 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       }
     };
 
-    prefetch_offsets(0);
-    prefetch_offsets(1);
-    prefetch_offsets(2);
-    int n = 0, ty0 = 0, tx0 = 0;
-    const __nv_bfloat16* xn = x;
-    for (int it = 0; it < n_iters; ++it) {
-      const int tap = it % TAPS, tl = it / TAPS;
-      if (tap == 0) {
-        tile_coords(tl, n, ty0, tx0);
-        xn = x + (size_t)n * xs_n;
-        mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);     // this tile's window has landed
-      }
-      cp_async_wait<2>();                                      // offsets of `it` have landed
-      __syncwarp();                                            // ... and everyone left buffer (it-1) % NOB
-      prefetch_offsets(it + 3);
-      const float* so = offF + (it % NOB) * (OFF_WARP_BUF / 4);
-      const int ti = tap / 3, tj = tap - ti * 3;
+    prefetch_next();
+    prefetch_next();
+    prefetch_next();
+    int it = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      int n, ty0, tx0;
+      tile_coords(tl, n, ty0, tx0);
+      const __nv_bfloat16* xn = x + (size_t)n * xs_n;
       const int wy0 = ty0 - PAD, wx0 = tx0 - PAD;
       const uint32_t win = sWin + (tl & 1) * WIN_BYTES + l * 16;
       const int gy = ty0 + wrow;
-      uint32_t res[2][4];
+      float pyb[2], pxb[2];                                   // (y-1, x-1) of this lane's two pixels
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int col = j * 4 + q;
-        const int gx = tx0 + wcol + col;
-        const float dy = so[(0 * DG + grp) * PLW + (col ^ colx)];
-        const float dx = so[(1 * DG + grp) * PLW + (col ^ colx)];
-        const float mk = so[(2 * DG + grp) * PLW + (col ^ colx)];
-        const bool live = gy < H && gx < W;
-        const float py = live ? (float)(gy - 1 + ti) + dy : -100000.f;
-        const float px = (float)(gx - 1 + tj) + dx;
-        const float fy = floorf(py), fx = floorf(px);
-        const float ly = py - fy, lx = px - fx;
-        const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)H), x0 = (int)fminf(fmaxf(fx, -2.f), (float)W);
-        const float wy0f = ((unsigned)y0 < (unsigned)H) ? mk * (1.f - ly) : 0.f;
-        const float wy1f = ((unsigned)(y0 + 1) < (unsigned)H) ? mk * ly : 0.f;
-        const float wx0f = ((unsigned)x0 < (unsigned)W) ? (1.f - lx) : 0.f;
-        const float wx1f = ((unsigned)(x0 + 1) < (unsigned)W) ? lx : 0.f;
-        const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
-        const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
-        const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
-        const int ry0 = cy0 - wy0, ry1 = cy1 - wy0, rx0 = cx0 - wx0, rx1 = cx1 - wx0;
-        const bool inwin = (unsigned)ry0 < (unsigned)WH && (unsigned)ry1 < (unsigned)WH &&
-                           (unsigned)rx0 < (unsigned)WW && (unsigned)rx1 < (unsigned)WW;
-        uint4 v00, v01, v10, v11;
-        if (inwin) {
-          const uint32_t a00 = win + (uint32_t)(ry0 * WW + rx0) * 128u;
-          const uint32_t sx = (uint32_t)(rx1 - rx0) * 128u, sy = (uint32_t)(ry1 - ry0) * (WW * 128u);
-          v00 = lds128(a00); v01 = lds128(a00 + sx); v10 = lds128(a00 + sy); v11 = lds128(a00 + sy + sx);
-        } else {                                               // far sample: global gather (rare)
-          const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
-          const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
-          v00 = __ldg(reinterpret_cast<const uint4*>(xn + b00));
-          v01 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
-          v10 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
-          v11 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
-        }
-        const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
-        const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
-        if (BLEND16) {
-          const uint32_t p00 = pack_bf16x2(w00, w00), p01 = pack_bf16x2(w01, w01);
-          const uint32_t p10 = pack_bf16x2(w10, w10), p11 = pack_bf16x2(w11, w11);
+        const int gx = tx0 + wcol + j * 4 + q;
+        pyb[j] = (gy < H && gx < W) ? (float)(gy - 1) : -100000.f;   // dead pixel: sample rejected
+        pxb[j] = (float)(gx - 1);
+      }
+      mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);       // this tile's window has landed
+      for (int tap = 0; tap < TAPS; ++tap, ++it) {
+        cp_async_wait<2>();                                    // offsets of `it` have landed
+        __syncwarp();                                          // ... and everyone left buffer (it-1) % NOB
+        prefetch_next();
+        const float* so = offF + (it % NOB) * (OFF_WARP_BUF / 4);
+        const int ti = tap / 3, tj = tap - ti * 3;
+        uint32_t res[2][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            res[j][e] = hfma2_bf16(p11, d[e], hfma2_bf16(p10, c[e], hfma2_bf16(p01, b[e], hmul2_bf16(p00, a[e]))));
-        } else {
+        for (int j = 0; j < 2; ++j) {
+          const int col = (j * 4 + q) ^ colx;
+          const float dy = so[(0 * DG + grp) * PLW + col];
+          const float dx = so[(1 * DG + grp) * PLW + col];
+          const float mk = so[(2 * DG + grp) * PLW + col];
+          const float py = (pyb[j] + (float)ti) + dy;
+          const float px = (pxb[j] + (float)tj) + dx;
+          const float fy = floorf(py), fx = floorf(px);
+          const float ly = py - fy, lx = px - fx;
+          // cell index, saturated so that wild / NaN offsets land on "all corners outside"
+          const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)H), x0 = (int)fminf(fmaxf(fx, -2.f), (float)W);
+          const float wy0f = ((unsigned)y0 < (unsigned)H) ? mk * (1.f - ly) : 0.f;
+          const float wy1f = ((unsigned)(y0 + 1) < (unsigned)H) ? mk * ly : 0.f;
+          const float wx0f = ((unsigned)x0 < (unsigned)W) ? (1.f - lx) : 0.f;
+          const float wx1f = ((unsigned)(x0 + 1) < (unsigned)W) ? lx : 0.f;
+          const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
+          // Window test on the un-clamped cell: both rows / columns of the 2x2 cell inside the window.
+          // Window cells outside the image hold finite stale data (buffers are zeroed once) and get
+          // weight 0, so no clamping is needed on this path.
+          const int ry = y0 - wy0, rx = x0 - wx0;
+          const bool inwin = (unsigned)ry < (unsigned)(WH - 1) && (unsigned)rx < (unsigned)(WW - 1);
+          uint4 v00, v01, v10, v11;
+          if (__all_sync(0xffffffffu, inwin)) {                // warp-uniform: the common case has no LDG code
+            const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
+            v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
+          } else if (inwin) {
+            const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
+            v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
+          } else {                                             // far sample: global gather, clamped corners
+            const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+            const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+            const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
+            const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
+            v00 = __ldg(reinterpret_cast<const uint4*>(xn + b00));
+            v01 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
+            v10 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
+            v11 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
+          }
+          const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
+          const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+          if (BLEND16) {
+            const uint32_t p00 = pack_bf16x2(w00, w00), p01 = pack_bf16x2(w01, w01);
+            const uint32_t p10 = pack_bf16x2(w10, w10), p11 = pack_bf16x2(w11, w11);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = w00 * bf16lo_to_f32(a[e]) + w01 * bf16lo_to_f32(b[e]) + w10 * bf16lo_to_f32(c[e]) +
-                             w11 * bf16lo_to_f32(d[e]);
-            const float hi = w00 * bf16hi_to_f32(a[e]) + w01 * bf16hi_to_f32(b[e]) + w10 * bf16hi_to_f32(c[e]) +
-                             w11 * bf16hi_to_f32(d[e]);
-            res[j][e] = pack_bf16x2(lo, hi);
+            for (int e = 0; e < 4; ++e)
+              res[j][e] = hfma2_bf16(p11, d[e], hfma2_bf16(p10, c[e], hfma2_bf16(p01, b[e], hmul2_bf16(p00, a[e]))));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = w00 * bf16lo_to_f32(a[e]) + w01 * bf16lo_to_f32(b[e]) + w10 * bf16lo_to_f32(c[e]) +
+                               w11 * bf16lo_to_f32(d[e]);
+              const float hi = w00 * bf16hi_to_f32(a[e]) + w01 * bf16hi_to_f32(b[e]) + w10 * bf16hi_to_f32(c[e]) +
+                               w11 * bf16hi_to_f32(d[e]);
+              res[j][e] = pack_bf16x2(lo, hi);
+            }
           }
         }
-      }
-      if (it >= NSA) mbar_wait(bar_empty + 8 * (it % NSA), ((it / NSA) - 1) & 1);
-      const uint32_t aStage = sA + (it % NSA) * A_TILE;
+        if (it >= NSA) mbar_wait(bar_empty + 8 * (it % NSA), ((it / NSA) - 1) & 1);
+        const uint32_t aStage = sA + (it % NSA) * A_TILE;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int m = wrow * 16 + wcol + j * 4 + q;
-        const uint32_t dst = aStage + sw128_offset(m, l * 16);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(res[j][0]), "r"(res[j][1]),
-                     "r"(res[j][2]), "r"(res[j][3]));
+        for (int j = 0; j < 2; ++j) {
+          const int m = wrow * 16 + wcol + j * 4 + q;
+          const uint32_t dst = aStage + sw128_offset(m, l * 16);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(res[j][0]), "r"(res[j][1]),
+                       "r"(res[j][2]), "r"(res[j][3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_full + 8 * (it % NSA));
+          if (tap == TAPS - 1) mbar_arrive(bar_wine + 8 * (tl & 1));   // this warp is done with the window
+        }
+        if (tap == 1 && tl >= 1) epilogue(tl - 1);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_full + 8 * (it % NSA));
-        if (tap == TAPS - 1) mbar_arrive(bar_wine + 8 * (tl & 1));   // this warp is done with the window
-      }
-      if (tap == 1 && tl >= 1) epilogue(tl - 1);
     }
     cp_async_wait<0>();
     epilogue(my_tiles - 1);
