@@ -32,14 +32,14 @@ constexpr int WIN_BYTES = WH * WW * 128;     // 59 904
 constexpr int CH = 64, TAPS = 9;
 constexpr int A_TILE = 128 * CH * 2;         // 16 KB
 constexpr int B_TILE = CH * CH * 2;          // 8 KB
-constexpr int NSA = 2, NSB = 3;
+constexpr int NSA = 3, NSB = 2;
 constexpr int PLW = 8;                       // staged offset plane: 8 pixels, XOR-swizzled (no padding)
 constexpr int MAX_PLANES = 24;
 constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 768 B
 // Offsets/masks come from HBM with ~1.5 us latency and each (tile, tap) needs 12 KB of them; with a
 // prefetch distance of 2 taps the first versions had only ~24 KB per SM in flight (Little: 2.4 TB/s
-// for the whole chip = the ~100 us floor every earlier kernel hit).  4 buffers -> distance 3.
-constexpr int NOB = 4;
+// for the whole chip = the ~100 us floor every earlier kernel hit).  3 buffers -> distance 2 (deeper did not pay: the A ring depth did).
+constexpr int NOB = 3;
 constexpr int TMEM_COLS = 128;
 
 struct Smem {
@@ -274,7 +274,6 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
     prefetch_next();
     prefetch_next();
-    prefetch_next();
     int it = 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
       int n, ty0, tx0;
@@ -290,9 +289,24 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         pyb[j] = (gy < H && gx < W) ? (float)(gy - 1) : -100000.f;   // dead pixel: sample rejected
         pxb[j] = (float)(gx - 1);
       }
+      // Border tiles: the window cells outside the image are not loaded; zero them so that the gather
+      // needs no per-corner validity test (an outside corner reads 0, which is DCNv2's zero padding
+      // and its "p <= -1 or p >= size -> 0" rule at once).  Safe against readers of the tile that used
+      // this buffer before (tl-2): no warp is more than NSA taps behind.  All 16 producer warps take
+      // this branch together (the condition is CTA-uniform).
+      if (wy0 < 0 || wx0 < 0 || wy0 + WH > H || wx0 + WW > W) {
+        uint8_t* wb = smem + Smem::WIN_OFF + (tl & 1) * WIN_BYTES;
+        for (int i = tid; i < WH * WW * 8; i += PWARPS * 32) {
+          const int cell = i >> 3;
+          const int cy = wy0 + cell / WW, cx = wx0 + cell % WW;
+          if ((unsigned)cy >= (unsigned)H || (unsigned)cx >= (unsigned)W)
+            *reinterpret_cast<uint4*>(wb + i * 16) = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(PWARPS * 32) : "memory");
+      }
       mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);       // this tile's window has landed
       for (int tap = 0; tap < TAPS; ++tap, ++it) {
-        cp_async_wait<2>();                                    // offsets of `it` have landed
+        cp_async_wait<1>();                                    // offsets of `it` have landed
         __syncwarp();                                          // ... and everyone left buffer (it-1) % NOB
         prefetch_next();
         const float* so = offF + (it % NOB) * (OFF_WARP_BUF / 4);
@@ -306,30 +320,29 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
           const float mk = so[(2 * DG + grp) * PLW + col];
           const float py = (pyb[j] + (float)ti) + dy;
           const float px = (pxb[j] + (float)tj) + dx;
-          const float fy = floorf(py), fx = floorf(px);
-          const float ly = py - fy, lx = px - fx;
-          // cell index, saturated so that wild / NaN offsets land on "all corners outside"
-          const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)H), x0 = (int)fminf(fmaxf(fx, -2.f), (float)W);
-          const float wy0f = ((unsigned)y0 < (unsigned)H) ? mk * (1.f - ly) : 0.f;
-          const float wy1f = ((unsigned)(y0 + 1) < (unsigned)H) ? mk * ly : 0.f;
-          const float wx0f = ((unsigned)x0 < (unsigned)W) ? (1.f - lx) : 0.f;
-          const float wx1f = ((unsigned)(x0 + 1) < (unsigned)W) ? lx : 0.f;
-          const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
-          // Window test on the un-clamped cell: both rows / columns of the 2x2 cell inside the window.
-          // Window cells outside the image hold finite stale data (buffers are zeroed once) and get
-          // weight 0, so no clamping is needed on this path.
+          // floor via a saturating float->int conversion (NaN -> 0, +-huge -> INT_MIN/MAX: such cells fail
+          // the window test and are rejected by the validity tests of the far path)
+          const int y0 = __float2int_rd(py), x0 = __float2int_rd(px);
+          const float ly = py - (float)y0, lx = px - (float)x0;
+          float wy0f = mk * (1.f - ly), wy1f = mk * ly, wx0f = 1.f - lx, wx1f = lx;
+          // both rows / columns of the 2x2 cell inside the window?
           const int ry = y0 - wy0, rx = x0 - wx0;
           const bool inwin = (unsigned)ry < (unsigned)(WH - 1) && (unsigned)rx < (unsigned)(WW - 1);
           uint4 v00, v01, v10, v11;
-          if (__all_sync(0xffffffffu, inwin)) {                // warp-uniform: the common case has no LDG code
+          if (__all_sync(0xffffffffu, inwin)) {                // warp-uniform common case: 4 LDS.128, no tests
             const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
             v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
           } else if (inwin) {
             const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
             v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
-          } else {                                             // far sample: global gather, clamped corners
-            const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
-            const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+          } else {                                             // far sample: global gather with explicit validity
+            wy0f = ((unsigned)y0 < (unsigned)H) ? wy0f : 0.f;
+            wy1f = ((unsigned)y0 + 1u < (unsigned)H) ? wy1f : 0.f;
+            wx0f = ((unsigned)x0 < (unsigned)W) ? wx0f : 0.f;
+            wx1f = ((unsigned)x0 + 1u < (unsigned)W) ? wx1f : 0.f;
+            const int ys = min(max(y0, -1), H), xs = min(max(x0, -1), W);      // keep the +1 below defined
+            const int cy0 = min(max(ys, 0), H - 1), cy1 = min(max(ys + 1, 0), H - 1);
+            const int cx0 = min(max(xs, 0), W - 1), cx1 = min(max(xs + 1, 0), W - 1);
             const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
             const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
             v00 = __ldg(reinterpret_cast<const uint4*>(xn + b00));
@@ -337,6 +350,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
             v10 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
             v11 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
           }
+          const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
           const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
           const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
           if (BLEND16) {
