@@ -258,8 +258,12 @@ def dcn_roofline(device, peaks, dg=8, iters=60):
     bytes_alg = px * (64 * 2 + dg * 18 * 4 + dg * 9 * 4 + 64 * 2)       # 1120 B/px at dg=8
     flops = 2.0 * px * 64 * 64 * 9
     ach = bytes_alg / sec / 1e9
-    return {"kernel": "dcn_fwd_tc_kernel<bf16,dg=%d> 1x64x270x480" % dg, "bound": "hbm", "achieved": round(ach, 1),
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
+    # capture summarised in profiles/r1_dcn_fwd_win_ncu.txt (128.7 MB read + 9.0 MB written; the 16.6 MB
+    # output is only partly evicted from L2 within the launch)
+    traffic = 137.7e6 if dg == 8 else None
+    return {"kernel": "win::dcn_fwd_win_kernel<dg=%d,bf16> 1x64x270x480" % dg, "bound": "hbm", "achieved": round(ach, 1),
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
             "peak_source": peaks["source"], "us_per_launch": round(sec * 1e6, 2),
             "algorithmic_bytes_per_launch": bytes_alg,
             "tensor": {"achieved_tflops": round(flops / sec / 1e12, 1), "peak_tflops": peaks["bf16_tflops"],
@@ -287,14 +291,14 @@ def run_reference_arm(args):
         from oracle import eavsrp_cpu as R
         torch.set_num_threads(os.cpu_count() or 1)
         fps, sample = R.time_model_sample(budget_s=60.0)
-        name = "eavsrp_x4_full_clip_30x270x480"
+        name = ModelWorkload.name
     else:
         fps, sample = cpu_hotpath_frames_per_s(20.0 * max(1, args.steps))
         name = HotpathWorkload.name
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name},
+            "config": {"workload": name, "clip": f"{T_FRAMES}x3x{LR_H}x{LR_W}"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act,
+from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
                   conv3x3_64, conv3x3_64_eligible, flow_warp, flow_warp_nhw2, fused_inference_ok,
                   modulated_deform_conv2d)
 
@@ -370,9 +370,9 @@ class EAVSRP(nn.Module):
             x = torch.cat([feats["spatial"][i]] + [feats[b][i] for b in _BRANCHES], 1)
             x = self.reconstruction(x)
             # LeakyReLU commutes with PixelShuffle: fold it into the conv epilogue
-            x = self.upsample1[1](conv2d_bias_act(self.upsample1[0], x, 0.1))
+            x = conv2d_bias_act_shuffle(self.upsample1[0], x, 0.1)
             if self.scale == 4:
-                x = self.upsample2[1](conv2d_bias_act(self.upsample2[0], x, 0.1))
+                x = conv2d_bias_act_shuffle(self.upsample2[0], x, 0.1)
             x = conv3x3_64(self.conv_hr, x, 0.1) if conv3x3_64_eligible(self.conv_hr, x) else \
                 conv2d_bias_act(self.conv_hr, x, 0.1)
             # the image-domain tail is fp32: residual (small) + bilinear base (the [0,1] frame itself)

@@ -35,7 +35,7 @@ __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "flow_warp", "flow_warp_nhw2",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
-    "conv3x3_64", "conv3x3_64_eligible", "ca_scale",
+    "conv3x3_64", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
 ]
 
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
@@ -551,4 +551,28 @@ def ca_scale(res, skip, sums, w1, b1, w2, b2, reduction: int = 16, res_bias=None
                                            w2.to(dt).contiguous().data_ptr(), b2.to(dt).contiguous().data_ptr(),
                                            _ptr(_b(res_bias, res)), out.data_ptr(), n, c, h, w, reduction,
                                            _dtype_code("ca_scale", rd), _stream(rd)), "ca_scale")
+    return out
+
+
+def conv2d_bias_act_shuffle(conv: nn.Conv2d, x, negative_slope: float = 1.0):
+    """``PixelShuffle(2)(LeakyReLU_slope(conv(x)))`` (LeakyReLU commutes with the shuffle): bias-free cuDNN
+    convolution, then bias + activation + shuffle in one NHWC pass.  Falls back to the PyTorch ops whenever
+    a gradient is needed or the layout does not allow it."""
+    cout = conv.out_channels
+    vec = 16 // x.element_size()
+    if (cout % (4 * vec) != 0 or not fused_inference_ok(x, conv.weight)
+            or not x.is_contiguous(memory_format=torch.channels_last)):
+        y = torch.nn.functional.pixel_shuffle(conv(x), 2)
+        return y if negative_slope == 1.0 else torch.nn.functional.leaky_relu(y, negative_slope)
+    lib = L.load()
+    y = torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if not y.is_contiguous(memory_format=torch.channels_last):
+        y = y.contiguous(memory_format=torch.channels_last)
+    n, _, h, w = y.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((n, cout // 4, 2 * h, 2 * w), dtype=y.dtype, device=y.device,
+                          memory_format=torch.channels_last)
+        L.check(lib.eavsr_bias_act_shuffle_forward(y.data_ptr(), _ptr(_b(conv.bias, y)), out.data_ptr(), n, cout // 4,
+                                                   h, w, float(negative_slope), _dtype_code("bias_act_shuffle", y),
+                                                   _stream(y)), "bias_act_shuffle")
     return out

@@ -155,6 +155,12 @@ int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1,
 int eavsr_bias_act_forward(void* x, const void* bias, int c, long long pixels, float negative_slope, int dtype,
                            void* stream);
 
+/* bias_act_shuffle: PixelShuffle(2) with the producing convolution's bias and LeakyReLU folded in
+ *   (the upsample1/upsample2 stages of EAVSRP.upsample, models/eavsrp_model.py:350-364):
+ *   out[n, c, 2h+i, 2w+j] = LeakyReLU_slope(x[n, 4c+2i+j, h, w] + bias[4c+2i+j]);
+ *   x: (n, 4*c_out, h, w), out: (n, c_out, 2h, 2w), both dense NHWC; bias may be NULL. */
+int eavsr_bias_act_shuffle_forward(const void* x, const void* bias, void* out, int n, int c_out, int h, int w,
+                                   float negative_slope, int dtype, void* stream);
 /* Second half of ca_residual with channel sums produced elsewhere (eavsr_conv3x3_forward). */
 int eavsr_ca_scale_forward(const void* res, const void* skip, const float* sums, const void* w1, const void* b1,
                            const void* w2, const void* b2, const void* res_bias, void* out, int n, int c, int h,

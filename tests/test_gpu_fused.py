@@ -170,6 +170,19 @@ def test_rcablock_tcgen05_path_matches_torch_path(cuda):
     assert (fused.double().cpu() - ref).abs().max() < 3e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_bias_act_shuffle_matches_pixel_shuffle(cuda, dtype):
+    g = torch.Generator().manual_seed(9)
+    conv = torch.nn.Conv2d(64, 256, 3, 1, 1).to(cuda, dtype).to(memory_format=torch.channels_last)
+    x = _cl(torch.randn(2, 64, 9, 13, generator=g).to(cuda, dtype))
+    with torch.no_grad():
+        fused = ops.conv2d_bias_act_shuffle(conv, x, 0.1)
+        ref = F.leaky_relu(F.pixel_shuffle(conv(x), 2), 0.1)
+    assert fused.shape == ref.shape == (2, 64, 18, 26)
+    assert fused.is_contiguous(memory_format=torch.channels_last)
+    assert (fused.float() - ref.float()).abs().max() < (1e-5 if dtype == torch.float32 else 5e-2)
+
+
 def test_model_uses_fused_path_only_without_grad(cuda):
     blk = M._RCABlock(64).to(cuda)
     x = _cl(torch.randn(1, 64, 12, 12, device=cuda))
