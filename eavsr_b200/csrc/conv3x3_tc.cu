@@ -132,7 +132,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
       const uint32_t stage = sA + warp * CV_ASTAGE;
 #pragma unroll 4
-      for (int i = lane; i < (dbg == 4 ? 0 : CV_HROWS * 8); i += 32) {
+      for (int i = lane; i < CV_HROWS * 8; i += 32) {
         const int p = i >> 3, ch = i & 7;
         const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
         const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
@@ -222,14 +222,13 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-      if (dbg == 3) continue;
       float f[CV_CH];
 #pragma unroll
       for (int c = 0; c < CV_CH; ++c) {
         const float t = __uint_as_float(acc[c]) + bsm[c];
         f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
       }
-      if (valid && dbg != 5) {
+      if (valid) {
         __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH;
 #pragma unroll
         for (int c = 0; c < CV_CH; c += 8) {
