@@ -306,9 +306,12 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
               const void* bias, void* out, const int64_t* os, int n, int h, int w, void* workspace,
               unsigned flags, cudaStream_t st) {
   using SM = TcSmem<SPLIT, DG>;
-  dcn_pack_weight<XT, SPLIT><<<(TAPS * CH * CH + 255) / 256, 256, 0, st>>>((const XT*)weight, (uint8_t*)workspace);
-  int rc = check_launch("dcn_forward(pack)");
-  if (rc) return rc;
+  int rc = 0;
+  if (!(flags & EAVSR_DCN_WS_PACKED)) {
+    dcn_pack_weight<XT, SPLIT><<<(TAPS * CH * CH + 255) / 256, 256, 0, st>>>((const XT*)weight, (uint8_t*)workspace);
+    rc = check_launch("dcn_forward(pack)");
+    if (rc) return rc;
+  }
   const int HW = h * w;
   const int tiles_per_img = (HW + TILE_M - 1) / TILE_M;
   const int total = tiles_per_img * n;

@@ -78,6 +78,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
                    long long xs_n, long long os_n, int tiles_x, int tiles_per_img, int total_tiles) {
   static_assert(DG <= 8, "window kernel: deform_groups <= 8");
+  static_assert(NSA == NOB, "the A ring and the offset ring share one counter");
   constexpr int NPLANES = 3 * DG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -193,40 +194,50 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
     // Offset/mask prefetch stream, 3 taps ahead of the gather.  Everything that needs an integer
     // division (tile -> image / row / column) is done once per tile, not once per tap.
-    struct TileRef { int n, ty0, tx0; const float* ob; const float* mb; bool row_ok; };
+    struct TileRef { const float* ob; const float* mb; uint32_t ok; };
+    // per-lane constants of the staging pattern: which plane / columns copy k of this lane moves
+    constexpr int PER_PLANE = VEC_OFF ? 2 : 8;
+    constexpr int NCOPY = (NPLANES * PER_PLANE + 31) / 32;
+    uint32_t cp_rel[NCOPY], cp_step[NCOPY], cp_dst[NCOPY];
+    int cp_col[NCOPY];
+    bool cp_mask[NCOPY];
+#pragma unroll
+    for (int k = 0; k < NCOPY; ++k) {
+      const int i = lane + 32 * k;
+      const int plane = min(i / PER_PLANE, NPLANES - 1), e = i % PER_PLANE;
+      const int comp = plane / DG, g = plane - comp * DG;
+      cp_col[k] = (i < NPLANES * PER_PLANE) ? (VEC_OFF ? e * 4 : e) : (1 << 28);   // unused copy: never in range
+      cp_mask[k] = comp == 2;
+      cp_rel[k] = (comp < 2 ? (uint32_t)(g * TAPS * 2 + comp) : (uint32_t)(g * TAPS)) * (uint32_t)HW + (uint32_t)(cp_col[k] & 15);
+      cp_step[k] = (comp < 2 ? 2u : 1u) * (uint32_t)HW;
+      cp_dst[k] = (uint32_t)(plane * PLW + ((cp_col[k] & 15) ^ ((g >> 2) << 2))) * 4u;
+    }
     auto make_ref = [&](int tl) {
       TileRef r;
-      tile_coords(tl, r.n, r.ty0, r.tx0);
-      const int gy = r.ty0 + wrow, gx = r.tx0 + wcol;
-      r.row_ok = gy < H;
+      int n, ty0, tx0;
+      tile_coords(tl, n, ty0, tx0);
+      const int gy = ty0 + wrow, gx = tx0 + wcol;
       const size_t pix = (size_t)gy * W + gx;
-      r.ob = offset + (size_t)r.n * DG * TAPS * 2 * HW + pix;
-      r.mb = mask + (size_t)r.n * DG * TAPS * HW + pix;
+      r.ob = offset + (size_t)n * DG * TAPS * 2 * HW + pix;
+      r.mb = mask + (size_t)n * DG * TAPS * HW + pix;
+      r.ok = 0;
+#pragma unroll
+      for (int k = 0; k < NCOPY; ++k) r.ok |= (gy < H && gx + cp_col[k] < W) ? (1u << k) : 0u;
       return r;
     };
     TileRef pref = make_ref(0);          // tile of the prefetch stream
-    int p_tl = 0, p_tap = 0;
-    auto prefetch_next = [&]() {         // stages (p_tl, p_tap) into buffer (p_tl*9 + p_tap) % NOB, then advances
+    int p_tl = 0, p_tap = 0, p_ring = 0;
+    auto prefetch_next = [&]() {         // stages (p_tl, p_tap) into buffer p_ring, then advances
       if (p_tl < my_tiles) {
-        const uint32_t dst0 = offBase + ((p_tl * TAPS + p_tap) % NOB) * OFF_WARP_BUF;
-        if (pref.row_ok) {
-          const int gx = pref.tx0 + wcol;
-          constexpr int PER_PLANE = VEC_OFF ? 2 : 8;
+        const uint32_t dst0 = offBase + p_ring * OFF_WARP_BUF;
 #pragma unroll
-          for (int k = 0; k < (NPLANES * PER_PLANE + 31) / 32; ++k) {
-            const int i = lane + 32 * k;
-            const int plane = i / PER_PLANE, e = i - plane * PER_PLANE;
-            const int comp = plane / DG, g = plane - comp * DG;
-            const int col = VEC_OFF ? e * 4 : e;
-            if (i < NPLANES * PER_PLANE && gx + col < W) {
-              const uint32_t rel = (comp < 2) ? (uint32_t)((g * TAPS + p_tap) * 2 + comp) * (uint32_t)HW
-                                              : (uint32_t)(g * TAPS + p_tap) * (uint32_t)HW;
-              const float* src = ((comp < 2) ? pref.ob : pref.mb) + rel + col;
-              const uint32_t dst = dst0 + (plane * PLW + (col ^ ((g >> 2) << 2))) * 4;
-              if (VEC_OFF) cp_async_16(dst, src); else cp_async_4(dst, src);
-            }
+        for (int k = 0; k < NCOPY; ++k) {
+          if (pref.ok & (1u << k)) {
+            const float* src = (cp_mask[k] ? pref.mb : pref.ob) + (cp_rel[k] + (uint32_t)p_tap * cp_step[k]);
+            if (VEC_OFF) cp_async_16(dst0 + cp_dst[k], src); else cp_async_4(dst0 + cp_dst[k], src);
           }
         }
+        if (++p_ring == NOB) p_ring = 0;
         if (++p_tap == TAPS) {
           p_tap = 0;
           if (++p_tl < my_tiles) pref = make_ref(p_tl);
@@ -274,7 +285,8 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
     prefetch_next();
     prefetch_next();
-    int it = 0;
+    int it = 0, ring = 0;                 // ring = it % NSA (= it % NOB), ring_ph = parity of it / NSA
+    uint32_t ring_ph = 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
       int n, ty0, tx0;
       tile_coords(tl, n, ty0, tx0);
@@ -309,9 +321,15 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         cp_async_wait<1>();                                    // offsets of `it` have landed
         __syncwarp();                                          // ... and everyone left buffer (it-1) % NOB
         prefetch_next();
-        const float* so = offF + (it % NOB) * (OFF_WARP_BUF / 4);
-        const int ti = tap / 3, tj = tap - ti * 3;
+        const float* so = offF + ring * (OFF_WARP_BUF / 4);
+        const int ti = (tap * 11) >> 5, tj = tap - ti * 3;       // tap / 3 for tap < 9
         uint32_t res[2][4];
+        // The two items of a thread are advanced in lock step (phase by phase), so that the scheduler
+        // always has two independent dependency chains per warp: the kernel is latency bound
+        // (ncu: "wait" and scoreboard stalls dominate with 4 warps per scheduler).
+        float wy0f[2], wy1f[2], wx0f[2], wx1f[2];
+        int y0[2], x0[2], ry[2], rx[2];
+        bool inwin[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int col = (j * 4 + q) ^ colx;
@@ -322,37 +340,51 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
           const float px = (pxb[j] + (float)tj) + dx;
           // floor via a saturating float->int conversion (NaN -> 0, +-huge -> INT_MIN/MAX: such cells fail
           // the window test and are rejected by the validity tests of the far path)
-          const int y0 = __float2int_rd(py), x0 = __float2int_rd(px);
-          const float ly = py - (float)y0, lx = px - (float)x0;
-          float wy0f = mk * (1.f - ly), wy1f = mk * ly, wx0f = 1.f - lx, wx1f = lx;
+          y0[j] = __float2int_rd(py); x0[j] = __float2int_rd(px);
+          const float ly = py - (float)y0[j], lx = px - (float)x0[j];
+          wy0f[j] = mk * (1.f - ly); wy1f[j] = mk * ly; wx0f[j] = 1.f - lx; wx1f[j] = lx;
           // both rows / columns of the 2x2 cell inside the window?
-          const int ry = y0 - wy0, rx = x0 - wx0;
-          const bool inwin = (unsigned)ry < (unsigned)(WH - 1) && (unsigned)rx < (unsigned)(WW - 1);
-          uint4 v00, v01, v10, v11;
-          if (__all_sync(0xffffffffu, inwin)) {                // warp-uniform common case: 4 LDS.128, no tests
-            const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
-            v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
-          } else if (inwin) {
-            const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
-            v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
-          } else {                                             // far sample: global gather with explicit validity
-            wy0f = ((unsigned)y0 < (unsigned)H) ? wy0f : 0.f;
-            wy1f = ((unsigned)y0 + 1u < (unsigned)H) ? wy1f : 0.f;
-            wx0f = ((unsigned)x0 < (unsigned)W) ? wx0f : 0.f;
-            wx1f = ((unsigned)x0 + 1u < (unsigned)W) ? wx1f : 0.f;
-            const int ys = min(max(y0, -1), H), xs = min(max(x0, -1), W);      // keep the +1 below defined
-            const int cy0 = min(max(ys, 0), H - 1), cy1 = min(max(ys + 1, 0), H - 1);
-            const int cx0 = min(max(xs, 0), W - 1), cx1 = min(max(xs + 1, 0), W - 1);
-            const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
-            const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
-            v00 = __ldg(reinterpret_cast<const uint4*>(xn + b00));
-            v01 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
-            v10 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
-            v11 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
+          ry[j] = y0[j] - wy0; rx[j] = x0[j] - wx0;
+          inwin[j] = (unsigned)ry[j] < (unsigned)(WH - 1) && (unsigned)rx[j] < (unsigned)(WW - 1);
+        }
+        uint4 v[2][4];
+        if (__all_sync(0xffffffffu, inwin[0] && inwin[1])) {   // warp-uniform common case: 8 LDS.128, no tests
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t a00 = win + (uint32_t)(ry[j] * WW + rx[j]) * 128u;
+            v[j][0] = lds128(a00); v[j][1] = lds128(a00 + 128u);
+            v[j][2] = lds128(a00 + WW * 128u); v[j][3] = lds128(a00 + WW * 128u + 128u);
           }
-          const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
-          const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
-          const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (inwin[j]) {
+              const uint32_t a00 = win + (uint32_t)(ry[j] * WW + rx[j]) * 128u;
+              v[j][0] = lds128(a00); v[j][1] = lds128(a00 + 128u);
+              v[j][2] = lds128(a00 + WW * 128u); v[j][3] = lds128(a00 + WW * 128u + 128u);
+            } else {                                           // far sample: global gather with explicit validity
+              const int yy = y0[j], xx = x0[j];
+              wy0f[j] = ((unsigned)yy < (unsigned)H) ? wy0f[j] : 0.f;
+              wy1f[j] = ((unsigned)yy + 1u < (unsigned)H) ? wy1f[j] : 0.f;
+              wx0f[j] = ((unsigned)xx < (unsigned)W) ? wx0f[j] : 0.f;
+              wx1f[j] = ((unsigned)xx + 1u < (unsigned)W) ? wx1f[j] : 0.f;
+              const int ys = min(max(yy, -1), H), xs = min(max(xx, -1), W);      // keep the +1 below defined
+              const int cy0 = min(max(ys, 0), H - 1), cy1 = min(max(ys + 1, 0), H - 1);
+              const int cx0 = min(max(xs, 0), W - 1), cx1 = min(max(xs + 1, 0), W - 1);
+              const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
+              const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
+              v[j][0] = __ldg(reinterpret_cast<const uint4*>(xn + b00));
+              v[j][1] = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
+              v[j][2] = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
+              v[j][3] = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float w00 = wy0f[j] * wx0f[j], w01 = wy0f[j] * wx1f[j], w10 = wy1f[j] * wx0f[j], w11 = wy1f[j] * wx1f[j];
+          const uint32_t a[4] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w}, b[4] = {v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+          const uint32_t c[4] = {v[j][2].x, v[j][2].y, v[j][2].z, v[j][2].w}, d[4] = {v[j][3].x, v[j][3].y, v[j][3].z, v[j][3].w};
           if (BLEND16) {
             const uint32_t p00 = pack_bf16x2(w00, w00), p01 = pack_bf16x2(w01, w01);
             const uint32_t p10 = pack_bf16x2(w10, w10), p11 = pack_bf16x2(w11, w11);
@@ -370,8 +402,8 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
             }
           }
         }
-        if (it >= NSA) mbar_wait(bar_empty + 8 * (it % NSA), ((it / NSA) - 1) & 1);
-        const uint32_t aStage = sA + (it % NSA) * A_TILE;
+        if (it >= NSA) mbar_wait(bar_empty + 8 * ring, ring_ph ^ 1);
+        const uint32_t aStage = sA + ring * A_TILE;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int m = wrow * 16 + wcol + j * 4 + q;
@@ -382,9 +414,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar_full + 8 * (it % NSA));
+          mbar_arrive(bar_full + 8 * ring);
           if (tap == TAPS - 1) mbar_arrive(bar_wine + 8 * (tl & 1));   // this warp is done with the window
         }
+        if (++ring == NSA) { ring = 0; ring_ph ^= 1; }
         if (tap == 1 && tl >= 1) epilogue(tl - 1);
       }
     }

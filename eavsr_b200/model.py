@@ -230,7 +230,8 @@ class MultiAdSTN(ModulatedDeformConv2d):
         feat = flow_warp(feat_prop, flow)
         offset, mask = self.adastn(nbr_w, ref[0])
         return modulated_deform_conv2d(feat, offset, mask, self.weight, self.bias, self.stride, self.padding,
-                                       self.dilation, self.groups, self.deform_groups)
+                                       self.dilation, self.groups, self.deform_groups,
+                                       static_weight=not torch.is_grad_enabled())
 
 
 class _ConvModule(nn.Module):

@@ -23,6 +23,8 @@ from __future__ import annotations
 import math
 from typing import Optional, Tuple, Union
 
+import weakref
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -192,6 +194,35 @@ def dcn_uses_tensor_cores(x, weight, stride=1, padding=0, dilation=1, groups=1, 
                                                         sh, sw, ph, pw, dh, dw, groups, deform_groups, 0))
 
 
+DCN_WS_PACKED = 16          # include/eavsr_b200.h EAVSR_DCN_WS_PACKED
+_DCN_STATIC_WEIGHT = 1 << 20  # Python-side only: the caller promises `weight` is constant (see _dcn_workspace)
+_DCN_WS_CACHE = {}          # id(weight) -> (weakref(weight), version, dtype, workspace)
+
+
+def _dcn_workspace(weight, dtype, ws_bytes, static):
+    """Workspace for eavsr_dcn_forward.  Weights the caller declares constant (``static_weight=True``,
+    inference only) keep their packed
+    image: the entry is valid only while it is the same tensor object at the same version counter,
+    so an optimizer step / load_state_dict / in-place edit re-packs.  Returns (workspace, already_packed)."""
+    if not static or (torch.is_grad_enabled() and weight.requires_grad):
+        return torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=weight.device), False
+    key = id(weight)
+    hit = _DCN_WS_CACHE.get(key)
+    if hit is not None:
+        ref, version, dt, ws = hit
+        if ref() is weight and version == weight._version and dt == dtype and ws.numel() >= ws_bytes \
+                and ws.device == weight.device:
+            return ws, True
+    if len(_DCN_WS_CACHE) > 256:
+        for k in [k for k, v in _DCN_WS_CACHE.items() if v[0]() is None]:
+            del _DCN_WS_CACHE[k]
+        if len(_DCN_WS_CACHE) > 256:
+            _DCN_WS_CACHE.clear()
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=weight.device)
+    _DCN_WS_CACHE[key] = (weakref.ref(weight), weight._version, dtype, ws)
+    return ws, False
+
+
 class _ModulatedDeformConv2dFn(Function):
     @staticmethod
     def forward(ctx, input, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups,
@@ -226,7 +257,10 @@ class _ModulatedDeformConv2dFn(Function):
             bd = bias.detach().to(input.dtype).contiguous() if bias is not None else None
             out = _empty_like_layout(xd, channels=cout, hw=(ho, wo))
             ws_bytes = lib.eavsr_dcn_forward_workspace(cin, cout, kh, kw, groups, deform_groups, code)
-            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=input.device)
+            ws, packed = _dcn_workspace(weight, input.dtype, ws_bytes, bool(flags & _DCN_STATIC_WEIGHT))
+            flags &= ~_DCN_STATIC_WEIGHT
+            if packed:
+                flags |= DCN_WS_PACKED
             L.check(lib.eavsr_dcn_forward(xd.data_ptr(), _strides(xd), off32.data_ptr(), msk32.data_ptr(),
                                           wd.data_ptr(), _ptr(bd), out.data_ptr(), _strides(out), n, cin, h, w,
                                           cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, deform_groups, code,
@@ -272,11 +306,12 @@ class _ModulatedDeformConv2dFn(Function):
 
 
 def modulated_deform_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
-                            groups=1, deform_groups=1):
+                            groups=1, deform_groups=1, *, static_weight=False):
     """Drop-in for ``mmcv.ops.modulated_deform_conv2d`` with the positional order the reference
-    uses at models/networks.py:627-630."""
+    uses at models/networks.py:627-630.  ``static_weight=True`` (extension, inference only) lets the
+    packed tensor-core image of ``weight`` be kept between calls while the tensor is unchanged."""
     return _ModulatedDeformConv2dFn.apply(input, offset, mask, weight, bias, stride, padding, dilation,
-                                          groups, deform_groups)
+                                          groups, deform_groups, _DCN_STATIC_WEIGHT if static_weight else 0)
 
 
 class ModulatedDeformConv2d(nn.Module):

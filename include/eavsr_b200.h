@@ -47,6 +47,9 @@ extern "C" {
 #define EAVSR_DCN_FORCE_V1 2u      /* flags bit: first-generation tcgen05 kernel (A/B timing only) */
 #define EAVSR_DCN_FORCE_WS 4u      /* flags bit: second-generation (warp-specialised, L1 gather) kernel */
 #define EAVSR_DCN_BLEND_FP32 8u    /* flags bit: window kernel with fp32 blend instead of bf16x2 HFMA2 */
+#define EAVSR_DCN_WS_PACKED 16u    /* flags bit: `workspace` still holds the packed image of this same `weight`
+                                      written by an earlier eavsr_dcn_forward call (constant inference
+                                      weights): skip the re-pack launch */
 
 /* ---- library ------------------------------------------------------------------------ */
 int eavsr_version(void);

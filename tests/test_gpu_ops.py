@@ -127,6 +127,31 @@ def test_dcn_tc_bf16(cuda, dg):
     assert rel_err(out, ref) < BF16_REL
 
 
+def test_dcn_static_weight_keeps_packed_image_and_tracks_updates(cuda):
+    """static_weight=True skips the re-pack launch while the weight tensor is unchanged and re-packs
+    after an in-place update (version counter) -- results always equal the uncached call."""
+    x, off, mask, wgt, bias = dcn_inputs(1, 64, 40, 56, 64, 8, seed=16)
+    xd, od, md = _cl(x.bfloat16().to(cuda)), off.to(cuda), mask.to(cuda)
+    wd, bd = wgt.bfloat16().to(cuda), bias.bfloat16().to(cuda)
+
+    def run(static):
+        with torch.no_grad():
+            return E.modulated_deform_conv2d(xd, od, md, wd, bd, 1, 1, 1, 1, 8, static_weight=static)
+    base = run(False)
+    n0 = L.launch_count()
+    a = run(True)                       # packs
+    n1 = L.launch_count()
+    b = run(True)                       # reuses
+    n2 = L.launch_count()
+    assert torch.equal(a, base) and torch.equal(b, base)
+    assert (n1 - n0) - (n2 - n1) == 1   # exactly the pack launch was saved
+    with torch.no_grad():
+        wd.mul_(0.5)                    # in-place update: must re-pack
+    c = run(True)
+    assert torch.equal(c, run(False))
+    assert not torch.equal(c, base)
+
+
 def test_dcn_tc_nchw_input_and_no_bias(cuda):
     x, off, mask, wgt, _ = dcn_inputs(1, 64, 21, 35, 64, 8, seed=7)
     ref = _dcn_ref(x, off, mask, wgt, None, dg=8)
