@@ -460,12 +460,29 @@ extern "C" int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], cons
   return dcn_forward_generic<__nv_bfloat16>(x, x_strides, offset, mask, weight, bias, out, out_strides, g, st);
 }
 
+namespace eavsr {
+size_t dcn_backward_tc_workspace();
+bool dcn_backward_tc_eligible(const int64_t* gs, const int64_t* xs, const int64_t* gxs, const DcnGeom& g, bool has_gx);
+int dcn_backward_tc(const void* gout, const int64_t* gs, const void* x, const int64_t* xs, const float* offset,
+                    const float* mask, const void* weight, float* gx32, const int64_t* gxs, float* goffset,
+                    float* gmask, float* gweight32, const DcnGeom& g, void* workspace, unsigned which,
+                    cudaStream_t st);
+}  // namespace eavsr
+
+extern "C" size_t eavsr_dcn_backward_workspace(int cin, int cout, int kh, int kw, int groups, int deform_groups,
+                                               int dtype) {
+  if (cin != CH || cout != CH || kh != 3 || kw != 3 || groups != 1 || dtype != EAVSR_BF16) return 0;
+  if (!(deform_groups == 1 || deform_groups == 2 || deform_groups == 4 || deform_groups == 8)) return 0;
+  return dcn_backward_tc_workspace();
+}
+
 extern "C" int eavsr_dcn_backward(const void* gout, const int64_t gout_strides[4], const void* x,
                                   const int64_t x_strides[4], const float* offset, const float* mask,
                                   const void* weight, float* gx32, const int64_t gx_strides[4], float* goffset,
                                   float* gmask, float* gweight32, float* gbias32, int n, int cin, int h, int w,
                                   int cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int groups,
-                                  int deform_groups, int dtype, void* stream) {
+                                  int deform_groups, int dtype, void* workspace, size_t workspace_bytes,
+                                  unsigned flags, void* stream) {
   EAVSR_REQUIRE(gout && x && offset && mask && weight && gout_strides && x_strides, "dcn_backward: null pointer");
   EAVSR_REQUIRE(!gx32 || gx_strides, "dcn_backward: gx32 without strides");
   EAVSR_REQUIRE(dtype == EAVSR_F32 || dtype == EAVSR_BF16, "dcn_backward: bad dtype %d", dtype);
@@ -476,6 +493,22 @@ extern "C" int eavsr_dcn_backward(const void* gout, const int64_t gout_strides[4
   if (dtype == EAVSR_F32)
     return dcn_backward_generic<float>(gout, gout_strides, x, x_strides, offset, mask, weight, gx32, gx_strides,
                                        goffset, gmask, gweight32, gbias32, g, st);
-  return dcn_backward_generic<__nv_bfloat16>(gout, gout_strides, x, x_strides, offset, mask, weight, gx32,
-                                             gx_strides, goffset, gmask, gweight32, gbias32, g, st);
+  unsigned which = 0;   // bit 0: data gradients, bit 1: weight gradient on the tcgen05 kernels
+  const size_t need = eavsr_dcn_backward_workspace(cin, cout, kh, kw, groups, deform_groups, dtype);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!(flags & EAVSR_DCN_FORCE_GENERIC) && need && workspace && workspace_bytes >= need && al16(workspace) &&
+      al16(gout) && al16(x) && (!gx32 || al16(gx32)) &&
+      dcn_backward_tc_eligible(gout_strides, x_strides, gx_strides, g, gx32 != nullptr)) {
+    if (!(flags & EAVSR_DCN_BWD_GENERIC_DATA)) which |= 1u;
+    if (!(flags & EAVSR_DCN_BWD_GENERIC_WEIGHT)) which |= 2u;
+  }
+  if (which) {
+    rc = dcn_backward_tc(gout, gout_strides, x, x_strides, offset, mask, weight, gx32, gx_strides, goffset, gmask,
+                         gweight32, g, workspace, which, st);
+    if (rc) return rc;
+  }
+  const bool tc_data = (which & 1u) != 0, tc_w = (which & 2u) != 0;
+  return dcn_backward_generic<__nv_bfloat16>(gout, gout_strides, x, x_strides, offset, mask, weight,
+                                             tc_data ? nullptr : gx32, gx_strides, tc_data ? nullptr : goffset,
+                                             tc_data ? nullptr : gmask, tc_w ? nullptr : gweight32, gbias32, g, st);
 }

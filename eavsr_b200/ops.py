@@ -268,6 +268,7 @@ class _ModulatedDeformConv2dFn(Function):
                     "dcn_forward")
         ctx.save_for_backward(xd, off32, msk32, wd)
         ctx.geom = (sh, sw, ph, pw, dh, dw, groups, deform_groups)
+        ctx.bwd_flags = flags & (1 | 32 | 64)     # FORCE_GENERIC, BWD_GENERIC_DATA, BWD_GENERIC_WEIGHT
         ctx.has_bias = bias is not None
         ctx.in_dtypes = (offset.dtype, mask.dtype, weight.dtype, bias.dtype if bias is not None else None)
         return out
@@ -289,11 +290,14 @@ class _ModulatedDeformConv2dFn(Function):
             gmsk = torch.empty_like(msk32) if need[2] else None
             gw32 = torch.empty(wd.shape, dtype=torch.float32, device=xd.device) if need[3] else None
             gb32 = torch.empty(cout, dtype=torch.float32, device=xd.device) if (need[4] and ctx.has_bias) else None
+            code = _dtype_code("modulated_deform_conv2d", xd)
+            ws_bytes = lib.eavsr_dcn_backward_workspace(cin, cout, kh, kw, groups, dg, code)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xd.device) if ws_bytes else None
             L.check(lib.eavsr_dcn_backward(g.data_ptr(), _strides(g), xd.data_ptr(), _strides(xd),
                                            off32.data_ptr(), msk32.data_ptr(), wd.data_ptr(), _ptr(gx32),
                                            _strides(gx32) if gx32 is not None else None, _ptr(goff), _ptr(gmsk),
                                            _ptr(gw32), _ptr(gb32), n, cin, h, w, cout, kh, kw, sh, sw, ph, pw,
-                                           dh, dw, groups, dg, _dtype_code("modulated_deform_conv2d", xd),
+                                           dh, dw, groups, dg, code, _ptr(ws), ws_bytes, ctx.bwd_flags,
                                            _stream(xd)),
                     "dcn_backward")
         od, md, wdt, bdt = ctx.in_dtypes

@@ -47,6 +47,8 @@ extern "C" {
 #define EAVSR_DCN_FORCE_V1 2u      /* flags bit: first-generation tcgen05 kernel (A/B timing only) */
 #define EAVSR_DCN_FORCE_WS 4u      /* flags bit: second-generation (warp-specialised, L1 gather) kernel */
 #define EAVSR_DCN_BLEND_FP32 8u    /* flags bit: window kernel with fp32 blend instead of bf16x2 HFMA2 */
+#define EAVSR_DCN_BWD_GENERIC_DATA 32u   /* flags bit (backward): d(x), d(offset), d(mask) on the generic kernel */
+#define EAVSR_DCN_BWD_GENERIC_WEIGHT 64u /* flags bit (backward): d(weight) on the generic kernel */
 #define EAVSR_DCN_WS_PACKED 16u    /* flags bit: `workspace` still holds the packed image of this same `weight`
                                       written by an earlier eavsr_dcn_forward call (constant inference
                                       weights): skip the re-pack launch */
@@ -102,13 +104,18 @@ int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], const float* of
 /* Gradients wrt x, offset, mask, weight, bias (any output pointer may be NULL = not needed).
  * gx32: fp32 accumulation buffer (zero-filled by the call) with strides gx_strides;
  * goffset/gmask: fp32, layouts of offset/mask;  gweight32: fp32 (cout,cin/groups,kh,kw),
- * gbias32: fp32 (cout) -- both zero-filled by the call. */
+ * gbias32: fp32 (cout) -- both zero-filled by the call.
+ * bf16 NHWC 64->64 3x3 (stride/pad/dilation 1, deform_groups 1/2/4/8) runs on the tcgen05 kernels
+ * (csrc/dcn_bwd_tc.cu) when `workspace` holds eavsr_dcn_backward_workspace() bytes (16-byte aligned);
+ * with workspace == NULL, or any other configuration, the generic kernels run.  This replaces the
+ * autograd of mmcv's ModulatedDeformConv2dFunction.backward under models/networks.py:627-630. */
+size_t eavsr_dcn_backward_workspace(int cin, int cout, int kh, int kw, int groups, int deform_groups, int dtype);
 int eavsr_dcn_backward(const void* gout, const int64_t gout_strides[4], const void* x,
                        const int64_t x_strides[4], const float* offset, const float* mask, const void* weight,
                        float* gx32, const int64_t gx_strides[4], float* goffset, float* gmask,
                        float* gweight32, float* gbias32, int n, int cin, int h, int w, int cout, int kh, int kw,
                        int sh, int sw, int ph, int pw, int dh, int dw, int groups, int deform_groups,
-                       int dtype, void* stream);
+                       int dtype, void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
 /* ---- PWC-Net cost volume -----------------------------------------------------------------
  * Replaces kernel_Correlation_rearrange + kernel_Correlation_updateOutput

@@ -260,6 +260,42 @@ def test_dcn_backward_fp32(cuda, cfg):
         assert max_err(a, r) < 1e-3 * max(1.0, r.abs().max().item()), name
 
 
+def _dcn_bf16_grads(cuda, n, h, w, dg, flags, seed=21, sigma=1.5):
+    x, off, mask, wgt, bias = dcn_inputs(n, 64, h, w, 64, dg, seed=seed, sigma=sigma)
+    xb, wb, bb = x.bfloat16(), wgt.bfloat16(), bias.bfloat16()
+    g = torch.randn(n, 64, h, w, generator=torch.Generator().manual_seed(seed + 1)).bfloat16()
+    gl = [t.requires_grad_() for t in (_cl(xb.to(cuda)), off.to(cuda), mask.to(cuda), wb.to(cuda), bb.to(cuda))]
+    out = _ModulatedDeformConv2dFn.apply(*gl, 1, 1, 1, 1, dg, flags)
+    grads = torch.autograd.grad(out, gl, _cl(g.to(cuda)))
+    return (xb, off, mask, wb, bb, g), grads
+
+
+@pytest.mark.parametrize("flags", [0, 32, 64])     # tcgen05 data+weight / generic data / generic weight
+@pytest.mark.parametrize("dg", [8, 4, 1])
+@pytest.mark.parametrize("shape", [(2, 19, 37), (1, 40, 72)])
+def test_dcn_backward_bf16_tensor_cores(cuda, shape, dg, flags):
+    """bf16 NHWC 64->64 backward on the tcgen05 kernels (csrc/dcn_bwd_tc.cu) against the fp64 oracle on
+    the same bf16-rounded inputs; `flags` swaps one half at a time for the generic kernel."""
+    n, h, w = shape
+    inputs, grads = _dcn_bf16_grads(cuda, n, h, w, dg, flags)
+    leaves = [t.double().requires_grad_() for t in inputs[:5]]
+    ref = O.modulated_deform_conv2d(*leaves, 1, 1, 1, 1, dg)
+    grefs = torch.autograd.grad(ref, leaves, inputs[5].double())
+    tol = {"x": BF16_REL, "offset": 2e-3, "mask": 2e-3, "weight": BF16_REL, "bias": BF16_REL}
+    for name, a, r in zip(("x", "offset", "mask", "weight", "bias"), grads, grefs):
+        assert a.shape == r.shape, name
+        assert rel_err(a, r) < tol[name], (name, rel_err(a, r))
+
+
+def test_dcn_backward_tensor_cores_match_generic_at_full_size(cuda):
+    """1x64x270x480 (BASELINE config 2/3 size): tcgen05 backward == generic backward."""
+    _, tc = _dcn_bf16_grads(cuda, 1, 270, 480, 8, 0, seed=23, sigma=2.0)
+    _, ge = _dcn_bf16_grads(cuda, 1, 270, 480, 8, 32 | 64, seed=23, sigma=2.0)
+    tol = {"x": BF16_REL, "offset": 2e-3, "mask": 2e-3, "weight": BF16_REL, "bias": BF16_REL}
+    for name, a, r in zip(("x", "offset", "mask", "weight", "bias"), tc, ge):
+        assert rel_err(a, r) < tol[name], (name, rel_err(a, r))
+
+
 # ---------------------------------------------------------------------------------------------
 # correlation
 # ---------------------------------------------------------------------------------------------

@@ -115,12 +115,17 @@ def bench_dcn():
                 if n == 1 and dg == 8:
                     sec = timeit(lambda i: _ModulatedDeformConv2dFn.apply(xs[i % k], offs[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg, L.DCN_FORCE_GENERIC), 3, warm=1)
                     rec(f"dcn fwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by, fl)
-                    xg = xs[0].clone().requires_grad_()
-                    og, mg, wg, bg = offs[0].clone().requires_grad_(), msks[0].clone().requires_grad_(), wgt.clone().requires_grad_(), bias.clone().requires_grad_()
-                    out = E.modulated_deform_conv2d(xg, og, mg, wg, bg, 1, 1, 1, 1, dg)
-                    go = torch.randn_like(out)
-                    sec = timeit(lambda i: torch.autograd.grad(out, [xg, og, mg, wg, bg], go, retain_graph=True), 3, warm=1, graph=False)
-                    rec(f"dcn bwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by * 2, fl * 2)
+                    for flags, tag in ((0, "tc (data+weight)" if dt == torch.bfloat16 else "generic"),
+                                       (32, "generic data + tc weight"), (64, "tc data + generic weight"),
+                                       (96, "generic")):
+                        if dt != torch.bfloat16 and flags:
+                            continue
+                        xg = xs[0].clone().requires_grad_()
+                        og, mg, wg, bg = offs[0].clone().requires_grad_(), msks[0].clone().requires_grad_(), wgt.clone().requires_grad_(), bias.clone().requires_grad_()
+                        out = _ModulatedDeformConv2dFn.apply(xg, og, mg, wg, bg, 1, 1, 1, 1, dg, flags)
+                        go = torch.randn_like(out)
+                        sec = timeit(lambda i: torch.autograd.grad(out, [xg, og, mg, wg, bg], go, retain_graph=True), 5, warm=2, graph=False)
+                        rec(f"dcn bwd {tag} {dt} dg={dg} {n}x64x{h}x{w} (incl. host autograd glue)", sec, by * 2, fl * 2)
                 del xs, offs, msks
                 torch.cuda.empty_cache()
 
