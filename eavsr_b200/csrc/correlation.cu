@@ -9,6 +9,8 @@
 // in shared memory, 8 channels at a time, and every thread keeps 4 pixels x 27 displacements
 // (3 displacement rows) in registers, so one 16-byte shared load feeds 9-12 FMAs.
 // out[n,(dy+4)*9+(dx+4),y,x] = 1/C * sum_c first[n,c,y,x] * second[n,c,y+dy,x+dx].
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace eavsr {
@@ -225,6 +227,143 @@ corr_fwd_f32(const float* __restrict__ f1, const float* __restrict__ f2, float* 
     }
 }
 
+// ---- fp32 main path: TMA-staged halos, persistent CTAs -------------------------------------------
+// ncu of corr_fwd_f32 (profiles/r1_corr_fwd_ncu.txt): 47 M warp instructions of which only 25 M are FMAs --
+// the cp.async staging loops (index arithmetic per 16 bytes) cost as much issue bandwidth as a third of
+// the math, every CTA exposes the latency of its first chunk, and 1200 CTAs on 296 slots run 5 waves for
+// 4.05 waves of work.  Here one elected thread issues two cp.async.bulk.tensor (4-D tensor maps over
+// (x, y, c, n); out-of-range coordinates -- the zero padding of the cost volume, the channel tail --
+// are filled with zeros by the TMA unit) per 8-channel chunk into a 3-stage ring, the six warps
+// only wait on mbarriers, and CTAs are persistent so the ring keeps streaming across tile boundaries.
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_STAGE_BYTES = (int)sizeof(CorrStage);            // 8 KB + 20 KB
+constexpr int TMA_THREADS = CORR_THREADS;
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int x, int y, int c, int n, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(c), "r"(n), "r"(bar)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 2)
+corr_fwd_tma(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+             float* __restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int total_tiles) {
+  extern __shared__ __align__(128) uint8_t corr_smem[];
+  const uint32_t sbase = (smem_u32(corr_smem) + 127u) & ~127u;
+  const uint8_t* sgen = corr_smem + (sbase - smem_u32(corr_smem));
+  const uint32_t bars = sbase + TMA_STAGES * TMA_STAGE_BYTES;      // full[TMA_STAGES], empty[TMA_STAGES]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int CWARPS = CORR_THREADS / 32;
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (TMA_STAGES + s), CWARPS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int nchunks = (C + CKC - 1) / CKC;
+  const size_t plane = (size_t)H * W;
+
+  // producer state (thread 0): stream position `pcnt` runs TMA_STAGES-1 chunks ahead of the consumers
+  int ptile = blockIdx.x, pk = 0, pcnt = 0;
+  auto produce = [&]() {
+    if (ptile >= total_tiles) return;
+    const int n = ptile / (tiles_x * tiles_y), rem = ptile - n * (tiles_x * tiles_y);
+    const int y0 = (rem / tiles_x) * TH, x0 = (rem % tiles_x) * TW;
+    const int s = pcnt % TMA_STAGES;
+    if (pcnt >= TMA_STAGES) mbar_wait(bars + 8 * (TMA_STAGES + s), ((pcnt / TMA_STAGES) - 1) & 1);
+    const uint32_t full = bars + 8 * s, dst = sbase + s * TMA_STAGE_BYTES;
+    mbar_arrive_expect_tx(full, TMA_STAGE_BYTES);
+    tma_load_4d(dst, &tm1, x0, y0, pk * CKC, n, full);
+    tma_load_4d(dst + (uint32_t)sizeof(float) * CKC * TH * TW, &tm2, x0 - D, y0 - D, pk * CKC, n, full);
+    ++pcnt;
+    if (++pk == nchunks) { pk = 0; ptile += gridDim.x; }
+  };
+  if (tid == 0)
+    for (int i = 0; i < TMA_STAGES - 1; ++i) produce();
+
+  const int tq = tid & 7, ty = (tid >> 3) & 7, dgrp = tid >> 6;
+  const float inv = 1.f / (float)C;
+  int cnt = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y), rem = tile - n * (tiles_x * tiles_y);
+    const int y0 = (rem / tiles_x) * TH, x0 = (rem % tiles_x) * TW;
+    float acc[3][ND][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < ND; ++b)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[a][b][p] = 0.f;
+    for (int k = 0; k < nchunks; ++k, ++cnt) {
+      const int s = cnt % TMA_STAGES;
+      if (tid == 0) produce();                               // refills the stage everyone left in iteration cnt-1
+      mbar_wait(bars + 8 * s, (cnt / TMA_STAGES) & 1);
+      const CorrStage& S = *reinterpret_cast<const CorrStage*>(sgen + s * TMA_STAGE_BYTES);
+#pragma unroll 2
+      for (int cc = 0; cc < CKC; ++cc) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&S.s1[cc][ty][4 * tq]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const float* row = &S.s2[cc][ty + dgrp * 3 + dyi][4 * tq];
+          const float4 b0 = *reinterpret_cast<const float4*>(row);
+          const float4 b1 = *reinterpret_cast<const float4*>(row + 4);
+          const float4 b2 = *reinterpret_cast<const float4*>(row + 8);
+          const float b[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+          for (int dxi = 0; dxi < ND; ++dxi)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[dyi][dxi][p] += a[p] * b[p + dxi];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (TMA_STAGES + s));
+    }
+    const int gy = y0 + ty, gx = x0 + 4 * tq;
+    if (gy < H && gx < W) {                                  // W % 4 == 0 on this path: whole quad in range
+      float* on = out + (size_t)n * (ND * ND) * plane + (size_t)gy * W + gx;
+#pragma unroll
+      for (int dyi = 0; dyi < 3; ++dyi)
+#pragma unroll
+        for (int dxi = 0; dxi < ND; ++dxi) {
+          const int kk = (dgrp * 3 + dyi) * ND + dxi;
+          __stcs(reinterpret_cast<float4*>(on + (size_t)kk * plane),
+                 make_float4(acc[dyi][dxi][0] * inv, acc[dyi][dxi][1] * inv, acc[dyi][dxi][2] * inv,
+                             acc[dyi][dxi][3] * inv));
+        }
+    }
+  }
+}
+
+// ---- small maps (the PWC pyramid as EAVSR training uses it: 1x1 ... 16x16) ------------------------
+// One thread per output element, channels in the inner loop; neighbouring threads are neighbouring
+// x, so both reads are coalesced and everything lives in L1/L2.  The tiled kernels above would stage
+// a whole 8x32 tile (+ halo) per 8 channels for a handful of pixels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+corr_fwd_small(const T* __restrict__ f1, const T* __restrict__ f2, T* __restrict__ out, int N, int C, int H, int W) {
+  const int plane = H * W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * (ND * ND) * plane) return;
+  const int x = (int)(idx % W), y = (int)((idx / W) % H);
+  const int k = (int)((idx / plane) % (ND * ND)), n = (int)(idx / ((long long)plane * ND * ND));
+  const int yy = y + k / ND - D, xx = x + k % ND - D;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+    const T* p1 = f1 + (size_t)n * C * plane + (size_t)y * W + x;
+    const T* p2 = f2 + (size_t)n * C * plane + (size_t)yy * W + xx;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      a0 += to_f32<T>(p1[(size_t)c * plane]) * to_f32<T>(p2[(size_t)c * plane]);
+      a1 += to_f32<T>(p1[(size_t)(c + 1) * plane]) * to_f32<T>(p2[(size_t)(c + 1) * plane]);
+      a2 += to_f32<T>(p1[(size_t)(c + 2) * plane]) * to_f32<T>(p2[(size_t)(c + 2) * plane]);
+      a3 += to_f32<T>(p1[(size_t)(c + 3) * plane]) * to_f32<T>(p2[(size_t)(c + 3) * plane]);
+    }
+    for (; c < C; ++c) a0 += to_f32<T>(p1[(size_t)c * plane]) * to_f32<T>(p2[(size_t)c * plane]);
+  }
+  out[idx] = from_f32<T>(((a0 + a1) + (a2 + a3)) / (float)C);
+}
+
 // Backward, one thread per input-gradient element; reads are coalesced along x and hit L1/L2.
 // gfirst[n,c,y,x]  = 1/C sum_k gout[n,k,y,x]       * second[n,c,y+dy,x+dx]
 // gsecond[n,c,y,x] = 1/C sum_k gout[n,k,y-dy,x-dx] * first[n,c,y-dy,x-dx]
@@ -256,12 +395,60 @@ corr_bwd(const T* __restrict__ other, const T* __restrict__ gout, T* __restrict_
   gin[idx] = from_f32<T>(a / (float)C);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// (x, y, c, n) fp32 tensor map with a [box_w x box_h x CKC x 1] box; zero fill outside
+bool make_corr_map(CUtensorMap* tm, const void* base, int n, int c, int h, int w, int box_w, int box_h) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)c, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4, (cuuint64_t)w * h * c * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)CKC, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T>
 int corr_forward_t(const void* f1, const void* f2, void* out, int n, int c, int h, int w, cudaStream_t st) {
+  if (h * w <= 256) {                       // PWC pyramid of 64x64 training crops: 1x1 ... 16x16
+    const long long total = (long long)n * ND * ND * h * w;
+    corr_fwd_small<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)f1, (const T*)f2, (T*)out, n, c, h, w);
+    return check_launch("correlation_forward(small)");
+  }
   dim3 grid(ceil_div(w, TW), ceil_div(h, TH), n);
   if (sizeof(T) == 4) {
     const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(f2) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    if (vec && (long long)w * h * c * 4 < (1ll << 40)) {
+      CUtensorMap tm1, tm2;
+      if (make_corr_map(&tm1, f1, n, c, h, w, TW, TH) && make_corr_map(&tm2, f2, n, c, h, w, HW_, HH)) {
+        const int smem = TMA_STAGES * TMA_STAGE_BYTES + 2 * TMA_STAGES * 8 + 128;
+        cudaError_t e = cudaFuncSetAttribute(corr_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("correlation_forward: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int tiles_x = ceil_div(w, TW), tiles_y = ceil_div(h, TH);
+        const long long total = (long long)tiles_x * tiles_y * n;
+        const int ctas = (int)(total < 2ll * sms ? total : 2ll * sms);
+        corr_fwd_tma<<<ctas, TMA_THREADS, smem, st>>>(tm1, tm2, (float*)out, c, h, w, tiles_x, tiles_y, (int)total);
+        return check_launch("correlation_forward(tma)");
+      }
+    }
     const int smem = 2 * (int)sizeof(CorrStage);
     auto kv = corr_fwd_f32<true>;
     auto ks = corr_fwd_f32<false>;

@@ -69,6 +69,33 @@ __global__ void dcn_pack_weight_t(const __nv_bfloat16* __restrict__ w, uint8_t* 
   *reinterpret_cast<__nv_bfloat16*>(packed + (size_t)t * B_TILE + sw128_offset(c, o * 2)) = w[((size_t)o * CH + c) * TAPS + t];
 }
 
+// d(bias)[o] = sum over pixels of gout[., o]: gout is NHWC, so a thread owns one 16-byte chunk (8 channels)
+// and strides over pixels; 256 threads = 32 pixels x 8 chunks per step, shared-memory tree, 64 atomics per CTA.
+__global__ void __launch_bounds__(256)
+dcn_bwd_bias_nhwc(const __nv_bfloat16* __restrict__ gout, float* __restrict__ gbias, int n, long long HW,
+                  long long gs_n) {
+  __shared__ float red[32][CH + 1];
+  const int c = threadIdx.x & 7, p = threadIdx.x >> 3;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long total = (long long)n * HW;
+  for (long long i = (long long)blockIdx.x * 32 + p; i < total; i += (long long)gridDim.x * 32) {
+    const long long img = i / HW, pix = i - img * HW;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(gout + img * gs_n + pix * CH + c * 8));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { a[2 * e] += bf16lo_to_f32(w[e]); a[2 * e + 1] += bf16hi_to_f32(w[e]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[p][c * 8 + e] = a[e];
+  __syncthreads();
+  if (threadIdx.x < CH) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    atomicAdd(gbias + threadIdx.x, s);
+  }
+}
+
 // ==================================================================================================
 // data kernel: d(x), d(offset), d(mask)
 // ==================================================================================================
@@ -714,8 +741,8 @@ bool dcn_backward_tc_eligible(const int64_t* gs, const int64_t* xs, const int64_
 template <int DG>
 static int launch_bwd_tc(const void* gout, const int64_t* gs, const void* x, const int64_t* xs, const float* offset,
                          const float* mask, const void* weight, float* gx32, const int64_t* gxs, float* goffset,
-                         float* gmask, float* gweight32, const DcnGeom& g, void* workspace, unsigned which,
-                         cudaStream_t st) {
+                         float* gmask, float* gweight32, float* gbias32, const DcnGeom& g, void* workspace,
+                         unsigned which, cudaStream_t st) {
   using namespace bwd;
   const int H = g.H, W = g.W;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
@@ -758,20 +785,29 @@ static int launch_bwd_tc(const void* gout, const int64_t* gs, const void* x, con
                                               gweight32, H, W, (long long)xs[0], (long long)gs[0], tiles_x,
                                               tiles_per_img, total);
     rc = check_launch("dcn_backward(weight, tcgen05)");
+    if (rc) return rc;
+  }
+  if (gbias32) {
+    cudaMemsetAsync(gbias32, 0, CH * sizeof(float), st);
+    const long long px = (long long)g.N * H * W;
+    int blocks = (int)((px + 1023) / 1024);
+    blocks = blocks < 1 ? 1 : (blocks > 2 * sms ? 2 * sms : blocks);
+    dcn_bwd_bias_nhwc<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gout, gbias32, g.N, (long long)H * W, (long long)gs[0]);
+    rc = check_launch("dcn_backward(bias)");
   }
   return rc;
 }
 
-// which: bit 0 = data gradients, bit 1 = weight gradient on the tensor-core kernels
+// which: bit 0 = data gradients, bit 1 = weight gradient on the tensor-core kernels; d(bias) always (NHWC kernel)
 int dcn_backward_tc(const void* gout, const int64_t* gs, const void* x, const int64_t* xs, const float* offset,
                     const float* mask, const void* weight, float* gx32, const int64_t* gxs, float* goffset,
-                    float* gmask, float* gweight32, const DcnGeom& g, void* workspace, unsigned which,
+                    float* gmask, float* gweight32, float* gbias32, const DcnGeom& g, void* workspace, unsigned which,
                     cudaStream_t st) {
   switch (g.DG) {
-    case 8: return launch_bwd_tc<8>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, g, workspace, which, st);
-    case 4: return launch_bwd_tc<4>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, g, workspace, which, st);
-    case 2: return launch_bwd_tc<2>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, g, workspace, which, st);
-    case 1: return launch_bwd_tc<1>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, g, workspace, which, st);
+    case 8: return launch_bwd_tc<8>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
+    case 4: return launch_bwd_tc<4>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
+    case 2: return launch_bwd_tc<2>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
+    case 1: return launch_bwd_tc<1>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
   }
   set_error("dcn_backward: deform_groups %d not supported by the tensor-core path", g.DG);
   return EAVSR_ERR_INVALID;

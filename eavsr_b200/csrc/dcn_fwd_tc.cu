@@ -465,7 +465,7 @@ size_t dcn_backward_tc_workspace();
 bool dcn_backward_tc_eligible(const int64_t* gs, const int64_t* xs, const int64_t* gxs, const DcnGeom& g, bool has_gx);
 int dcn_backward_tc(const void* gout, const int64_t* gs, const void* x, const int64_t* xs, const float* offset,
                     const float* mask, const void* weight, float* gx32, const int64_t* gxs, float* goffset,
-                    float* gmask, float* gweight32, const DcnGeom& g, void* workspace, unsigned which,
+                    float* gmask, float* gweight32, float* gbias32, const DcnGeom& g, void* workspace, unsigned which,
                     cudaStream_t st);
 }  // namespace eavsr
 
@@ -504,8 +504,9 @@ extern "C" int eavsr_dcn_backward(const void* gout, const int64_t gout_strides[4
   }
   if (which) {
     rc = dcn_backward_tc(gout, gout_strides, x, x_strides, offset, mask, weight, gx32, gx_strides, goffset, gmask,
-                         gweight32, g, workspace, which, st);
+                         gweight32, gbias32, g, workspace, which, st);
     if (rc) return rc;
+    gbias32 = nullptr;
   }
   const bool tc_data = (which & 1u) != 0, tc_w = (which & 2u) != 0;
   return dcn_backward_generic<__nv_bfloat16>(gout, gout_strides, x, x_strides, offset, mask, weight,

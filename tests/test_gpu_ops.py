@@ -300,7 +300,8 @@ def test_dcn_backward_tensor_cores_match_generic_at_full_size(cuda):
 # correlation
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(2, 32, 20, 32), (1, 196, 5, 8), (8, 64, 4, 4), (8, 196, 1, 1), (2, 96, 10, 16),
-                                   (1, 7, 9, 13), (1, 16, 33, 70)])
+                                   (1, 7, 9, 13), (1, 16, 33, 70), (2, 20, 24, 72), (1, 32, 80, 128), (3, 9, 17, 44),
+                                   (2, 64, 16, 16), (1, 5, 18, 16)])
 def test_correlation_forward_backward(cuda, shape):
     g = torch.Generator().manual_seed(14)
     f1 = torch.randn(shape, generator=g)

@@ -18,7 +18,7 @@ if what == "corr":
     b = torch.randn(30, 32, 80, 128, generator=g).to(dev)
     for _ in range(3):
         E.FunctionCorrelation(tenFirst=a, tenSecond=b)
-elif what in ("dcn", "dcn_bwd"):
+elif what in ("dcn", "dcn_bwd", "dcn_bwd_nox"):
     h, w, dg = 270, 480, 8
     x = torch.randn(1, 64, h, w, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
     off = (torch.randn(1, dg * 18, h, w, generator=g) * 2).clamp(-12, 12).to(dev)
@@ -29,7 +29,7 @@ elif what in ("dcn", "dcn_bwd"):
         for _ in range(3):
             E.modulated_deform_conv2d(x, off, msk, wgt, bias, 1, 1, 1, 1, dg)
     else:
-        x.requires_grad_(); off.requires_grad_(); msk.requires_grad_(); wgt.requires_grad_(); bias.requires_grad_()
+        x.requires_grad_(what == "dcn_bwd"); off.requires_grad_(); msk.requires_grad_(); wgt.requires_grad_(); bias.requires_grad_()
         for _ in range(2):
             out = E.modulated_deform_conv2d(x, off, msk, wgt, bias, 1, 1, 1, 1, dg)
             out.backward(torch.ones_like(out))
