@@ -228,7 +228,7 @@ corr_fwd_f32(const float* __restrict__ f1, const float* __restrict__ f2, float* 
 }
 
 // ---- fp32 main path: TMA-staged halos, persistent CTAs -------------------------------------------
-// ncu of corr_fwd_f32 (profiles/r1_corr_fwd_ncu.txt): 47 M warp instructions of which only 25 M are FMAs --
+// ncu of corr_fwd_f32 (profiles/r1_corr_fwd_f32_ncu.txt): 47 M warp instructions of which only 25 M are FMAs --
 // the cp.async staging loops (index arithmetic per 16 bytes) cost as much issue bandwidth as a third of
 // the math, every CTA exposes the latency of its first chunk, and 1200 CTAs on 296 slots run 5 waves for
 // 4.05 waves of work.  Here one elected thread issues two cp.async.bulk.tensor (4-D tensor maps over
