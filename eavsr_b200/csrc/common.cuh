@@ -172,6 +172,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
+// One lane of a converged warp.  Unlike `lane == 0`, the compiler knows that exactly one thread is
+// active inside `if (elect_one())`, so warp-level instructions with uniform-register operands
+// (tcgen05.mma / commit, bulk copies) are emitted straight instead of inside an ELECT / BRA.U.ANY loop
+// that re-issues them once per possibly-active thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
 }

@@ -14,13 +14,17 @@
 // One MMA covers 128 consecutive halo positions = a 4 x 32 block of which 4 x 30 are real outputs
 // (the 2 wrap-around columns per row are computed and dropped: 6 % waste).
 //
-// Warp roles (288 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (416 threads, 1 CTA / SM, persistent over tiles):
 //   warps 0-3  producers: cp.async (zero-fill outside the image = conv padding) into a 3-stage ring
 //   warp  4    one lane issues 36 tcgen05.mma per tile (A: no-swizzle descriptors, B: 9 resident
 //              128B-swizzled 64x64 weight tiles) and commits to mbarriers
-//   warps 5-8  epilogue: tcgen05.ld -> +bias -> activation -> bf16 NHWC store, channel sums kept in
-//              registers across the CTA's tiles and flushed with one atomicAdd per channel
-// Two TMEM accumulators (2 x 64 columns) decouple the epilogue from the next tile's MMAs.
+//   warps 5-12 epilogue, two groups of four: group g drains output channels 32g .. 32g+31 of every tile:
+//              tcgen05.ld -> +bias -> activation -> bf16 NHWC store (32-byte st.global.v8), channel sums
+//              kept in registers across the CTA's tiles and flushed with one atomicAdd per channel.
+//              ncu stall sampling of the single-group version (profiles/r1_conv3x3_tc_ncu.txt) showed the
+//              epilogue as the serial critical path: as many samples on the store-drain (WAR on the STG
+//              source registers, 30 half-filled sectors per STG.128) as on the wait for the MMAs.
+// Two TMEM accumulators (2 x 64 columns) decouple the epilogues from the next tile's MMAs.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -38,7 +42,7 @@ constexpr int CV_ASTAGE = 8 * CV_PLANE;         // 8 chunks of 8 bf16 = 64 chann
 constexpr int CV_NS = 4;                        // one stage per producer warp
 constexpr int CV_BTILE = CV_CH * CV_CH * 2;     // 8 KB per tap
 constexpr int CV_PRODUCERS = 128;
-constexpr int CV_THREADS = 288;
+constexpr int CV_THREADS = 416;                 // 4 producer + 1 MMA + 2 x 4 epilogue warps
 constexpr int CV_TMEM = 128;
 
 struct CvSmem {
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ wpacked,
                   const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                   float* __restrict__ chan_sums, int H, int W, int tiles_x, int tiles_per_img, int total_tiles,
-                  float slope, int dbg) {
+                  float slope) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -96,7 +100,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_accf + 8 * b, 1);
-      mbar_init(bar_acce + 8 * b, 4);
+      mbar_init(bar_acce + 8 * b, 8);
     }
     mbar_init(bar_w, 1);
     fence_mbar_init();
@@ -147,7 +151,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_w, 9 * CV_BTILE);
       for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
       mbar_wait(bar_w, 0);
@@ -165,9 +169,9 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // descriptors differ from the bases only in the 16-byte-granular start address field
-            const uint64_t adesc = a_base + (uint64_t)(((dbg == 2 ? 0 : ((t / 3) * CV_PW + (t % 3)) * 16) + 2 * k * CV_PLANE) >> 4);
+            const uint64_t adesc = a_base + (uint64_t)((((t / 3) * CV_PW + (t % 3)) * 16 + 2 * k * CV_PLANE) >> 4);
             const uint64_t bdesc = b_base + (uint64_t)((t * CV_BTILE) >> 4) + 2 * k;
-            if (dbg != 1 || (t | k) == 0) umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
+            umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
           }
         }
         umma_commit(bar_empty + 8 * s);
@@ -176,23 +180,25 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 5..8 -> TMEM lane quadrants 1,2,3,0) =====================
+    // ===================== epilogue (warps 5..12 -> TMEM lane quadrants 1,2,3,0, 1,2,3,0) =====================
     const int q = warp & 3;                       // output row of the tile handled by this warp
-    float csum[CV_CH];                            // this thread's running channel sums (its pixels)
+    const int chalf = (warp - 5) >> 2;            // this group's 32 output channels
+    constexpr int HC = CV_CH / 2;
+    float csum[HC];                               // this thread's running channel sums (its pixels)
 #pragma unroll
-    for (int c = 0; c < CV_CH; ++c) csum[c] = 0.f;
-    const float* bsm = reinterpret_cast<const float*>(smem + CvSmem::BIAS_OFF);
+    for (int c = 0; c < HC; ++c) csum[c] = 0.f;
+    const float* bsm = reinterpret_cast<const float*>(smem + CvSmem::BIAS_OFF) + chalf * HC;
     int cur_n = -1;
     auto flush = [&]() {
       if (chan_sums && cur_n >= 0) {
-        // transpose-reduce over the 32 lanes: 62 shuffles leave lane l with the sums of channels 2l, 2l+1
-        // (step k adds (32 >> k) to the channel base when lane bit (16 >> k) is set: base = 2 * lane)
+        // transpose-reduce over the 32 lanes: 31 shuffles leave lane l with the sum of channel l of this half
+        // (step k adds (16 >> k) to the channel base when lane bit (16 >> k) is set: base = lane)
 #pragma unroll
         for (int step = 0; step < 5; ++step) {
-          const int m = 16 >> step, len = 32 >> step;
+          const int m = 16 >> step, len = 16 >> step;
           const bool up = (lane & m) != 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             if (i < len) {
               const float send = up ? csum[i] : csum[i + len];
               const float keep = up ? csum[i + len] : csum[i];
@@ -200,11 +206,10 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
             }
           }
         }
-        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane, csum[0]);
-        atomicAdd(chan_sums + cur_n * CV_CH + 2 * lane + 1, csum[1]);
+        atomicAdd(chan_sums + cur_n * CV_CH + chalf * HC + lane, csum[0]);
       }
 #pragma unroll
-      for (int c = 0; c < CV_CH; ++c) csum[c] = 0.f;
+      for (int c = 0; c < HC; ++c) csum[c] = 0.f;
     };
     for (int tl = 0; tl < my_tiles; ++tl) {
       const int buf = tl & 1;
@@ -215,32 +220,33 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       const bool valid = lane < CV_TC && oy < H && ox < W;
       mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
       tc_fence_after();
-      uint32_t acc[CV_CH];
-      tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH, acc);
-      tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH + 32, acc + 32);
+      uint32_t acc[HC];
+      tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH + chalf * HC, acc);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-      float f[CV_CH];
+      float f[HC];
 #pragma unroll
-      for (int c = 0; c < CV_CH; ++c) {
+      for (int c = 0; c < HC; ++c) {
         const float t = __uint_as_float(acc[c]) + bsm[c];
         f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
       }
       if (valid) {
-        __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH;
+        __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH + chalf * HC;
 #pragma unroll
-        for (int c = 0; c < CV_CH; c += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(f[c], f[c + 1]); u.y = pack_bf16x2(f[c + 2], f[c + 3]);
-          u.z = pack_bf16x2(f[c + 4], f[c + 5]); u.w = pack_bf16x2(f[c + 6], f[c + 7]);
-          *reinterpret_cast<uint4*>(op + c) = u;
+        for (int c = 0; c < HC; c += 16) {                   // one full 32-byte sector per store
+          uint32_t u[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[c + 2 * e], f[c + 2 * e + 1]);
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(op + c), "r"(u[0]), "r"(u[1]),
+                       "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                       : "memory");
         }
       }
       if (chan_sums) {
 #pragma unroll
-        for (int c = 0; c < CV_CH; ++c) csum[c] += f[c];
+        for (int c = 0; c < HC; ++c) csum[c] += f[c];
       }
     }
     flush();
@@ -291,8 +297,6 @@ extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(total < sms ? total : sms);
-  const char* dbg_env = getenv("EAVSR_CONV_DBG");      // timing experiments only (results are wrong when set)
-  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   if (channel_sums) {
     cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
     if (em != cudaSuccess) { set_error("conv3x3_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
@@ -302,6 +306,6 @@ extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, c
   conv3x3_tc_kernel<<<grid, CV_THREADS, CvSmem::DYN, st>>>((const __nv_bfloat16*)x, (const uint8_t*)packed_weight,
                                                           (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
                                                           channel_sums, h, w, tiles_x, tiles_per_img, (int)total,
-                                                          negative_slope, dbg);
+                                                          negative_slope);
   return check_launch("conv3x3_forward");
 }

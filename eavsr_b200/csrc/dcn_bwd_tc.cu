@@ -159,7 +159,7 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
 
   if (warp == CWARPS) {
     // ============ MMA issuer + weight-tile loader (one lane) ============
-    if (lane == 0) {
+    if (elect_one()) {
       auto issue_b = [&](int j) {
         const uint32_t bar = bar_bfull + 8 * (j % NSB);
         mbar_arrive_expect_tx(bar, B_TILE);
@@ -458,7 +458,7 @@ dcn_bwd_weight_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat1
 
   if (warp == CWARPS) {
     // ============ MMA issuer + window loader (one lane) ============
-    if (lane == 0) {
+    if (elect_one()) {
       auto load_window = [&](int tl) {
         int n, ty0, tx0;
         tile_coords(tl, n, ty0, tx0);

@@ -240,7 +240,7 @@ dcn_fwd_tc_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
       }
       fence_proxy_async_smem();  // generic-proxy writes (A tile, cp.async'd B) -> visible to the tensor core
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         const uint32_t bStage = sB + (it % NB_STAGES) * SM::B_STAGE;
         const uint64_t a_hi = umma_desc_sw128_kmajor(aStage), b_hi = umma_desc_sw128_kmajor(bStage);

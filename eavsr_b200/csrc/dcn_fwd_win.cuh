@@ -130,7 +130,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
   if (warp == PWARPS) {
     // ============ MMA issuer + weight-tile loader + window loader (one lane) ============
-    if (lane == 0) {
+    if (elect_one()) {
       auto issue_b = [&](int j) {
         const uint32_t bar = bar_bfull + 8 * (j % NSB);
         mbar_arrive_expect_tx(bar, B_TILE);

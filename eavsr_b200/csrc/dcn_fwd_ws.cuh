@@ -95,7 +95,7 @@ dcn_fwd_ws_kernel(const XT* __restrict__ x, const float* __restrict__ offset, co
 
   if (warp == PRODUCER_WARPS) {
     // ================= MMA issuer + weight-tile loader (one elected lane) =================
-    if (lane == 0) {
+    if (elect_one()) {
       auto issue_b = [&](int j) {
         const uint32_t bar = bar_bfull + 8 * (j % NS);
         mbar_arrive_expect_tx(bar, SM::B_STAGE);
