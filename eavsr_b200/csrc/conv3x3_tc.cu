@@ -7,10 +7,13 @@
 // D[128 positions x 64 cout] = sum_{tap} A_tap[128 x 64 cin] * W_tap[64 x 64]
 //
 // The trick that makes the nine A_tap operands free: the CTA stages ONE halo tile of the input
-// (6 rows x 32 columns of pixels) in the *non-swizzled* K-major UMMA layout
-// [16-byte channel chunk][pixel row][16 B].  In that layout consecutive pixels of one channel
-// chunk are 16 bytes apart, so the A operand of tap (r, s) is the same buffer with the descriptor
-// start address advanced by (r*32 + s) * 16 bytes -- no im2col, no re-staging, no second copy.
+// (6 rows x 32 columns of pixels) as a K-major, 128-byte-swizzled UMMA tile whose rows are the halo
+// pixels (128 B = 64 channels per row, 16-byte chunk c of row p stored at chunk c ^ (p & 7)).  The A
+// operand of tap (r, s) is the same buffer with the descriptor start address advanced by (r*32 + s)
+// rows (the 128B swizzle is a function of absolute address bits, so any whole-row shift of a tile that
+// was swizzled by absolute row index is again a valid operand) -- no im2col, no re-staging, no second copy.  (The first version used the non-swizzled layout with 16-byte rows; its tap views
+// started at 16-byte granularity, every 8x16 B core matrix straddled two 128-byte lines and the MMA
+// issue thread sat blocked on tcgen05.mma: profiles/r1_conv3x3_tc_ncu.txt.)
 // One MMA covers 128 consecutive halo positions = a 4 x 32 block of which 4 x 30 are real outputs
 // (the 2 wrap-around columns per row are computed and dropped: 6 % waste).
 //
@@ -37,8 +40,7 @@ constexpr int CV_TR = 4, CV_TC = 30;            // real outputs per tile
 constexpr int CV_PW = 32;                       // halo pitch in pixels (= MMA rows per output row)
 constexpr int CV_HROWS = (CV_TR + 2) * CV_PW;   // 192 staged halo positions
 constexpr int CV_ROWS = 200;                    // + padding rows read by the wrap-around outputs
-constexpr int CV_PLANE = CV_ROWS * 16 + 16;     // bytes per 16-byte-chunk plane (+16: bank spread)
-constexpr int CV_ASTAGE = 8 * CV_PLANE;         // 8 chunks of 8 bf16 = 64 channels
+constexpr int CV_ASTAGE = CV_ROWS * 128;        // 200 rows of 64 bf16 (25 x 1024 B: stages stay atom-aligned)
 constexpr int CV_NS = 4;                        // one stage per producer warp
 constexpr int CV_BTILE = CV_CH * CV_CH * 2;     // 8 KB per tap
 constexpr int CV_PRODUCERS = 128;
@@ -54,17 +56,6 @@ struct CvSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * CV_NS + 5) * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
 };
-
-// no-swizzle K-major descriptor: core matrix = 8 rows x 16 B contiguous; SBO = 128 B between
-// 8-row groups (rows are 16 B apart), LBO = distance between the two 16-byte K chunks of one MMA.
-__device__ __forceinline__ uint64_t umma_desc_nosw_kmajor(uint32_t addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)(128 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
 
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;
@@ -107,10 +98,9 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   }
   if (tid < CV_CH) reinterpret_cast<float*>(smem + CvSmem::BIAS_OFF)[tid] = bias ? __bfloat162float(bias[tid]) : 0.f;
   // zero the padding rows of every stage once (they only feed dropped wrap-around outputs)
-  for (int i = tid; i < CV_NS * 8 * (CV_ROWS - CV_HROWS + 1); i += CV_THREADS) {
-    const int s = i / (8 * (CV_ROWS - CV_HROWS + 1)), r = i % (8 * (CV_ROWS - CV_HROWS + 1));
-    const int ch = r / (CV_ROWS - CV_HROWS + 1), row = CV_HROWS + r % (CV_ROWS - CV_HROWS + 1);
-    *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + s * CV_ASTAGE + ch * CV_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < CV_NS * (CV_ROWS - CV_HROWS) * 8; i += CV_THREADS) {
+    const int s = i / ((CV_ROWS - CV_HROWS) * 8), r = i % ((CV_ROWS - CV_HROWS) * 8);
+    *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + s * CV_ASTAGE + CV_HROWS * 128 + r * 16) = make_uint4(0, 0, 0, 0);
   }
   if (warp == 4) tmem_alloc<CV_TMEM>(tmem_slot_addr);
   fence_proxy_async_smem();
@@ -141,7 +131,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
         const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
         const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
         const __nv_bfloat16* src = ok ? xn + ((size_t)gy * W + gx) * CV_CH + ch * 8 : xn;
-        cp_async_16_zfill(stage + ch * CV_PLANE + p * 16, src, ok);
+        cp_async_16_zfill(stage + p * 128 + ((ch ^ (p & 7)) << 4), src, ok);
       }
       cp_async_commit();
       cp_async_wait<0>();
@@ -162,14 +152,16 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
         if (tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
         mbar_wait(bar_full + 8 * s, (tl / CV_NS) & 1);
         tc_fence_after();
-        const uint64_t a_base = umma_desc_nosw_kmajor(sA + s * CV_ASTAGE, CV_PLANE);
+        const uint64_t a_base = umma_desc_sw128_kmajor(sA + s * CV_ASTAGE);
         const uint32_t d = tmem_d + buf * CV_CH;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // descriptors differ from the bases only in the 16-byte-granular start address field
-            const uint64_t adesc = a_base + (uint64_t)((((t / 3) * CV_PW + (t % 3)) * 16 + 2 * k * CV_PLANE) >> 4);
+            // tap view: start (r*32 + s) rows further; K step = 32 B.  The swizzle XOR is taken from the
+            // absolute shared-memory address bits, so the shifted view needs no base_offset (measured:
+            // base_offset = s gives wrong results, 0 is exact).
+            const uint64_t adesc = a_base + (uint64_t)((((t / 3) * CV_PW + (t % 3)) * 128) >> 4) + 2 * k;
             const uint64_t bdesc = b_base + (uint64_t)((t * CV_BTILE) >> 4) + 2 * k;
             umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
           }
