@@ -59,7 +59,7 @@ _SIGNATURES = {
     "eavsr_conv3x3_packed_weight_bytes": (c_size_t, []),
     "eavsr_conv3x3_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "eavsr_conv3x3_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _PF] + [c_int] * 5 +
-                              [c_float, c_int, c_void_p]),
+                              [c_float, c_int, c_uint, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

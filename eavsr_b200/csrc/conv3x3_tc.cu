@@ -51,7 +51,8 @@ struct CvSmem {
   static constexpr int B_OFF = 0;                                  // 9 x 8 KB, 1024-aligned
   static constexpr int A_OFF = B_OFF + 9 * CV_BTILE;               // 3 stages
   static constexpr int BIAS_OFF = ((A_OFF + CV_NS * CV_ASTAGE + 15) / 16) * 16;   // 64 fp32
-  static constexpr int BAR_OFF = BIAS_OFF + CV_CH * 4;
+  static constexpr int RED_OFF = BIAS_OFF + CV_CH * 4;             // 64 fp32: per-CTA channel sums before the atomics
+  static constexpr int BAR_OFF = RED_OFF + CV_CH * 4;
   // full[NS], empty[NS], accf[2], acce[2], wbar, tmem slot
   static constexpr int TOTAL = BAR_OFF + (2 * CV_NS + 5) * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
@@ -84,6 +85,14 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CvSmem::BAR_OFF + (2 * CV_NS + 5) * 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // The 72 KB of packed weights start streaming before anything else is set up (the launch is short --
+  // ~8 tiles per CTA -- so every microsecond of prologue counts).
+  if (warp == 4 && elect_one()) {
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(bar_w, 9 * CV_BTILE);
+    for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
+  }
   if (tid == 0) {
     for (int s = 0; s < CV_NS; ++s) {
       mbar_init(bar_full + 8 * s, 32);
@@ -93,7 +102,6 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       mbar_init(bar_accf + 8 * b, 1);
       mbar_init(bar_acce + 8 * b, 8);
     }
-    mbar_init(bar_w, 1);
     fence_mbar_init();
   }
   if (tid < CV_CH) reinterpret_cast<float*>(smem + CvSmem::BIAS_OFF)[tid] = bias ? __bfloat162float(bias[tid]) : 0.f;
@@ -102,15 +110,32 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     const int s = i / ((CV_ROWS - CV_HROWS) * 8), r = i % ((CV_ROWS - CV_HROWS) * 8);
     *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + s * CV_ASTAGE + CV_HROWS * 128 + r * 16) = make_uint4(0, 0, 0, 0);
   }
+  const int first = blockIdx.x;
+  const int my_tiles = (total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
+  // producer warp w streams the halo tile of tile tl (== w mod 4) into stage w
+  auto issue_tile = [&](int tl) {
+    const int tile = first + tl * (int)gridDim.x;
+    const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+    const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+    const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
+    const uint32_t stage = sA + warp * CV_ASTAGE;
+#pragma unroll 4
+    for (int i = lane; i < CV_HROWS * 8; i += 32) {
+      const int p = i >> 3, ch = i & 7;
+      const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+      const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+      const __nv_bfloat16* src = ok ? xn + ((size_t)gy * W + gx) * CV_CH + ch * 8 : xn;
+      cp_async_16_zfill(stage + p * 128 + ((ch ^ (p & 7)) << 4), src, ok);
+    }
+    cp_async_commit();
+  };
+  if (warp < 4 && warp < my_tiles) issue_tile(warp);         // first loads in flight before the set-up barrier
   if (warp == 4) tmem_alloc<CV_TMEM>(tmem_slot_addr);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-
-  const int first = blockIdx.x;
-  const int my_tiles = (total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < 4) {
     // ===================== producers =====================
@@ -119,21 +144,10 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     // to four tiles are in flight and a late MMA never delays the publication of a landed tile.
     for (int tl = warp; tl < my_tiles; tl += CV_NS) {
       const int u = tl / CV_NS;
-      if (u >= 1) mbar_wait(bar_empty + 8 * warp, (u - 1) & 1);
-      const int tile = first + tl * (int)gridDim.x;
-      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-      const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
-      const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
-      const uint32_t stage = sA + warp * CV_ASTAGE;
-#pragma unroll 4
-      for (int i = lane; i < CV_HROWS * 8; i += 32) {
-        const int p = i >> 3, ch = i & 7;
-        const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
-        const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-        const __nv_bfloat16* src = ok ? xn + ((size_t)gy * W + gx) * CV_CH + ch * 8 : xn;
-        cp_async_16_zfill(stage + p * 128 + ((ch ^ (p & 7)) << 4), src, ok);
+      if (u >= 1) {
+        mbar_wait(bar_empty + 8 * warp, (u - 1) & 1);
+        issue_tile(tl);                                      // (the first tile of this warp was issued in the prologue)
       }
-      cp_async_commit();
       cp_async_wait<0>();
       fence_proxy_async_smem();
       __syncwarp();
@@ -142,8 +156,6 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar_w, 9 * CV_BTILE);
-      for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_CH);
       const uint64_t b_base = umma_desc_sw128_kmajor(sB);
@@ -198,7 +210,15 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
             }
           }
         }
-        atomicAdd(chan_sums + cur_n * CV_CH + chalf * HC + lane, csum[0]);
+        // four warps hold the same 32 channels: combine them in shared memory, one global atomic per
+        // channel and CTA (148 instead of 592 reductions on each of the 64 addresses)
+        float* red = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");       // previous flush fully drained
+        if (q == 0) red[chalf * HC + lane] = csum[0];
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        if (q != 0) atomicAdd(red + chalf * HC + lane, csum[0]);
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        if (q == 0) atomicAdd(chan_sums + cur_n * CV_CH + chalf * HC + lane, red[chalf * HC + lane]);
       }
 #pragma unroll
       for (int c = 0; c < HC; ++c) csum[c] = 0.f;
@@ -270,7 +290,7 @@ extern "C" int eavsr_conv3x3_pack_weight(const void* weight, void* packed, int c
 
 extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
                                      float* channel_sums, int n, int cin, int cout, int h, int w,
-                                     float negative_slope, int dtype, void* stream) {
+                                     float negative_slope, int dtype, unsigned flags, void* stream) {
   EAVSR_REQUIRE(x && packed_weight && out, "conv3x3_forward: null pointer");
   EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_forward: empty tensor");
   if (cin != CV_CH || cout != CV_CH || dtype != EAVSR_BF16) {
@@ -289,7 +309,7 @@ extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(total < sms ? total : sms);
-  if (channel_sums) {
+  if (channel_sums && !(flags & EAVSR_CONV_SUMS_PREZEROED)) {
     cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
     if (em != cudaSuccess) { set_error("conv3x3_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
   }

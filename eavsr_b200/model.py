@@ -49,13 +49,13 @@ class _RCABlock(nn.Module):
         self.res = nn.Sequential(nn.Conv2d(ch, ch, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv2d(ch, ch, 3, 1, 1))
         self.ca = _CALayer(ch)
 
-    def forward(self, x):
+    def forward(self, x, sums_buf=None):
         du = self.ca.conv_du
         if conv3x3_64_eligible(self.res[0], x):
             # both convolutions on tcgen05: bias+ReLU in the first epilogue, bias + the channel sums of
             # the attention layer in the second; then one scale+residual pass.  3 kernels per block.
             h = conv3x3_64(self.res[0], x, 0.0)
-            res, sums = conv3x3_64(self.res[2], h, 1.0, want_sums=True)
+            res, sums = conv3x3_64(self.res[2], h, 1.0, want_sums=True, sums_out=sums_buf)
             return ca_scale(res, x, sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16)
         if x.shape[1] == 64 and fused_inference_ok(x, self.res[0].weight):
             # conv+bias+ReLU epilogue in one pass, second conv bias-free (its bias is folded into the
@@ -74,8 +74,11 @@ class _RCAGroup(nn.Module):
 
     def forward(self, x):
         y = x
-        for blk in self.rg[:-1]:
-            y = blk(y)
+        pool = None
+        if conv3x3_64_eligible(self.rg[-1], x):      # one zeroed buffer for the channel sums of all blocks
+            pool = torch.zeros((len(self.rg) - 1, x.shape[0], 64), dtype=torch.float32, device=x.device)
+        for i, blk in enumerate(self.rg[:-1]):
+            y = blk(y, None if pool is None else pool[i])
         if conv3x3_64_eligible(self.rg[-1], y):
             return conv3x3_64(self.rg[-1], y, 1.0) + x
         return conv2d_bias_act(self.rg[-1], y, 1.0) + x

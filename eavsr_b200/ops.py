@@ -557,20 +557,29 @@ def _packed_conv_weight(conv: nn.Conv2d, device) -> torch.Tensor:
     return packed
 
 
-def conv3x3_64(conv: nn.Conv2d, x, negative_slope: float = 1.0, want_sums: bool = False):
+def conv3x3_64(conv: nn.Conv2d, x, negative_slope: float = 1.0, want_sums: bool = False, sums_out=None):
     """``LeakyReLU_slope(conv(x))`` for a 64->64 3x3 stride-1 pad-1 convolution on tcgen05 (bf16
     channels_last, inference).  With ``want_sums`` also returns the per-(n, channel) sums of the
-    output over (h, w) in fp32, computed in the epilogue.  Check `conv3x3_64_eligible` first."""
+    output over (h, w) in fp32, computed in the epilogue; ``sums_out`` is an already ZEROED (n, 64)
+    fp32 buffer to accumulate them into (one memset for a whole residual group instead of one per
+    convolution).  Check `conv3x3_64_eligible` first."""
     lib = L.load()
     n, c, h, w = x.shape
     with torch.cuda.device(x.device):
         xd = x.contiguous(memory_format=torch.channels_last)
         out = torch.empty_like(xd)
-        sums = torch.empty((n, 64), dtype=torch.float32, device=x.device) if want_sums else None
+        sums = None
+        if want_sums:
+            if sums_out is not None:
+                assert sums_out.shape == (n, 64) and sums_out.dtype == torch.float32 and sums_out.is_contiguous()
+                sums = sums_out
+            else:
+                sums = torch.empty((n, 64), dtype=torch.float32, device=x.device)
         packed = _packed_conv_weight(conv, x.device)
         bias = conv.bias.detach().to(torch.bfloat16).contiguous() if conv.bias is not None else None
         L.check(lib.eavsr_conv3x3_forward(xd.data_ptr(), packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(sums),
-                                          n, 64, 64, h, w, float(negative_slope), L.BF16, _stream(xd)),
+                                          n, 64, 64, h, w, float(negative_slope), L.BF16,
+                                          1 if (want_sums and sums_out is not None) else 0, _stream(xd)),
                 "conv3x3_forward")
     return (out, sums) if want_sums else out
 

@@ -180,15 +180,17 @@ int eavsr_ca_scale_forward(const void* res, const void* skip, const float* sums,
  * models/networks.py:449-482) -------------------------------------------------------------------
  * x, out: (n,64,h,w) dense NHWC bf16, stride 1, pad 1.  out = LeakyReLU_slope(conv(x) + bias)
  * (slope 1 = none, 0 = ReLU).  If channel_sums != NULL it receives sum over (h,w) of `out` per
- * (n, channel) in fp32 (zero-filled by the call) -- the global average pool of CALayer for free.
+ * (n, channel) in fp32 -- the global average pool of CALayer for free.  The call zero-fills it unless
+ * EAVSR_CONV_SUMS_PREZEROED is set in `flags` (the caller zeroes one buffer for a whole residual group).
  * Weights are packed once with eavsr_conv3x3_pack_weight into eavsr_conv3x3_packed_weight_bytes()
  * bytes (16-byte aligned). */
 size_t eavsr_conv3x3_packed_weight_bytes(void);
 int eavsr_conv3x3_pack_weight(const void* weight /* (64,64,3,3) */, void* packed, int cin, int cout, int dtype,
                               void* stream);
+#define EAVSR_CONV_SUMS_PREZEROED 1u
 int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
                           float* channel_sums, int n, int cin, int cout, int h, int w, float negative_slope,
-                          int dtype, void* stream);
+                          int dtype, unsigned flags, void* stream);
 
 #ifdef __cplusplus
 }

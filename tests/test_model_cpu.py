@@ -20,7 +20,7 @@ def oracle_ops(monkeypatch):
     monkeypatch.setattr(M, "flow_warp", lambda x, f, padding_mode="zeros": O.flow_warp(x, f.to(x.dtype), "n2hw", padding_mode))
     monkeypatch.setattr(M, "flow_warp_nhw2", lambda x, f, padding_mode="zeros": O.flow_warp(x, f.to(x.dtype), "nhw2", padding_mode))
     monkeypatch.setattr(M, "modulated_deform_conv2d",
-                        lambda x, off, m, w, b, s, p, d, g, dg: O.modulated_deform_conv2d(x, off, m, w, b, s, p, d, g, dg))
+                        lambda x, off, m, w, b, s, p, d, g, dg, static_weight=False: O.modulated_deform_conv2d(x, off, m, w, b, s, p, d, g, dg))
 
 
 @pytest.mark.parametrize("scale,t", [(4, 4), (2, 3)])
