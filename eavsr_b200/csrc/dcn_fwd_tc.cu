@@ -322,8 +322,8 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
   const int grid = total < sms * per_sm ? total : sms * per_sm;
   const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
-  if constexpr (DG <= 8 && !SPLIT) {
-    if (!(flags & (EAVSR_DCN_FORCE_V1 | EAVSR_DCN_FORCE_WS)) && (long long)h * w <= (1ll << 24)) {
+  if constexpr (!SPLIT) {
+    if (!(flags & (EAVSR_DCN_FORCE_V1 | EAVSR_DCN_FORCE_WS)) && (long long)h * w <= (DG == 16 ? (1ll << 23) : (1ll << 24))) {
       // third generation: shared-memory window gather (bf16)
       const bool vecw = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(offset) & 15u) == 0) &&
                         ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
@@ -335,9 +335,9 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
                 __nv_bfloat16*, int, int, long long, long long, int, int, int) =
           vecw ? (b16 ? win::dcn_fwd_win_kernel<DG, true, true> : win::dcn_fwd_win_kernel<DG, true, false>)
                : (b16 ? win::dcn_fwd_win_kernel<DG, false, true> : win::dcn_fwd_win_kernel<DG, false, false>);
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, win::Smem::DYN);
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, win::Cfg<DG>::DYN);
       if (e != cudaSuccess) { set_error("dcn_forward(win): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
-      k<<<g3, win::THREADS, win::Smem::DYN, st>>>((const __nv_bfloat16*)x, offset, mask, (const uint8_t*)workspace,
+      k<<<g3, win::THREADS, win::Cfg<DG>::DYN, st>>>((const __nv_bfloat16*)x, offset, mask, (const uint8_t*)workspace,
                                                  (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0], os[0],
                                                  tiles_x, tpi, tot);
       return check_launch("dcn_forward(win)");

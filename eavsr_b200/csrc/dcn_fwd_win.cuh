@@ -26,25 +26,32 @@ namespace win {
 constexpr int PWARPS = 16;
 constexpr int THREADS = (PWARPS + 1) * 32;   // 544
 constexpr int TH = 8, TW = 16;               // tile
-constexpr int PAD = 5;
-constexpr int WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 18 x 26 window
-constexpr int WIN_BYTES = WH * WW * 128;     // 59 904
 constexpr int CH = 64, TAPS = 9;
 constexpr int A_TILE = 128 * CH * 2;         // 16 KB
 constexpr int B_TILE = CH * CH * 2;          // 8 KB
 constexpr int NSA = 3, NSB = 2;
 constexpr int PLW = 8;                       // staged offset plane: 8 pixels, XOR-swizzled (no padding)
-constexpr int MAX_PLANES = 24;
-constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 768 B
-// Offsets/masks come from HBM with ~1.5 us latency and each (tile, tap) needs 12 KB of them; with a
-// prefetch distance of 2 taps the first versions had only ~24 KB per SM in flight (Little: 2.4 TB/s
-// for the whole chip = the ~100 us floor every earlier kernel hit).  3 buffers -> distance 2 (deeper did not pay: the A ring depth did).
-constexpr int NOB = 3;
 constexpr int TMEM_COLS = 128;
 
-struct Smem {
+// Per-deform_groups configuration.  deform_groups <= 8: one 16-byte chunk (8 channels) belongs to one
+// group, 5-pixel apron, 3 offset buffers per warp.  deform_groups = 16 (BASELINE config 2): a chunk holds
+// two groups of 4 channels (two samples with their own offsets per 16 bytes of the A tile, 8-byte corner
+// loads) and 48 offset/mask planes per tap; the planes take twice the room, so the apron shrinks to 4
+// pixels and the offset ring to 2 buffers to stay inside 227 KB.
+// Offsets/masks come from HBM with ~1.5 us latency and each (tile, tap) needs 12 KB of them; with a
+// prefetch distance of 2 taps the first versions had only ~24 KB per SM in flight (Little: 2.4 TB/s
+// for the whole chip = the ~100 us floor every earlier kernel hit).  3 buffers -> distance 2 (deeper
+// did not pay: the A ring depth did).
+template <int DG> struct Cfg {
+  static constexpr int NSUB = DG == 16 ? 2 : 1;           // samples (groups) per 16-byte chunk
+  static constexpr int PAD = DG == 16 ? 4 : 5;
+  static constexpr int WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 18 x 26 (16 x 24) window
+  static constexpr int WIN_BYTES = WH * WW * 128;              // 59 904 (49 152)
+  static constexpr int NOB = DG == 16 ? 2 : 3;
+  static constexpr int MAX_PLANES = DG == 16 ? 48 : 24;
+  static constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;    // 768 B (1 536 B)
   static constexpr int WIN_OFF = 0;
-  static constexpr int A_OFF = WIN_OFF + 2 * WIN_BYTES;                    // 119 808 (1024-aligned: 117 KB)
+  static constexpr int A_OFF = WIN_OFF + 2 * WIN_BYTES;        // multiple of 1024
   static constexpr int B_OFF = A_OFF + NSA * A_TILE;
   static constexpr int OFFS_OFF = B_OFF + NSB * B_TILE;
   static constexpr int BAR_OFF = OFFS_OFF + PWARPS * NOB * OFF_WARP_BUF;
@@ -52,8 +59,10 @@ struct Smem {
   static constexpr int NBARS = 2 * NSA + NSB + 8;
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
+  static_assert(A_OFF % 1024 == 0, "A stages must be 1024-byte aligned for the 128B swizzle");
+  static_assert(DYN <= 232448, "shared memory budget");
 };
-static_assert(Smem::A_OFF % 1024 == 0, "A stages must be 1024-byte aligned for the 128B swizzle");
+using Smem = Cfg<8>;                         // layout shared by deform_groups 1, 2, 4, 8
 
 __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -64,6 +73,11 @@ __device__ __forceinline__ uint32_t hfma2_bf16(uint32_t a, uint32_t b, uint32_t 
   uint32_t d;
   asm("fma.rn.bf16x2 %0, %1, %2, %3;\n" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -77,8 +91,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                    const float* __restrict__ mask, const uint8_t* __restrict__ wpacked,
                    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
                    long long xs_n, long long os_n, int tiles_x, int tiles_per_img, int total_tiles) {
-  static_assert(DG <= 8, "window kernel: deform_groups <= 8");
-  static_assert(NSA == NOB, "the A ring and the offset ring share one counter");
+  using C = Cfg<DG>;
+  using Smem = Cfg<DG>;
+  constexpr int NSUB = C::NSUB, PAD = C::PAD, WH = C::WH, WW = C::WW, WIN_BYTES = C::WIN_BYTES;
+  constexpr int NOB = C::NOB, OFF_WARP_BUF = C::OFF_WARP_BUF;
   constexpr int NPLANES = 3 * DG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -184,13 +200,11 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   } else {
     // ============ producers: window gather -> blend -> swizzled A stage ============
     const int q = lane >> 3, l = lane & 7;
-    const int grp = (l * DG) / 8;
     const int wrow = warp >> 1, wcol = (warp & 1) * 8;       // this warp: tile row wrow, columns wcol..wcol+7
     const uint32_t offBase = sbase + Smem::OFFS_OFF + warp * NOB * OFF_WARP_BUF;
     const float* offF = reinterpret_cast<const float*>(smem + Smem::OFFS_OFF + warp * NOB * OFF_WARP_BUF);
-    // column swizzle of the staged planes: groups 4..7 swap the two 4-pixel halves, which makes the
-    // 32 lanes (8 groups x 4 pixels) of one load hit 32 distinct banks without padding
-    const int colx = (grp >> 2) << 2;
+    // column swizzle of the staged planes: groups 4..7 (12..15) swap the two 4-pixel halves, which makes
+    // the 32 lanes (8 groups x 4 pixels) of one load hit 32 distinct banks without padding
 
     // Offset/mask prefetch stream, 3 taps ahead of the gather.  Everything that needs an integer
     // division (tile -> image / row / column) is done once per tile, not once per tap.
@@ -210,7 +224,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       cp_mask[k] = comp == 2;
       cp_rel[k] = (comp < 2 ? (uint32_t)(g * TAPS * 2 + comp) : (uint32_t)(g * TAPS)) * (uint32_t)HW + (uint32_t)(cp_col[k] & 15);
       cp_step[k] = (comp < 2 ? 2u : 1u) * (uint32_t)HW;
-      cp_dst[k] = (uint32_t)(plane * PLW + ((cp_col[k] & 15) ^ ((g >> 2) << 2))) * 4u;
+      cp_dst[k] = (uint32_t)(plane * PLW + ((cp_col[k] & 15) ^ (((g >> 2) & 1) << 2))) * 4u;
     }
     auto make_ref = [&](int tl) {
       TileRef r;
@@ -283,9 +297,9 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       }
     };
 
-    prefetch_next();
-    prefetch_next();
-    int it = 0, ring = 0;                 // ring = it % NSA (= it % NOB), ring_ph = parity of it / NSA
+#pragma unroll
+    for (int i = 0; i < NOB - 1; ++i) prefetch_next();
+    int it = 0, ring = 0, oring = 0;      // ring = it % NSA, ring_ph = parity of it / NSA, oring = it % NOB
     uint32_t ring_ph = 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
       int n, ty0, tx0;
@@ -318,87 +332,108 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       }
       mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);       // this tile's window has landed
       for (int tap = 0; tap < TAPS; ++tap, ++it) {
-        cp_async_wait<1>();                                    // offsets of `it` have landed
+        cp_async_wait<NOB - 2>();                              // offsets of `it` have landed
         __syncwarp();                                          // ... and everyone left buffer (it-1) % NOB
         prefetch_next();
-        const float* so = offF + ring * (OFF_WARP_BUF / 4);
+        const float* so = offF + oring * (OFF_WARP_BUF / 4);
+        if (++oring == NOB) oring = 0;
         const int ti = (tap * 11) >> 5, tj = tap - ti * 3;       // tap / 3 for tap < 9
         uint32_t res[2][4];
-        // The two items of a thread are advanced in lock step (phase by phase), so that the scheduler
-        // always has two independent dependency chains per warp: the kernel is latency bound
-        // (ncu: "wait" and scoreboard stalls dominate with 4 warps per scheduler).
-        float wy0f[2], wy1f[2], wx0f[2], wx1f[2];
-        int y0[2], x0[2], ry[2], rx[2];
-        bool inwin[2];
+        // The samples of a thread (2 items x NSUB groups per 16-byte chunk) are advanced in lock step
+        // (phase by phase), so that the scheduler always has independent dependency chains per warp: the
+        // kernel is latency bound (ncu: "wait" and scoreboard stalls dominate with 4 warps per scheduler).
+        constexpr int NI = 2 * NSUB;         // samples per thread and tap
+        constexpr int CW = 4 / NSUB;         // 32-bit words per corner (8 or 4 channels)
+        float wy0f[NI], wy1f[NI], wx0f[NI], wx1f[NI];
+        int y0[NI], x0[NI], ry[NI], rx[NI];
+        bool inwin[NI];
+        bool allin = true;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int col = (j * 4 + q) ^ colx;
-          const float dy = so[(0 * DG + grp) * PLW + col];
-          const float dx = so[(1 * DG + grp) * PLW + col];
-          const float mk = so[(2 * DG + grp) * PLW + col];
+        for (int u = 0; u < NI; ++u) {
+          const int j = u / NSUB, sb = u % NSUB;
+          const int g = NSUB == 2 ? 2 * l + sb : (l * DG) / 8;
+          const int col = (j * 4 + q) ^ (((g >> 2) & 1) << 2);
+          const float dy = so[(0 * DG + g) * PLW + col];
+          const float dx = so[(1 * DG + g) * PLW + col];
+          const float mk = so[(2 * DG + g) * PLW + col];
           const float py = (pyb[j] + (float)ti) + dy;
           const float px = (pxb[j] + (float)tj) + dx;
           // floor via a saturating float->int conversion (NaN -> 0, +-huge -> INT_MIN/MAX: such cells fail
           // the window test and are rejected by the validity tests of the far path)
-          y0[j] = __float2int_rd(py); x0[j] = __float2int_rd(px);
-          const float ly = py - (float)y0[j], lx = px - (float)x0[j];
-          wy0f[j] = mk * (1.f - ly); wy1f[j] = mk * ly; wx0f[j] = 1.f - lx; wx1f[j] = lx;
+          y0[u] = __float2int_rd(py); x0[u] = __float2int_rd(px);
+          const float ly = py - (float)y0[u], lx = px - (float)x0[u];
+          wy0f[u] = mk * (1.f - ly); wy1f[u] = mk * ly; wx0f[u] = 1.f - lx; wx1f[u] = lx;
           // both rows / columns of the 2x2 cell inside the window?
-          ry[j] = y0[j] - wy0; rx[j] = x0[j] - wx0;
-          inwin[j] = (unsigned)ry[j] < (unsigned)(WH - 1) && (unsigned)rx[j] < (unsigned)(WW - 1);
+          ry[u] = y0[u] - wy0; rx[u] = x0[u] - wx0;
+          inwin[u] = (unsigned)ry[u] < (unsigned)(WH - 1) && (unsigned)rx[u] < (unsigned)(WW - 1);
+          allin = allin && inwin[u];
         }
-        uint4 v[2][4];
-        if (__all_sync(0xffffffffu, inwin[0] && inwin[1])) {   // warp-uniform common case: 8 LDS.128, no tests
+        uint32_t v[NI][4][CW];               // [sample][corner][words]
+        auto load_win = [&](int u) {
+          const uint32_t a00 = win + (uint32_t)(ry[u] * WW + rx[u]) * 128u + (u % NSUB) * 8u;
+          const uint32_t ad[4] = {a00, a00 + 128u, a00 + WW * 128u, a00 + WW * 128u + 128u};
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t a00 = win + (uint32_t)(ry[j] * WW + rx[j]) * 128u;
-            v[j][0] = lds128(a00); v[j][1] = lds128(a00 + 128u);
-            v[j][2] = lds128(a00 + WW * 128u); v[j][3] = lds128(a00 + WW * 128u + 128u);
+          for (int c = 0; c < 4; ++c) {
+            if (CW == 4) {
+              const uint4 t = lds128(ad[c]);
+              v[u][c][0] = t.x; v[u][c][1] = t.y; v[u][c][CW - 2] = t.z; v[u][c][CW - 1] = t.w;
+            } else {
+              const uint2 t = lds64(ad[c]);
+              v[u][c][0] = t.x; v[u][c][1] = t.y;
+            }
           }
+        };
+        if (__all_sync(0xffffffffu, allin)) {                  // warp-uniform common case: no tests
+#pragma unroll
+          for (int u = 0; u < NI; ++u) load_win(u);
         } else {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (inwin[j]) {
-              const uint32_t a00 = win + (uint32_t)(ry[j] * WW + rx[j]) * 128u;
-              v[j][0] = lds128(a00); v[j][1] = lds128(a00 + 128u);
-              v[j][2] = lds128(a00 + WW * 128u); v[j][3] = lds128(a00 + WW * 128u + 128u);
+          for (int u = 0; u < NI; ++u) {
+            if (inwin[u]) {
+              load_win(u);
             } else {                                           // far sample: global gather with explicit validity
-              const int yy = y0[j], xx = x0[j];
-              wy0f[j] = ((unsigned)yy < (unsigned)H) ? wy0f[j] : 0.f;
-              wy1f[j] = ((unsigned)yy + 1u < (unsigned)H) ? wy1f[j] : 0.f;
-              wx0f[j] = ((unsigned)xx < (unsigned)W) ? wx0f[j] : 0.f;
-              wx1f[j] = ((unsigned)xx + 1u < (unsigned)W) ? wx1f[j] : 0.f;
+              const int yy = y0[u], xx = x0[u];
+              wy0f[u] = ((unsigned)yy < (unsigned)H) ? wy0f[u] : 0.f;
+              wy1f[u] = ((unsigned)yy + 1u < (unsigned)H) ? wy1f[u] : 0.f;
+              wx0f[u] = ((unsigned)xx < (unsigned)W) ? wx0f[u] : 0.f;
+              wx1f[u] = ((unsigned)xx + 1u < (unsigned)W) ? wx1f[u] : 0.f;
               const int ys = min(max(yy, -1), H), xs = min(max(xx, -1), W);      // keep the +1 below defined
               const int cy0 = min(max(ys, 0), H - 1), cy1 = min(max(ys + 1, 0), H - 1);
               const int cx0 = min(max(xs, 0), W - 1), cx1 = min(max(xs + 1, 0), W - 1);
-              const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
+              const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8 + (u % NSUB) * 4;
               const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
-              v[j][0] = __ldg(reinterpret_cast<const uint4*>(xn + b00));
-              v[j][1] = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
-              v[j][2] = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
-              v[j][3] = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
+              const uint32_t bo[4] = {b00, (uint32_t)(b00 + sx), (uint32_t)(b00 + sy), (uint32_t)(b00 + sy + sx)};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (CW == 4) {
+                  const uint4 t = __ldg(reinterpret_cast<const uint4*>(xn + bo[c]));
+                  v[u][c][0] = t.x; v[u][c][1] = t.y; v[u][c][CW - 2] = t.z; v[u][c][CW - 1] = t.w;
+                } else {
+                  const uint2 t = __ldg(reinterpret_cast<const uint2*>(xn + bo[c]));
+                  v[u][c][0] = t.x; v[u][c][1] = t.y;
+                }
+              }
             }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float w00 = wy0f[j] * wx0f[j], w01 = wy0f[j] * wx1f[j], w10 = wy1f[j] * wx0f[j], w11 = wy1f[j] * wx1f[j];
-          const uint32_t a[4] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w}, b[4] = {v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
-          const uint32_t c[4] = {v[j][2].x, v[j][2].y, v[j][2].z, v[j][2].w}, d[4] = {v[j][3].x, v[j][3].y, v[j][3].z, v[j][3].w};
+        for (int u = 0; u < NI; ++u) {
+          const int j = u / NSUB, sb = u % NSUB;
+          const float w00 = wy0f[u] * wx0f[u], w01 = wy0f[u] * wx1f[u], w10 = wy1f[u] * wx0f[u], w11 = wy1f[u] * wx1f[u];
           if (BLEND16) {
             const uint32_t p00 = pack_bf16x2(w00, w00), p01 = pack_bf16x2(w01, w01);
             const uint32_t p10 = pack_bf16x2(w10, w10), p11 = pack_bf16x2(w11, w11);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              res[j][e] = hfma2_bf16(p11, d[e], hfma2_bf16(p10, c[e], hfma2_bf16(p01, b[e], hmul2_bf16(p00, a[e]))));
+            for (int e = 0; e < CW; ++e)
+              res[j][sb * CW + e] = hfma2_bf16(p11, v[u][3][e], hfma2_bf16(p10, v[u][2][e], hfma2_bf16(p01, v[u][1][e], hmul2_bf16(p00, v[u][0][e]))));
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = w00 * bf16lo_to_f32(a[e]) + w01 * bf16lo_to_f32(b[e]) + w10 * bf16lo_to_f32(c[e]) +
-                               w11 * bf16lo_to_f32(d[e]);
-              const float hi = w00 * bf16hi_to_f32(a[e]) + w01 * bf16hi_to_f32(b[e]) + w10 * bf16hi_to_f32(c[e]) +
-                               w11 * bf16hi_to_f32(d[e]);
-              res[j][e] = pack_bf16x2(lo, hi);
+            for (int e = 0; e < CW; ++e) {
+              const float lo = w00 * bf16lo_to_f32(v[u][0][e]) + w01 * bf16lo_to_f32(v[u][1][e]) +
+                               w10 * bf16lo_to_f32(v[u][2][e]) + w11 * bf16lo_to_f32(v[u][3][e]);
+              const float hi = w00 * bf16hi_to_f32(v[u][0][e]) + w01 * bf16hi_to_f32(v[u][1][e]) +
+                               w10 * bf16hi_to_f32(v[u][2][e]) + w11 * bf16hi_to_f32(v[u][3][e]);
+              res[j][sb * CW + e] = pack_bf16x2(lo, hi);
             }
           }
         }

@@ -194,6 +194,22 @@ def test_dcn_tc_kernels_agree(cuda, shape):
     print(f"dcn bf16 rel err: fp32-blend {rel_err(w32, ref):.2e}  bf16x2-blend {rel_err(w16, ref):.2e}")
 
 
+@pytest.mark.parametrize("shape", [(1, 40, 72), (2, 37, 53), (1, 270, 480)])
+def test_dcn_window_kernel_deform_groups_16(cuda, shape):
+    """BASELINE config 2 (deform_groups = 16): two 4-channel groups per 16-byte chunk in the window
+    kernel.  With the fp32 blend it is bit-identical to the first-generation tcgen05 kernel; the default
+    bf16x2 blend stays inside the bf16 tolerance of the fp64 oracle."""
+    n, h, w = shape
+    x, off, mask, wgt, bias = dcn_inputs(n, 64, h, w, 64, 16, seed=31)
+    xb, wb, bb = _cl(x.bfloat16().to(cuda)), wgt.bfloat16().to(cuda), bias.bfloat16().to(cuda)
+    run = lambda fl: _ModulatedDeformConv2dFn.apply(xb, off.to(cuda), mask.to(cuda), wb, bb, 1, 1, 1, 1, 16, fl)   # noqa: E731
+    w16, w32, v1 = run(0), run(L.DCN_BLEND_FP32), run(L.DCN_FORCE_V1)
+    assert torch.equal(w32, v1)
+    ref = _dcn_ref(xb.cpu(), off, mask, wb.cpu(), bb.cpu(), dg=16)
+    assert rel_err(w32, ref) < BF16_REL
+    assert rel_err(w16, ref) < BF16_REL
+
+
 @pytest.mark.parametrize("cfg", [
     dict(cin=16, cout=8, k=3, stride=1, padding=1, dilation=1, groups=1, dg=4),
     dict(cin=16, cout=8, k=3, stride=2, padding=2, dilation=2, groups=2, dg=4),
