@@ -1,5 +1,5 @@
 // DCNv2 backward on tcgen05 / TMEM (sm_100a) for the model's configuration: 64 -> 64 channels, 3x3,
-// stride 1, pad 1, dilation 1, groups 1, deform_groups in {1,2,4,8}, bf16 NHWC features and gradients.
+// stride 1, pad 1, dilation 1, groups 1, deform_groups in {1,2,4,8,16}, bf16 NHWC features and gradients.
 //
 // Replaces, for that configuration, what mmcv runs under the autograd of models/networks.py:627-630:
 // modulated_deformable_col2im + col2im_coord over a 576 x P fp32 column-gradient buffer in HBM and
@@ -25,6 +25,7 @@ namespace eavsr {
 namespace bwd {
 
 using win::lds128;
+using win::lds64;
 
 constexpr int CWARPS = 16;
 constexpr int THREADS = (CWARPS + 1) * 32;      // 16 worker warps + 1 MMA / loader warp
@@ -220,8 +221,12 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
       }
     };
 
-    // offsets / mask of this thread's pixel for its two 8-channel chunks
-    struct Om { float dy[2], dx[2], mk[2]; };
+    // offsets / mask of this thread's pixel for the groups of its two 8-channel chunks
+    constexpr int NSUB = DG == 16 ? 2 : 1;    // groups (samples) per chunk
+    constexpr int NS = 2 * NSUB;              // samples per thread and tap
+    constexpr int CPS = 8 / NSUB;             // channels per sample
+    constexpr int CW = CPS / 2;               // 32-bit words per corner
+    struct Om { float dy[NS], dx[NS], mk[NS]; };
     auto load_om = [&](int tl, int tap) {
       Om o;
       int n, ty0, tx0;
@@ -229,14 +234,15 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
       const int gy = ty0 + prow, gx = tx0 + pcol;
       const bool live = gy < H && gx < W;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int g = ((2 * cq + j) * DG) >> 3;
+      for (int u = 0; u < NS; ++u) {
+        const int jc = 2 * cq + u / NSUB;
+        const int g = NSUB == 2 ? 2 * jc + u % NSUB : (jc * DG) >> 3;
         const size_t pix = (size_t)gy * W + gx;
         const size_t ob = ((size_t)(n * DG + g) * TAPS + tap) * 2 * HW + pix;
         const size_t mb = ((size_t)(n * DG + g) * TAPS + tap) * HW + pix;
-        o.dy[j] = live ? __ldg(offset + ob) : 0.f;
-        o.dx[j] = live ? __ldg(offset + ob + HW) : 0.f;
-        o.mk[j] = live ? __ldg(mask + mb) : 0.f;
+        o.dy[u] = live ? __ldg(offset + ob) : 0.f;
+        o.dx[u] = live ? __ldg(offset + ob + HW) : 0.f;
+        o.mk[u] = live ? __ldg(mask + mb) : 0.f;
       }
       return o;
     };
@@ -293,11 +299,13 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
         if (live) {
           const int ti = (tap * 11) >> 5, tj = tap - ti * 3;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int u = 0; u < NS; ++u) {
+            const int j = u / NSUB, sb = u % NSUB;
             const int jc = 2 * cq + j;                         // 8-channel chunk
-            const int g = (jc * DG) >> 3;
-            const float mk = cur.mk[j];
-            const float py = (float)(gy - 1 + ti) + cur.dy[j], px = (float)(gx - 1 + tj) + cur.dx[j];
+            const int g = NSUB == 2 ? 2 * jc + sb : (jc * DG) >> 3;
+            const int d0 = 8 * j + sb * CPS;                   // first dcol register of this sample
+            const float mk = cur.mk[u];
+            const float py = (float)(gy - 1 + ti) + cur.dy[u], px = (float)(gx - 1 + tj) + cur.dx[u];
             const bool inside = py > -1.f && py < (float)H && px > -1.f && px < (float)W;   // mmcv's rule
             float dm = 0.f, gyv = 0.f, gxv = 0.f;
             if (inside) {
@@ -305,37 +313,49 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
               const float ly = py - (float)y0, lx = px - (float)x0;
               const int ry = y0 - wy0, rx = x0 - wx0;
               const bool vy0 = y0 >= 0, vy1 = y0 + 1 < H, vx0 = x0 >= 0, vx1 = x0 + 1 < W;
-              uint4 v[4];
+              uint32_t v[4][CW];
               if ((unsigned)ry < (unsigned)(WH - 1) && (unsigned)rx < (unsigned)(WW - 1)) {
                 const int c00 = ry * WW + rx;
                 const int cells[4] = {c00, c00 + 1, c00 + WW, c00 + WW + 1};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = lds128(win + cells[q] * 128 + ((jc ^ (cells[q] & 7)) << 4));
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t ad = win + cells[q] * 128 + ((jc ^ (cells[q] & 7)) << 4) + sb * 8;
+                  if (CW == 4) {
+                    const uint4 t = lds128(ad);
+                    v[q][0] = t.x; v[q][1] = t.y; v[q][CW - 2] = t.z; v[q][CW - 1] = t.w;
+                  } else {
+                    const uint2 t = lds64(ad);
+                    v[q][0] = t.x; v[q][1] = t.y;
+                  }
+                }
               } else {                                         // far sample: global gather, zero where invalid
                 const int cy0 = max(y0, 0), cy1 = min(y0 + 1, H - 1), cx0 = max(x0, 0), cx1 = min(x0 + 1, W - 1);
-                const __nv_bfloat16* xb = xn + jc * 8;
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                v[0] = (vy0 && vx0) ? __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)cy0 * W + cx0) * CH)) : z;
-                v[1] = (vy0 && vx1) ? __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)cy0 * W + cx1) * CH)) : z;
-                v[2] = (vy1 && vx0) ? __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)cy1 * W + cx0) * CH)) : z;
-                v[3] = (vy1 && vx1) ? __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)cy1 * W + cx1) * CH)) : z;
-              }
-              const uint32_t* a = reinterpret_cast<const uint32_t*>(&v[0]);
-              const uint32_t* b = reinterpret_cast<const uint32_t*>(&v[1]);
-              const uint32_t* c = reinterpret_cast<const uint32_t*>(&v[2]);
-              const uint32_t* d = reinterpret_cast<const uint32_t*>(&v[3]);
+                const __nv_bfloat16* xb = xn + jc * 8 + sb * CPS;
+                const size_t po[4] = {(size_t)cy0 * W + cx0, (size_t)cy0 * W + cx1, (size_t)cy1 * W + cx0, (size_t)cy1 * W + cx1};
+                const bool okq[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float fa = (e & 1) ? bf16hi_to_f32(a[e >> 1]) : bf16lo_to_f32(a[e >> 1]);
-                const float fb = (e & 1) ? bf16hi_to_f32(b[e >> 1]) : bf16lo_to_f32(b[e >> 1]);
-                const float fc = (e & 1) ? bf16hi_to_f32(c[e >> 1]) : bf16lo_to_f32(c[e >> 1]);
-                const float fd = (e & 1) ? bf16hi_to_f32(d[e >> 1]) : bf16lo_to_f32(d[e >> 1]);
+                for (int q = 0; q < 4; ++q) {
+                  if (CW == 4) {
+                    const uint4 t = okq[q] ? __ldg(reinterpret_cast<const uint4*>(xb + po[q] * CH)) : make_uint4(0, 0, 0, 0);
+                    v[q][0] = t.x; v[q][1] = t.y; v[q][CW - 2] = t.z; v[q][CW - 1] = t.w;
+                  } else {
+                    const uint2 t = okq[q] ? __ldg(reinterpret_cast<const uint2*>(xb + po[q] * CH)) : make_uint2(0, 0);
+                    v[q][0] = t.x; v[q][1] = t.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < CPS; ++e) {
+                const float fa = (e & 1) ? bf16hi_to_f32(v[0][e >> 1]) : bf16lo_to_f32(v[0][e >> 1]);
+                const float fb = (e & 1) ? bf16hi_to_f32(v[1][e >> 1]) : bf16lo_to_f32(v[1][e >> 1]);
+                const float fc = (e & 1) ? bf16hi_to_f32(v[2][e >> 1]) : bf16lo_to_f32(v[2][e >> 1]);
+                const float fd = (e & 1) ? bf16hi_to_f32(v[3][e >> 1]) : bf16lo_to_f32(v[3][e >> 1]);
                 const float ba = fb - fa, dc = fd - fc;
                 const float top = fmaf(lx, ba, fa), bot = fmaf(lx, dc, fc);
                 const float bt = bot - top;
                 const float val = fmaf(ly, bt, top);
                 const float ddx = fmaf(ly, dc - ba, ba);
-                const float dcol = __uint_as_float(dr[8 * j + e]);
+                const float dcol = __uint_as_float(dr[d0 + e]);
                 dm = fmaf(dcol, val, dm);
                 gyv = fmaf(dcol, bt, gyv);
                 gxv = fmaf(dcol, ddx, gxv);
@@ -347,21 +367,20 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   if (okq[q]) {
-                    float* dst = gxn + ((size_t)(y0 + (q >> 1)) * W + (x0 + (q & 1))) * CH + jc * 8;
+                    float* dst = gxn + ((size_t)(y0 + (q >> 1)) * W + (x0 + (q & 1))) * CH + jc * 8 + sb * CPS;
                     const float s = wq[q];
-                    atomicAdd(reinterpret_cast<float4*>(dst),
-                              make_float4(s * __uint_as_float(dr[8 * j + 0]), s * __uint_as_float(dr[8 * j + 1]),
-                                          s * __uint_as_float(dr[8 * j + 2]), s * __uint_as_float(dr[8 * j + 3])));
-                    atomicAdd(reinterpret_cast<float4*>(dst + 4),
-                              make_float4(s * __uint_as_float(dr[8 * j + 4]), s * __uint_as_float(dr[8 * j + 5]),
-                                          s * __uint_as_float(dr[8 * j + 6]), s * __uint_as_float(dr[8 * j + 7])));
+#pragma unroll
+                    for (int e = 0; e < CPS; e += 4)
+                      atomicAdd(reinterpret_cast<float4*>(dst + e),
+                                make_float4(s * __uint_as_float(dr[d0 + e]), s * __uint_as_float(dr[d0 + e + 1]),
+                                            s * __uint_as_float(dr[d0 + e + 2]), s * __uint_as_float(dr[d0 + e + 3])));
                   }
                 }
               }
             }
             const size_t ob = ((size_t)(n * DG + g) * TAPS + tap) * 2 * HW + pix;
             const size_t mb = ((size_t)(n * DG + g) * TAPS + tap) * HW + pix;
-            if (DG == 8) {                                     // one chunk per group: plain stores
+            if (DG >= 8) {                                     // one sample per group: plain stores
               if (gmask) gmask[mb] = dm;
               if (goffset) { goffset[ob] = mk * gyv; goffset[ob + HW] = mk * gxv; }
             } else if (inside) {                               // several chunks per group: accumulate
@@ -388,10 +407,17 @@ dcn_bwd_data_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16*
 namespace wgt {
 constexpr int NSA = 3, NOB = 2;
 constexpr int A_TILE = 128 * CH * 2;
-constexpr int PLW = 8, MAX_PLANES = 24;
-constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;   // 768 B
+constexpr int PLW = 8;
 constexpr int TMEM_COLS = 512;                  // 5 x 64 columns used (two taps per 64 columns)
-struct Smem {
+// deform_groups = 16: two 4-channel groups per chunk, 48 offset planes per tap, 4-pixel apron (as in
+// win::Cfg<16>) -- the window is the only thing that can shrink to make room for the planes.
+template <int DG> struct Cfg {
+  static constexpr int NSUB = DG == 16 ? 2 : 1;
+  static constexpr int PAD = DG == 16 ? 4 : 5;
+  static constexpr int WH = TH + 2 * PAD, WW = TW + 2 * PAD;
+  static constexpr int WIN_BYTES = WH * WW * 128;
+  static constexpr int MAX_PLANES = DG == 16 ? 48 : 24;
+  static constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;
   static constexpr int WIN_OFF = 0;
   static constexpr int A_OFF = WIN_OFF + 2 * WIN_BYTES;
   static constexpr int G_OFF = A_OFF + NSA * A_TILE;
@@ -401,15 +427,18 @@ struct Smem {
   static constexpr int NBARS = 2 * NSA + 7;
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
+  static_assert(A_OFF % 1024 == 0 && G_OFF % 1024 == 0, "operand tiles must be 1024-byte aligned");
+  static_assert(DYN <= 232448, "shared memory budget");
 };
-static_assert(Smem::A_OFF % 1024 == 0 && Smem::G_OFF % 1024 == 0, "operand tiles must be 1024-byte aligned");
-static_assert(Smem::DYN <= 232448, "shared memory budget");
 
 template <int DG, bool VEC_OFF>
 __global__ void __launch_bounds__(THREADS, 1)
 dcn_bwd_weight_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ x,
                       const float* __restrict__ offset, const float* __restrict__ mask, float* __restrict__ gweight,
                       int H, int W, long long xs_n, long long gs_n, int tiles_x, int tiles_per_img, int total_tiles) {
+  using Smem = Cfg<DG>;
+  constexpr int NSUB = Smem::NSUB, PAD = Smem::PAD, WH = Smem::WH, WW = Smem::WW, WIN_BYTES = Smem::WIN_BYTES;
+  constexpr int OFF_WARP_BUF = Smem::OFF_WARP_BUF;
   constexpr int NPLANES = 3 * DG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -502,11 +531,9 @@ dcn_bwd_weight_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat1
   } else {
     // ============ producers: window gather -> blend -> swizzled col tile (as in the forward kernel) ============
     const int q = lane >> 3, l = lane & 7;
-    const int grp = (l * DG) / 8;
     const int wrow = warp >> 1, wcol = (warp & 1) * 8;
     const uint32_t offBase = sbase + Smem::OFFS_OFF + warp * NOB * OFF_WARP_BUF;
     const float* offF = reinterpret_cast<const float*>(smem + Smem::OFFS_OFF + warp * NOB * OFF_WARP_BUF);
-    const int colx = (grp >> 2) << 2;
 
     struct TileRef { const float* ob; const float* mb; uint32_t ok; };
     constexpr int PER_PLANE = VEC_OFF ? 2 : 8;
@@ -523,7 +550,7 @@ dcn_bwd_weight_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat1
       cp_mask[k] = comp == 2;
       cp_rel[k] = (comp < 2 ? (uint32_t)(g * TAPS * 2 + comp) : (uint32_t)(g * TAPS)) * (uint32_t)HW + (uint32_t)(cp_col[k] & 15);
       cp_step[k] = (comp < 2 ? 2u : 1u) * (uint32_t)HW;
-      cp_dst[k] = (uint32_t)(plane * PLW + ((cp_col[k] & 15) ^ ((g >> 2) << 2))) * 4u;
+      cp_dst[k] = (uint32_t)(plane * PLW + ((cp_col[k] & 15) ^ (((g >> 2) & 1) << 2))) * 4u;
     }
     auto make_ref = [&](int tl) {
       TileRef r;
@@ -625,22 +652,38 @@ dcn_bwd_weight_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat1
         if (++oring == NOB) oring = 0;
         const int ti = (tap * 11) >> 5, tj = tap - ti * 3;
         uint32_t res[2][4];
+        constexpr int NI = 2 * NSUB, CW = 4 / NSUB;           // samples per thread and tap; words per corner
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int col = (j * 4 + q) ^ colx;
-          const float dy = so[(0 * DG + grp) * PLW + col];
-          const float dx = so[(1 * DG + grp) * PLW + col];
-          const float mk = so[(2 * DG + grp) * PLW + col];
+        for (int u = 0; u < NI; ++u) {
+          const int j = u / NSUB, sb = u % NSUB;
+          const int g = NSUB == 2 ? 2 * l + sb : (l * DG) / 8;
+          const int col = (j * 4 + q) ^ (((g >> 2) & 1) << 2);
+          // dead pixels (outside the image) have no staged offsets: whatever the buffer holds must not
+          // reach the col tile, every row of which is summed into dW
+          const bool live = pyb[j] > -50000.f;
+          const float dy = live ? so[(0 * DG + g) * PLW + col] : 0.f;
+          const float dx = live ? so[(1 * DG + g) * PLW + col] : 0.f;
+          const float mk = live ? so[(2 * DG + g) * PLW + col] : 0.f;
           const float py = (pyb[j] + (float)ti) + dy;
           const float px = (pxb[j] + (float)tj) + dx;
           const int y0 = __float2int_rd(py), x0 = __float2int_rd(px);
           const float ly = py - (float)y0, lx = px - (float)x0;
           float wy0f = mk * (1.f - ly), wy1f = mk * ly, wx0f = 1.f - lx, wx1f = lx;
           const int ry = y0 - wy0, rx = x0 - wx0;
-          uint4 v00, v01, v10, v11;
+          uint32_t v[4][CW];
           if ((unsigned)ry < (unsigned)(WH - 1) && (unsigned)rx < (unsigned)(WW - 1)) {
-            const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u;
-            v00 = lds128(a00); v01 = lds128(a00 + 128u); v10 = lds128(a00 + WW * 128u); v11 = lds128(a00 + WW * 128u + 128u);
+            const uint32_t a00 = win + (uint32_t)(ry * WW + rx) * 128u + sb * 8u;
+            const uint32_t ad[4] = {a00, a00 + 128u, a00 + WW * 128u, a00 + WW * 128u + 128u};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (CW == 4) {
+                const uint4 t = lds128(ad[c]);
+                v[c][0] = t.x; v[c][1] = t.y; v[c][CW - 2] = t.z; v[c][CW - 1] = t.w;
+              } else {
+                const uint2 t = lds64(ad[c]);
+                v[c][0] = t.x; v[c][1] = t.y;
+              }
+            }
           } else {
             wy0f = ((unsigned)y0 < (unsigned)H) ? wy0f : 0.f;
             wy1f = ((unsigned)y0 + 1u < (unsigned)H) ? wy1f : 0.f;
@@ -649,23 +692,28 @@ dcn_bwd_weight_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat1
             const int ys = min(max(y0, -1), H), xs = min(max(x0, -1), W);
             const int cy0 = min(max(ys, 0), H - 1), cy1 = min(max(ys + 1, 0), H - 1);
             const int cx0 = min(max(xs, 0), W - 1), cx1 = min(max(xs + 1, 0), W - 1);
-            const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8;
+            const uint32_t b00 = (uint32_t)(cy0 * W + cx0) * CH + l * 8 + sb * 4;
             const uint32_t sx = (uint32_t)(cx1 - cx0) * CH, sy = (uint32_t)((cy1 - cy0) * W) * CH;
-            v00 = __ldg(reinterpret_cast<const uint4*>(xn + b00));
-            v01 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sx)));
-            v10 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy)));
-            v11 = __ldg(reinterpret_cast<const uint4*>(xn + (uint32_t)(b00 + sy + sx)));
+            const uint32_t bo[4] = {b00, (uint32_t)(b00 + sx), (uint32_t)(b00 + sy), (uint32_t)(b00 + sy + sx)};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (CW == 4) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(xn + bo[c]));
+                v[c][0] = t.x; v[c][1] = t.y; v[c][CW - 2] = t.z; v[c][CW - 1] = t.w;
+              } else {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(xn + bo[c]));
+                v[c][0] = t.x; v[c][1] = t.y;
+              }
+            }
           }
           const float w00 = wy0f * wx0f, w01 = wy0f * wx1f, w10 = wy1f * wx0f, w11 = wy1f * wx1f;
-          const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, b[4] = {v01.x, v01.y, v01.z, v01.w};
-          const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = w00 * bf16lo_to_f32(a[e]) + w01 * bf16lo_to_f32(b[e]) + w10 * bf16lo_to_f32(c[e]) +
-                             w11 * bf16lo_to_f32(d[e]);
-            const float hi = w00 * bf16hi_to_f32(a[e]) + w01 * bf16hi_to_f32(b[e]) + w10 * bf16hi_to_f32(c[e]) +
-                             w11 * bf16hi_to_f32(d[e]);
-            res[j][e] = pack_bf16x2(lo, hi);
+          for (int e = 0; e < CW; ++e) {
+            const float lo = w00 * bf16lo_to_f32(v[0][e]) + w01 * bf16lo_to_f32(v[1][e]) + w10 * bf16lo_to_f32(v[2][e]) +
+                             w11 * bf16lo_to_f32(v[3][e]);
+            const float hi = w00 * bf16hi_to_f32(v[0][e]) + w01 * bf16hi_to_f32(v[1][e]) + w10 * bf16hi_to_f32(v[2][e]) +
+                             w11 * bf16hi_to_f32(v[3][e]);
+            res[j][sb * CW + e] = pack_bf16x2(lo, hi);
           }
         }
         if (it >= NSA) mbar_wait(bar_empty + 8 * ring, ring_ph ^ 1);
@@ -731,8 +779,8 @@ bool dcn_backward_tc_eligible(const int64_t* gs, const int64_t* xs, const int64_
   };
   const bool cfg = g.Cin == 64 && g.Cout == 64 && g.KH == 3 && g.KW == 3 && g.SH == 1 && g.SW == 1 && g.PH == 1 &&
                    g.PW == 1 && g.DH == 1 && g.DW == 1 && g.G == 1 &&
-                   (g.DG == 1 || g.DG == 2 || g.DG == 4 || g.DG == 8);
-  if (!cfg || (long long)g.H * g.W > (1ll << 24) || (long long)g.N * g.DG * 18 * g.H * g.W >= (1ll << 40)) return false;
+                   (g.DG == 1 || g.DG == 2 || g.DG == 4 || g.DG == 8 || g.DG == 16);
+  if (!cfg || (long long)g.H * g.W > (g.DG == 16 ? (1ll << 23) : (1ll << 24)) || (long long)g.N * g.DG * 18 * g.H * g.W >= (1ll << 40)) return false;
   if (!dense(gs) || !dense(xs)) return false;
   if (has_gx && !dense(gxs)) return false;
   return true;
@@ -758,7 +806,7 @@ static int launch_bwd_tc(const void* gout, const int64_t* gs, const void* x, con
     if (rc) return rc;
     const size_t P = (size_t)H * W;
     if (gx32) cudaMemsetAsync(gx32, 0, (size_t)g.N * (size_t)gxs[0] * sizeof(float), st);
-    if (DG != 8) {
+    if (DG < 8) {
       if (goffset) cudaMemsetAsync(goffset, 0, (size_t)g.N * DG * 18 * P * sizeof(float), st);
       if (gmask) cudaMemsetAsync(gmask, 0, (size_t)g.N * DG * 9 * P * sizeof(float), st);
     }
@@ -779,9 +827,9 @@ static int launch_bwd_tc(const void* gout, const int64_t* gs, const void* x, con
     auto kv = wgt::dcn_bwd_weight_kernel<DG, true>;
     auto ks = wgt::dcn_bwd_weight_kernel<DG, false>;
     auto k = vec ? kv : ks;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wgt::Smem::DYN);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wgt::Cfg<DG>::DYN);
     if (e != cudaSuccess) { set_error("dcn_backward(weight): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
-    k<<<grid, THREADS, wgt::Smem::DYN, st>>>((const __nv_bfloat16*)gout, (const __nv_bfloat16*)x, offset, mask,
+    k<<<grid, THREADS, wgt::Cfg<DG>::DYN, st>>>((const __nv_bfloat16*)gout, (const __nv_bfloat16*)x, offset, mask,
                                               gweight32, H, W, (long long)xs[0], (long long)gs[0], tiles_x,
                                               tiles_per_img, total);
     rc = check_launch("dcn_backward(weight, tcgen05)");
@@ -804,6 +852,7 @@ int dcn_backward_tc(const void* gout, const int64_t* gs, const void* x, const in
                     float* gmask, float* gweight32, float* gbias32, const DcnGeom& g, void* workspace, unsigned which,
                     cudaStream_t st) {
   switch (g.DG) {
+    case 16: return launch_bwd_tc<16>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
     case 8: return launch_bwd_tc<8>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
     case 4: return launch_bwd_tc<4>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);
     case 2: return launch_bwd_tc<2>(gout, gs, x, xs, offset, mask, weight, gx32, gxs, goffset, gmask, gweight32, gbias32, g, workspace, which, st);

@@ -472,7 +472,8 @@ int dcn_backward_tc(const void* gout, const int64_t* gs, const void* x, const in
 extern "C" size_t eavsr_dcn_backward_workspace(int cin, int cout, int kh, int kw, int groups, int deform_groups,
                                                int dtype) {
   if (cin != CH || cout != CH || kh != 3 || kw != 3 || groups != 1 || dtype != EAVSR_BF16) return 0;
-  if (!(deform_groups == 1 || deform_groups == 2 || deform_groups == 4 || deform_groups == 8)) return 0;
+  if (!(deform_groups == 1 || deform_groups == 2 || deform_groups == 4 || deform_groups == 8 || deform_groups == 16))
+    return 0;
   return dcn_backward_tc_workspace();
 }
 

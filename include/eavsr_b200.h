@@ -105,7 +105,7 @@ int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], const float* of
  * gx32: fp32 accumulation buffer (zero-filled by the call) with strides gx_strides;
  * goffset/gmask: fp32, layouts of offset/mask;  gweight32: fp32 (cout,cin/groups,kh,kw),
  * gbias32: fp32 (cout) -- both zero-filled by the call.
- * bf16 NHWC 64->64 3x3 (stride/pad/dilation 1, deform_groups 1/2/4/8) runs on the tcgen05 kernels
+ * bf16 NHWC 64->64 3x3 (stride/pad/dilation 1, deform_groups 1/2/4/8/16) runs on the tcgen05 kernels
  * (csrc/dcn_bwd_tc.cu) when `workspace` holds eavsr_dcn_backward_workspace() bytes (16-byte aligned);
  * with workspace == NULL, or any other configuration, the generic kernels run.  This replaces the
  * autograd of mmcv's ModulatedDeformConv2dFunction.backward under models/networks.py:627-630. */

@@ -287,7 +287,7 @@ def _dcn_bf16_grads(cuda, n, h, w, dg, flags, seed=21, sigma=1.5):
 
 
 @pytest.mark.parametrize("flags", [0, 32, 64])     # tcgen05 data+weight / generic data / generic weight
-@pytest.mark.parametrize("dg", [8, 4, 1])
+@pytest.mark.parametrize("dg", [8, 16, 4, 1])
 @pytest.mark.parametrize("shape", [(2, 19, 37), (1, 40, 72)])
 def test_dcn_backward_bf16_tensor_cores(cuda, shape, dg, flags):
     """bf16 NHWC 64->64 backward on the tcgen05 kernels (csrc/dcn_bwd_tc.cu) against the fp64 oracle on
@@ -303,10 +303,11 @@ def test_dcn_backward_bf16_tensor_cores(cuda, shape, dg, flags):
         assert rel_err(a, r) < tol[name], (name, rel_err(a, r))
 
 
-def test_dcn_backward_tensor_cores_match_generic_at_full_size(cuda):
+@pytest.mark.parametrize("dg", [8, 16])
+def test_dcn_backward_tensor_cores_match_generic_at_full_size(cuda, dg):
     """1x64x270x480 (BASELINE config 2/3 size): tcgen05 backward == generic backward."""
-    _, tc = _dcn_bf16_grads(cuda, 1, 270, 480, 8, 0, seed=23, sigma=2.0)
-    _, ge = _dcn_bf16_grads(cuda, 1, 270, 480, 8, 32 | 64, seed=23, sigma=2.0)
+    _, tc = _dcn_bf16_grads(cuda, 1, 270, 480, dg, 0, seed=23, sigma=2.0)
+    _, ge = _dcn_bf16_grads(cuda, 1, 270, 480, dg, 32 | 64, seed=23, sigma=2.0)
     tol = {"x": BF16_REL, "offset": 2e-3, "mask": 2e-3, "weight": BF16_REL, "bias": BF16_REL}
     for name, a, r in zip(("x", "offset", "mask", "weight", "bias"), tc, ge):
         assert rel_err(a, r) < tol[name], (name, rel_err(a, r))

@@ -112,7 +112,7 @@ def bench_dcn():
                     sec = timeit(lambda i: E.modulated_deform_conv2d(xs[i % k], small[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg), 40)
                     rec(f"dcn fwd tc {dt} dg={dg} {n}x64x{h}x{w} sigma=0.5", sec, by, fl)
                     del small
-                if n == 1 and dg == 8:
+                if n == 1:
                     sec = timeit(lambda i: _ModulatedDeformConv2dFn.apply(xs[i % k], offs[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg, L.DCN_FORCE_GENERIC), 3, warm=1)
                     rec(f"dcn fwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by, fl)
                     for flags, tag in ((0, "tc (data+weight)" if dt == torch.bfloat16 else "generic"),
