@@ -232,7 +232,34 @@ def make_workload(name, device):
 # ------------------------------------------------------------------------------------------------
 # roofline of the dominant kernel: tcgen05 DCNv2 forward, timed live with CUDA events
 # ------------------------------------------------------------------------------------------------
-def dcn_roofline(device, peaks, dg=8, iters=60):
+def dcn_backward_us(device, dg, iters=5):
+    """fwd+bwd of BASELINE config 2 (1x64x270x480): device time of one backward (all five gradients)
+    through autograd, CUDA events, includes ~0.1 ms of host-side autograd glue per call."""
+    import eavsr_b200 as E
+    h, w = LR_H, LR_W
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 64, h, w, generator=g).to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    off = (torch.randn(1, dg * 18, h, w, generator=g) * 2).clamp(-12, 12).to(device)
+    msk = torch.sigmoid(torch.randn(1, dg * 9, h, w, generator=g)).to(device)
+    wgt = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24).to(device, torch.bfloat16)
+    bias = torch.zeros(64, device=device, dtype=torch.bfloat16)
+    with torch.enable_grad():
+        leaves = [t.requires_grad_() for t in (x, off, msk, wgt, bias)]
+        out = E.modulated_deform_conv2d(*leaves, 1, 1, 1, 1, dg)
+        go = torch.randn_like(out)
+        for _ in range(2):
+            torch.autograd.grad(out, leaves, go, retain_graph=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            torch.autograd.grad(out, leaves, go, retain_graph=True)
+        b.record()
+        torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / iters
+
+
+def dcn_roofline(device, peaks, dg=8, iters=60, nested=True):
     import eavsr_b200 as E
     h, w = LR_H, LR_W
     g = torch.Generator().manual_seed(0)
@@ -274,12 +301,28 @@ def dcn_roofline(device, peaks, dg=8, iters=60):
     # capture summarised in profiles/r1_dcn_fwd_win_ncu.txt (128.7 MB read + 9.0 MB written; the 16.6 MB
     # output is only partly evicted from L2 within the launch)
     traffic = 137.7e6 if dg == 8 else None
-    return {"kernel": "win::dcn_fwd_win_kernel<dg=%d,bf16> 1x64x270x480" % dg, "bound": "hbm", "achieved": round(ach, 1),
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
-            "peak_source": peaks["source"], "us_per_launch": round(sec * 1e6, 2),
-            "algorithmic_bytes_per_launch": bytes_alg,
-            "tensor": {"achieved_tflops": round(flops / sec / 1e12, 1), "peak_tflops": peaks["bf16_tflops"],
-                       "frac": round(flops / sec / 1e12 / peaks["bf16_tflops"], 4)}}
+    res = {"kernel": "win::dcn_fwd_win_kernel<dg=%d,bf16> 1x64x270x480" % dg, "bound": "hbm", "achieved": round(ach, 1),
+           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
+           "peak_source": peaks["source"], "us_per_launch": round(sec * 1e6, 2),
+           "algorithmic_bytes_per_launch": bytes_alg,
+           "tensor": {"achieved_tflops": round(flops / sec / 1e12, 1), "peak_tflops": peaks["bf16_tflops"],
+                      "frac": round(flops / sec / 1e12 / peaks["bf16_tflops"], 4)}}
+    if nested:
+        # BASELINE config 2 (the DCNv2 micro-bench the "DCN TC util" half of the metric is quoted on):
+        # deform_groups = 16, forward + backward, same shape
+        del xs, offs, msks
+        torch.cuda.empty_cache()
+        try:
+            c2 = dcn_roofline(device, peaks, dg=16, iters=30, nested=False)
+            bwd = dcn_backward_us(device, 16)
+            res["config2_dg16"] = {"fwd_us": c2["us_per_launch"], "fwd_hbm_frac": c2["frac"],
+                                   "fwd_tensor_frac": c2["tensor"]["frac"], "bwd_us": round(bwd, 1),
+                                   "fwd_bwd_tensor_frac": round(3 * flops / ((c2["us_per_launch"] + bwd) * 1e-6) / 1e12
+                                                                / peaks["bf16_tflops"], 4),
+                                   "bwd_us_dg8": round(dcn_backward_us(device, 8), 1)}
+        except Exception as exc:  # an extra, never a reason to lose the bench line
+            res["config2_dg16"] = {"failed": repr(exc)}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
