@@ -179,14 +179,25 @@ class _AdaptBlockOffset(_AdaptBase):
     def forward(self, x, ref):
         f = self._mix(x, ref)
         if fused_inference_ok(f, self.mask_conv.weight):
+            # the three 5x5 convolutions read the same input: ONE bias-free 64 -> 15*D convolution, whose
+            # channel slices (strided views, no copies) feed the expansion kernel; biases are added there
             ct, cr, cm = self.transform_matrix_conv, self.translation_conv, self.mask_conv
-            T = F.conv2d(f, ct.weight, None, 1, ct.padding)
-            t = F.conv2d(f, cr.weight, None, 1, cr.padding)
-            m = F.conv2d(f, cm.weight, None, 1, cm.padding)
-            return affine_offsets_mask(T, t, m, self.D, ct.bias, cr.bias, cm.bias)
+            y = F.conv2d(f, self._merged_weight(), None, 1, ct.padding)
+            D = self.D
+            return affine_offsets_mask(y[:, :4 * D], y[:, 4 * D:6 * D], y[:, 6 * D:], D, ct.bias, cr.bias, cm.bias)
         T, t, m = self.transform_matrix_conv(f), self.translation_conv(f), self.mask_conv(f)
         off = _affine_offsets(T.float(), t.float(), self.D, self.regular_matrix)
         return off, torch.sigmoid(m.float())
+
+
+    def _merged_weight(self):
+        ws = (self.transform_matrix_conv.weight, self.translation_conv.weight, self.mask_conv.weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
+        hit = getattr(self, "_merged", None)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([w.detach() for w in ws], 0).contiguous(memory_format=torch.channels_last))
+            self._merged = hit
+        return hit[1]
 
 
 class _TransOffset(nn.Module):
