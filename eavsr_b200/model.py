@@ -144,6 +144,17 @@ class _AdaptBase(nn.Module):
         self.transform_matrix_conv = nn.Conv2d(ch, n_mat, k, 1, k // 2)
         self.translation_conv = nn.Conv2d(ch, n_trans, k, 1, k // 2)
 
+    def _merged_weight(self):
+        ws = [self.transform_matrix_conv.weight, self.translation_conv.weight]
+        if hasattr(self, "mask_conv"):
+            ws.append(self.mask_conv.weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
+        hit = getattr(self, "_merged", None)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([w.detach() for w in ws], 0).contiguous(memory_format=torch.channels_last))
+            self._merged = hit
+        return hit[1]
+
     def _mix(self, x, ref):
         if x.shape[1] == 64 and fused_inference_ok(x, ref):      # both grouped convs in one pass
             return adapt_mix(x, ref, self.concat[0].weight, self.concat[0].bias, self.concat2[0].weight,
@@ -161,9 +172,8 @@ class _AdaptBlock2_3x3(_AdaptBase):
         f = self._mix(x, ref)
         if fused_inference_ok(f, self.transform_matrix_conv.weight):
             ct, cr = self.transform_matrix_conv, self.translation_conv      # bias-free; biases added in-kernel
-            T = F.conv2d(f, ct.weight, None, 1, ct.padding)
-            t = F.conv2d(f, cr.weight, None, 1, cr.padding)
-            return affine_offsets_mask(T, t, None, 1, ct.bias, cr.bias)[0]
+            y = F.conv2d(f, self._merged_weight(), None, 1, ct.padding)     # one 64 -> 6 convolution
+            return affine_offsets_mask(y[:, :4], y[:, 4:6], None, 1, ct.bias, cr.bias)[0]
         T, t = self.transform_matrix_conv(f), self.translation_conv(f)
         return _affine_offsets(T.float(), t.float(), 1, self.regular_matrix)
 
@@ -188,16 +198,6 @@ class _AdaptBlockOffset(_AdaptBase):
         T, t, m = self.transform_matrix_conv(f), self.translation_conv(f), self.mask_conv(f)
         off = _affine_offsets(T.float(), t.float(), self.D, self.regular_matrix)
         return off, torch.sigmoid(m.float())
-
-
-    def _merged_weight(self):
-        ws = (self.transform_matrix_conv.weight, self.translation_conv.weight, self.mask_conv.weight)
-        key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
-        hit = getattr(self, "_merged", None)
-        if hit is None or hit[0] != key:
-            hit = (key, torch.cat([w.detach() for w in ws], 0).contiguous(memory_format=torch.channels_last))
-            self._merged = hit
-        return hit[1]
 
 
 class _TransOffset(nn.Module):
