@@ -8,6 +8,8 @@ from .ops import (  # noqa: F401
     FunctionCorrelation,
     ModuleCorrelation,
     ModulatedDeformConv2d,
+    dcn_affine,
+    dcn_affine_eligible,
     dcn_uses_tensor_cores,
     flow_warp,
     flow_warp_nhw2,

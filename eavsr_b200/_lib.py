@@ -45,6 +45,8 @@ _SIGNATURES = {
     "eavsr_dcn_backward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, _PF, c_void_p, _PF, _P64, _PF, _PF, _PF,
                                    _PF] + [c_int] * 16 + [c_void_p, c_size_t, c_uint, c_void_p]),
     "eavsr_dcn_backward_workspace": (c_size_t, [c_int] * 7),
+    "eavsr_dcn_affine_forward": (c_int, [c_void_p, _P64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _P64] +
+                                 [c_int] * 5 + [c_void_p, c_size_t, c_uint, c_void_p]),
     "eavsr_correlation_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),
     "eavsr_correlation_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

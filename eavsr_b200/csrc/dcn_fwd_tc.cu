@@ -332,14 +332,15 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
       const int g3 = tot < sms ? tot : sms;
       const bool b16 = !(flags & EAVSR_DCN_BLEND_FP32);
       void (*k)(const __nv_bfloat16*, const float*, const float*, const uint8_t*, const __nv_bfloat16*,
-                __nv_bfloat16*, int, int, long long, long long, int, int, int) =
+                __nv_bfloat16*, int, int, long long, long long, int, int, int, const __nv_bfloat16*,
+                const __nv_bfloat16*) =
           vecw ? (b16 ? win::dcn_fwd_win_kernel<DG, true, true> : win::dcn_fwd_win_kernel<DG, true, false>)
                : (b16 ? win::dcn_fwd_win_kernel<DG, false, true> : win::dcn_fwd_win_kernel<DG, false, false>);
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, win::Cfg<DG>::DYN);
       if (e != cudaSuccess) { set_error("dcn_forward(win): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
       k<<<g3, win::THREADS, win::Cfg<DG>::DYN, st>>>((const __nv_bfloat16*)x, offset, mask, (const uint8_t*)workspace,
                                                  (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0], os[0],
-                                                 tiles_x, tpi, tot);
+                                                 tiles_x, tpi, tot, nullptr, nullptr);
       return check_launch("dcn_forward(win)");
     }
   }
@@ -458,6 +459,62 @@ extern "C" int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], cons
   if (dtype == EAVSR_F32)
     return dcn_forward_generic<float>(x, x_strides, offset, mask, weight, bias, out, out_strides, g, st);
   return dcn_forward_generic<__nv_bfloat16>(x, x_strides, offset, mask, weight, bias, out, out_strides, g, st);
+}
+
+namespace eavsr {
+namespace {
+template <int DG>
+int launch_affine(const void* x, const int64_t* xs, const void* affine, const void* affine_bias, const void* weight,
+                  const void* bias, void* out, const int64_t* os, int n, int h, int w, void* workspace, unsigned flags,
+                  cudaStream_t st) {
+  int rc = 0;
+  if (!(flags & EAVSR_DCN_WS_PACKED)) {
+    dcn_pack_weight<__nv_bfloat16, false><<<(TAPS * CH * CH + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)weight,
+                                                                                      (uint8_t*)workspace);
+    rc = check_launch("dcn_affine_forward(pack)");
+    if (rc) return rc;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_x = (w + win::TW - 1) / win::TW, tiles_y = (h + win::TH - 1) / win::TH;
+  const int tpi = tiles_x * tiles_y, tot = tpi * n;
+  const int grid = tot < sms ? tot : sms;
+  const bool b16 = !(flags & EAVSR_DCN_BLEND_FP32);
+  auto k = b16 ? win::dcn_fwd_win_kernel<DG, true, true, true> : win::dcn_fwd_win_kernel<DG, true, false, true>;
+  using C = win::Cfg<DG, true>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN);
+  if (e != cudaSuccess) { set_error("dcn_affine_forward: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  k<<<grid, win::THREADS, C::DYN, st>>>((const __nv_bfloat16*)x, nullptr, nullptr, (const uint8_t*)workspace,
+                                        (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0], os[0], tiles_x,
+                                        tpi, tot, (const __nv_bfloat16*)affine, (const __nv_bfloat16*)affine_bias);
+  return check_launch("dcn_affine_forward");
+}
+}  // namespace
+}  // namespace eavsr
+
+extern "C" int eavsr_dcn_affine_forward(const void* x, const int64_t x_strides[4], const void* affine,
+                                        const void* affine_bias, const void* weight, const void* bias, void* out,
+                                        const int64_t out_strides[4], int n, int h, int w, int deform_groups,
+                                        int dtype, void* workspace, size_t workspace_bytes, unsigned flags,
+                                        void* stream) {
+  EAVSR_REQUIRE(x && affine && weight && out && x_strides && out_strides, "dcn_affine_forward: null pointer");
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "dcn_affine_forward: empty tensor");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool ok = dtype == EAVSR_BF16 &&
+                  deform_groups == 8 &&   // 15*dg bf16 per pixel must be a multiple of 16 bytes
+                  nhwc_dense(x_strides, CH, h, w) && nhwc_dense(out_strides, CH, h, w) && al16(x) && al16(out) &&
+                  al16(affine) && (x_strides[0] * 2) % 16 == 0 && (out_strides[0] * 2) % 16 == 0 &&
+                  (long long)h * w <= (1ll << 24) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 3u) == 0);
+  if (!ok) {
+    set_error("dcn_affine_forward: only bf16 dense NHWC 64->64 with deform_groups = 8 is fused");
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  const size_t need = eavsr_dcn_forward_workspace(CH, CH, 3, 3, 1, deform_groups, dtype);
+  EAVSR_REQUIRE(workspace && workspace_bytes >= need && al16(workspace),
+                "dcn_affine_forward: needs a 16-byte aligned workspace of %zu bytes (got %zu)", need, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  return launch_affine<8>(x, x_strides, affine, affine_bias, weight, bias, out, out_strides, n, h, w, workspace, flags, st);
 }
 
 namespace eavsr {

@@ -42,14 +42,19 @@ constexpr int TMEM_COLS = 128;
 // prefetch distance of 2 taps the first versions had only ~24 KB per SM in flight (Little: 2.4 TB/s
 // for the whole chip = the ~100 us floor every earlier kernel hit).  3 buffers -> distance 2 (deeper
 // did not pay: the A ring depth did).
-template <int DG> struct Cfg {
+// AFF (fused offset generation): the kernel reads the (n, h, w, 15*DG) bf16 output of
+// the offset-generating convolution (4*DG transform, 2*DG translation, 9*DG mask logits per pixel) instead
+// of fp32 offset / mask planes: a warp stages the 8 x 15*DG*2 bytes of its pixels once per TILE (double
+// buffered), keeps the affine part in registers and expands offset = T*R - R + t and sigmoid(logit) per tap.
+template <int DG, bool AFF = false> struct Cfg {
   static constexpr int NSUB = DG == 16 ? 2 : 1;           // samples (groups) per 16-byte chunk
-  static constexpr int PAD = DG == 16 ? 4 : 5;
+  static constexpr int PAD = (DG == 16 || AFF) ? 4 : 5;
   static constexpr int WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 18 x 26 (16 x 24) window
   static constexpr int WIN_BYTES = WH * WW * 128;              // 59 904 (49 152)
-  static constexpr int NOB = DG == 16 ? 2 : 3;
+  static constexpr int NOB = (DG == 16 || AFF) ? 2 : 3;
   static constexpr int MAX_PLANES = DG == 16 ? 48 : 24;
-  static constexpr int OFF_WARP_BUF = MAX_PLANES * PLW * 4;    // 768 B (1 536 B)
+  static constexpr int APX = 15 * DG * 2;                      // AFF: bytes per pixel of the affine block
+  static constexpr int OFF_WARP_BUF = AFF ? PLW * APX : MAX_PLANES * PLW * 4;    // 768 B (1 536 B; AFF: 1 920 B)
   static constexpr int WIN_OFF = 0;
   static constexpr int A_OFF = WIN_OFF + 2 * WIN_BYTES;        // multiple of 1024
   static constexpr int B_OFF = A_OFF + NSA * A_TILE;
@@ -57,10 +62,12 @@ template <int DG> struct Cfg {
   static constexpr int BAR_OFF = OFFS_OFF + PWARPS * NOB * OFF_WARP_BUF;
   // full[NSA], empty[NSA], bfull[NSB], accf[2], acce[2], winf[2], wine[2]; tmem slot
   static constexpr int NBARS = 2 * NSA + NSB + 8;
-  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+  static constexpr int ABIAS_OFF = BAR_OFF + NBARS * 8 + 16;   // AFF: 15*DG fp32 biases
+  static constexpr int TOTAL = ABIAS_OFF + (AFF ? 15 * DG * 4 : 0);
   static constexpr int DYN = TOTAL + 1024;
   static_assert(A_OFF % 1024 == 0, "A stages must be 1024-byte aligned for the 128B swizzle");
   static_assert(DYN <= 232448, "shared memory budget");
+  static_assert(!AFF || (DG <= 8 && APX % 16 == 0), "fused offsets: deform_groups <= 8");
 };
 using Smem = Cfg<8>;                         // layout shared by deform_groups 1, 2, 4, 8
 
@@ -85,14 +92,16 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-template <int DG, bool VEC_OFF, bool BLEND16>
+template <int DG, bool VEC_OFF, bool BLEND16, bool AFF = false>
 __global__ void __launch_bounds__(THREADS, 1)
 dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ offset,
                    const float* __restrict__ mask, const uint8_t* __restrict__ wpacked,
                    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
-                   long long xs_n, long long os_n, int tiles_x, int tiles_per_img, int total_tiles) {
-  using C = Cfg<DG>;
-  using Smem = Cfg<DG>;
+                   long long xs_n, long long os_n, int tiles_x, int tiles_per_img, int total_tiles,
+                   const __nv_bfloat16* __restrict__ aff = nullptr,
+                   const __nv_bfloat16* __restrict__ aff_bias = nullptr) {
+  using C = Cfg<DG, AFF>;
+  using Smem = Cfg<DG, AFF>;
   constexpr int NSUB = C::NSUB, PAD = C::PAD, WH = C::WH, WW = C::WW, WIN_BYTES = C::WIN_BYTES;
   constexpr int NOB = C::NOB, OFF_WARP_BUF = C::OFF_WARP_BUF;
   constexpr int NPLANES = 3 * DG;
@@ -119,6 +128,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       mbar_init(bar_wine + 8 * b, PWARPS);
     }
     fence_mbar_init();
+  }
+  if constexpr (AFF) {
+    float* sb = reinterpret_cast<float*>(smem + Smem::ABIAS_OFF);
+    for (int i = tid; i < 15 * DG; i += THREADS) sb[i] = aff_bias ? __bfloat162float(aff_bias[i]) : 0.f;
   }
   // window cells that lie outside the image are never loaded; zero both buffers once so that whatever
   // they hold later (stale x) is finite and their 0 weights really give 0
@@ -260,6 +273,25 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       cp_async_commit();
     };
 
+    // AFF: the affine block of this warp's 8 pixels, once per tile, double buffered
+    auto prefetch_tile = [&](int tl) {
+      if (AFF && tl < my_tiles) {
+        int n, ty0, tx0;
+        tile_coords(tl, n, ty0, tx0);
+        const int gy = ty0 + wrow, gx = tx0 + wcol;
+        const uint32_t dst0 = offBase + (tl & 1) * OFF_WARP_BUF;
+        if (gy < H) {
+          const __nv_bfloat16* src = aff + (((size_t)n * H + gy) * W + gx) * (15 * DG);
+          constexpr int CPX = C::APX / 16;                     // 16-byte chunks per pixel
+          for (int i = lane; i < PLW * CPX; i += 32) {
+            const int px = i / CPX, c = i - px * CPX;
+            if (gx + px < W) cp_async_16(dst0 + px * C::APX + c * 16, src + px * (15 * DG) + c * 8);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+
     auto epilogue = [&](int tl) {
       const int buf = tl & 1;
       mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
@@ -297,8 +329,13 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       }
     };
 
+    if constexpr (AFF) {
+      prefetch_tile(0);
+      prefetch_tile(1);
+    } else {
 #pragma unroll
-    for (int i = 0; i < NOB - 1; ++i) prefetch_next();
+      for (int i = 0; i < NOB - 1; ++i) prefetch_next();
+    }
     int it = 0, ring = 0, oring = 0;      // ring = it % NSA, ring_ph = parity of it / NSA, oring = it % NOB
     uint32_t ring_ph = 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
@@ -314,6 +351,27 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         const int gx = tx0 + wcol + j * 4 + q;
         pyb[j] = (gy < H && gx < W) ? (float)(gy - 1) : -100000.f;   // dead pixel: sample rejected
         pxb[j] = (float)(gx - 1);
+      }
+      // AFF: affine parameters of this thread's two (pixel, group) items; logits stay in the staged block
+      float af[2][6];
+      const __nv_bfloat16* lgp[2] = {nullptr, nullptr};
+      const float* sbias = reinterpret_cast<const float*>(smem + Smem::ABIAS_OFF);
+      if constexpr (AFF) {
+        cp_async_wait<1>();                                    // this tile's block (the next one may be in flight)
+        __syncwarp();
+        const int g = (l * DG) / 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(
+              smem + Smem::OFFS_OFF + (warp * NOB + (tl & 1)) * OFF_WARP_BUF + (j * 4 + q) * C::APX);
+          const bool live = pyb[j] > -50000.f;                 // dead pixels were not staged
+#pragma unroll
+          for (int e = 0; e < 4; ++e) af[j][e] = live ? __bfloat162float(pp[g * 4 + e]) + sbias[g * 4 + e] : 0.f;
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            af[j][4 + e] = live ? __bfloat162float(pp[4 * DG + g * 2 + e]) + sbias[4 * DG + g * 2 + e] : 0.f;
+          lgp[j] = pp + 6 * DG + g * 9;
+        }
       }
       // Border tiles: the window cells outside the image are not loaded; zero them so that the gather
       // needs no per-corner validity test (an outside corner reads 0, which is DCNv2's zero padding
@@ -332,11 +390,14 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       }
       mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);       // this tile's window has landed
       for (int tap = 0; tap < TAPS; ++tap, ++it) {
-        cp_async_wait<NOB - 2>();                              // offsets of `it` have landed
-        __syncwarp();                                          // ... and everyone left buffer (it-1) % NOB
-        prefetch_next();
-        const float* so = offF + oring * (OFF_WARP_BUF / 4);
-        if (++oring == NOB) oring = 0;
+        const float* so = offF;
+        if constexpr (!AFF) {
+          cp_async_wait<NOB - 2>();                            // offsets of `it` have landed
+          __syncwarp();                                        // ... and everyone left buffer (it-1) % NOB
+          prefetch_next();
+          so = offF + oring * (OFF_WARP_BUF / 4);
+          if (++oring == NOB) oring = 0;
+        }
         const int ti = (tap * 11) >> 5, tj = tap - ti * 3;       // tap / 3 for tap < 9
         uint32_t res[2][4];
         // The samples of a thread (2 items x NSUB groups per 16-byte chunk) are advanced in lock step
@@ -353,9 +414,18 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
           const int j = u / NSUB, sb = u % NSUB;
           const int g = NSUB == 2 ? 2 * l + sb : (l * DG) / 8;
           const int col = (j * 4 + q) ^ (((g >> 2) & 1) << 2);
-          const float dy = so[(0 * DG + g) * PLW + col];
-          const float dx = so[(1 * DG + g) * PLW + col];
-          const float mk = so[(2 * DG + g) * PLW + col];
+          float dy, dx, mk;
+          if constexpr (AFF) {                                 // models/networks.py:302-313, as affine_offsets_kernel
+            const float r0 = (float)(ti - 1), r1 = (float)(tj - 1);
+            dy = af[j][0] * r0 + af[j][1] * r1 - r0 + af[j][4];
+            dx = af[j][2] * r0 + af[j][3] * r1 - r1 + af[j][5];
+            const float lg = __bfloat162float(lgp[j][tap]) + sbias[6 * DG + g * 9 + tap];
+            mk = pyb[j] > -50000.f ? 1.f / (1.f + __expf(-lg)) : 0.f;
+          } else {
+            dy = so[(0 * DG + g) * PLW + col];
+            dx = so[(1 * DG + g) * PLW + col];
+            mk = so[(2 * DG + g) * PLW + col];
+          }
           const float py = (pyb[j] + (float)ti) + dy;
           const float px = (pxb[j] + (float)tj) + dx;
           // floor via a saturating float->int conversion (NaN -> 0, +-huge -> INT_MIN/MAX: such cells fail
@@ -454,6 +524,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         }
         if (++ring == NSA) { ring = 0; ring_ph ^= 1; }
         if (tap == 1 && tl >= 1) epilogue(tl - 1);
+      }
+      if constexpr (AFF) {
+        __syncwarp();                                          // every lane is done with this tile's block
+        prefetch_tile(tl + 2);
       }
     }
     cp_async_wait<0>();

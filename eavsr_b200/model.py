@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
+                  dcn_affine, dcn_affine_eligible,
                   conv3x3_64, conv3x3_64_eligible, flow_warp, flow_warp_nhw2, fused_inference_ok,
                   modulated_deform_conv2d)
 
@@ -186,6 +187,19 @@ class _AdaptBlockOffset(_AdaptBase):
         self.D = D
         self.mask_conv = nn.Conv2d(ch, 9 * D, 5, 1, 2)
 
+    def raw(self, x, ref):
+        """(n, 15*D, h, w) output of the merged bias-free convolution and the concatenated biases: the
+        operands of `dcn_affine` (row f1), which expands offsets and masks inside the DCN kernel."""
+        f = self._mix(x, ref)
+        ct, cr, cm = self.transform_matrix_conv, self.translation_conv, self.mask_conv
+        y = F.conv2d(f, self._merged_weight(), None, 1, ct.padding)
+        key = tuple((b.data_ptr(), b._version) for b in (ct.bias, cr.bias, cm.bias))
+        hit = getattr(self, "_merged_bias", None)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([ct.bias.detach(), cr.bias.detach(), cm.bias.detach()]).contiguous())
+            self._merged_bias = hit
+        return y, hit[1]
+
     def forward(self, x, ref):
         f = self._mix(x, ref)
         if fused_inference_ok(f, self.mask_conv.weight):
@@ -223,6 +237,7 @@ class MultiAdSTN(ModulatedDeformConv2d):
         for i in (1, 2, 3):
             setattr(self, f"flow_l{i}", _AdaptBlock2_3x3(ch))
         self.adastn = _AdaptBlockOffset(ch, deformable_groups)
+        self.fuse_offsets = True     # inference: expand offsets / masks inside the DCN kernel (dcn_affine)
         for i in (3, 2, 1):
             setattr(self, f"trans_l{i}", _TransOffset())
 
@@ -242,7 +257,16 @@ class MultiAdSTN(ModulatedDeformConv2d):
         flow = p3 + p2_up + flow
         nbr_w = flow_warp(nbr[0], flow)
         feat = flow_warp(feat_prop, flow)
-        offset, mask = self.adastn(nbr_w, ref[0])
+        if (self.fuse_offsets and fused_inference_ok(nbr_w, self.adastn.mask_conv.weight)
+                and nbr_w.dtype == torch.bfloat16 and tuple(self.weight.shape) == (64, 64, 3, 3)):
+            y, yb = self.adastn.raw(nbr_w, ref[0])
+            if dcn_affine_eligible(feat, y, self.weight, self.deform_groups):
+                return dcn_affine(feat, y, yb, self.weight, self.bias, self.deform_groups, static_weight=True)
+            D = self.deform_groups
+            offset, mask = affine_offsets_mask(y[:, :4 * D], y[:, 4 * D:6 * D], y[:, 6 * D:], D, yb[:4 * D],
+                                               yb[4 * D:6 * D], yb[6 * D:])
+        else:
+            offset, mask = self.adastn(nbr_w, ref[0])
         return modulated_deform_conv2d(feat, offset, mask, self.weight, self.bias, self.stride, self.padding,
                                        self.dilation, self.groups, self.deform_groups,
                                        static_weight=not torch.is_grad_enabled())

@@ -34,7 +34,7 @@ from torch.nn.modules.utils import _pair
 from . import _lib as L
 
 __all__ = [
-    "modulated_deform_conv2d", "ModulatedDeformConv2d", "flow_warp", "flow_warp_nhw2",
+    "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
@@ -472,6 +472,45 @@ def affine_offsets_mask(transform, translation, mask_logits, deform_groups: int,
             _ptr(mask), n, D, h, w, _dtype_code("affine_offsets_mask", transform), _stream(transform)),
             "affine_offsets")
     return offset, mask
+
+
+def dcn_affine_eligible(x, affine, weight, deform_groups: int) -> bool:
+    """True when `dcn_affine` can run: inference, bf16 channels_last 64-channel features, a dense
+    (n, 15*dg, h, w) channels_last bf16 affine block, 64->64 3x3 weights, deform_groups = 8."""
+    return (deform_groups == 8 and x.dim() == 4 and x.shape[1] == 64 and x.dtype == torch.bfloat16
+            and tuple(weight.shape) == (64, 64, 3, 3) and affine.dtype == torch.bfloat16
+            and affine.shape[1] == 15 * deform_groups and affine.shape[0] == x.shape[0]
+            and affine.shape[2:] == x.shape[2:]
+            and affine.is_contiguous(memory_format=torch.channels_last) and affine.data_ptr() % 16 == 0
+            and fused_inference_ok(x, affine, weight))
+
+
+def dcn_affine(x, affine, affine_bias, weight, bias, deform_groups: int = 8, static_weight: bool = False,
+               flags: int = 0):
+    """DCNv2 with the offset generation fused in: equals
+    ``modulated_deform_conv2d(x, *affine_offsets_mask(T, t, m, dg, bT, bt, bm), weight, bias, 1, 1, 1, 1, dg)``
+    with ``T, t, m = affine[:, :4dg], affine[:, 4dg:6dg], affine[:, 6dg:]`` (the raw outputs of
+    AdaptBlockOffset's three convolutions, models/networks.py:302-315) and ``affine_bias`` their
+    concatenated biases -- without the (n, 27*dg, h, w) fp32 offset / mask tensors in HBM.
+    Inference only; check `dcn_affine_eligible` first."""
+    _require_cuda("dcn_affine", x, affine, weight)
+    lib = L.load()
+    n, c, h, w = x.shape
+    with torch.cuda.device(x.device):
+        xd = x.contiguous(memory_format=torch.channels_last)
+        wd = weight.detach().to(x.dtype).contiguous()
+        bd = bias.detach().to(x.dtype).contiguous() if bias is not None else None
+        ab = affine_bias.detach().to(x.dtype).contiguous() if affine_bias is not None else None
+        out = torch.empty_like(xd)
+        code = _dtype_code("dcn_affine", xd)
+        ws_bytes = lib.eavsr_dcn_forward_workspace(64, 64, 3, 3, 1, deform_groups, code)
+        ws, packed = _dcn_workspace(weight, x.dtype, ws_bytes, static_weight)
+        if packed:
+            flags |= DCN_WS_PACKED
+        L.check(lib.eavsr_dcn_affine_forward(xd.data_ptr(), _strides(xd), affine.data_ptr(), _ptr(ab), wd.data_ptr(),
+                                             _ptr(bd), out.data_ptr(), _strides(out), n, h, w, deform_groups, code,
+                                             ws.data_ptr(), ws.numel(), flags, _stream(xd)), "dcn_affine_forward")
+    return out
 
 
 def ca_residual(res, skip, w1, b1, w2, b2, reduction: int = 16, res_bias=None):

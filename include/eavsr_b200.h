@@ -101,6 +101,22 @@ int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], const float* of
                       int dw, int groups, int deform_groups, int dtype, void* workspace,
                       size_t workspace_bytes, unsigned flags, void* stream);
 
+/* DCNv2 with the offset generation fused in.  Replaces the tail of
+ * AdaptBlockOffset.forward -- the T*R - R + t expansion, the sigmoid and the 144 + 72 channel fp32
+ * offset / mask tensors, models/networks.py:302-315 -- together with the modulated_deform_conv2d call at
+ * :627-630.  affine: (n, h, w, 15*dg) dense NHWC bf16, per pixel [4*dg transform | 2*dg translation |
+ * 9*dg mask logits] = the raw output of the transform / translation / mask convolutions;
+ * affine_bias: their 15*dg biases (bf16) or NULL.  For group g and tap k = 3i + j:
+ *   offset_y = T[g][0]*(i-1) + T[g][1]*(j-1) - (i-1) + t[g][0]
+ *   offset_x = T[g][2]*(i-1) + T[g][3]*(j-1) - (j-1) + t[g][1],   mask = sigmoid(logit[g*9+k]).
+ * Only the tensor-core configuration is implemented (64 -> 64, 3x3, stride/pad/dilation 1, groups 1,
+ * dg = 8 -- the model's configuration --, bf16 NHWC x / out): anything else returns EAVSR_ERR_UNSUPPORTED and the caller
+ * composes eavsr_affine_offsets_forward + eavsr_dcn_forward.  workspace as for eavsr_dcn_forward. */
+int eavsr_dcn_affine_forward(const void* x, const int64_t x_strides[4], const void* affine, const void* affine_bias,
+                             const void* weight, const void* bias, void* out, const int64_t out_strides[4], int n,
+                             int h, int w, int deform_groups, int dtype, void* workspace, size_t workspace_bytes,
+                             unsigned flags, void* stream);
+
 /* Gradients wrt x, offset, mask, weight, bias (any output pointer may be NULL = not needed).
  * gx32: fp32 accumulation buffer (zero-filled by the call) with strides gx_strides;
  * goffset/gmask: fp32, layouts of offset/mask;  gweight32: fp32 (cout,cin/groups,kh,kw),

@@ -195,3 +195,42 @@ def test_model_uses_fused_path_only_without_grad(cuda):
     y_torch = blk(x.requires_grad_())
     assert _lib.launch_count() == n1 and y_torch.requires_grad
     assert (y_fused - y_torch.detach()).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 72), (2, 37, 53), (1, 270, 480)])
+def test_dcn_affine_equals_expansion_then_dcn(cuda, shape):
+    """the DCN kernel that expands T*R - R + t and sigmoid(logits) itself equals
+    eavsr_affine_offsets_forward followed by eavsr_dcn_forward on the same bf16 operands (same fp32
+    expansion, same gather; only the window apron differs), and stays inside the bf16 tolerance of the
+    fp64 oracle of the composition."""
+    from eavsr_b200 import ops
+    from oracle import alignment as O
+    n, h, w = shape
+    D = 8
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(n, 64, h, w, generator=g).bfloat16()
+    aff = torch.randn(n, 15 * D, h, w, generator=g)
+    aff[:, :4 * D] = aff[:, :4 * D] * 0.3 + torch.tensor([1.0, 0.0, 0.0, 1.0]).repeat(D).view(1, -1, 1, 1)
+    aff[:, 4 * D:6 * D] *= 1.5
+    aff = aff.bfloat16()
+    ab = (torch.randn(15 * D, generator=g) * 0.2).bfloat16()
+    wgt = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24).bfloat16()
+    bias = (torch.randn(64, generator=g) * 0.1).bfloat16()
+    xd = x.to(cuda).contiguous(memory_format=torch.channels_last)
+    ad = aff.to(cuda).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        assert ops.dcn_affine_eligible(xd, ad, wgt.to(cuda), D)
+        fused = ops.dcn_affine(xd, ad, ab.to(cuda), wgt.to(cuda), bias.to(cuda), D)
+        off, msk = ops.affine_offsets_mask(ad[:, :4 * D], ad[:, 4 * D:6 * D], ad[:, 6 * D:], D, ab[:4 * D].to(cuda),
+                                           ab[4 * D:6 * D].to(cuda), ab[6 * D:].to(cuda))
+        comp = ops.modulated_deform_conv2d(xd, off, msk, wgt.to(cuda), bias.to(cuda), 1, 1, 1, 1, D)
+    assert fused.shape == comp.shape and fused.dtype == torch.bfloat16
+    rms = comp.float().pow(2).mean().sqrt().item()
+    assert (fused.float() - comp.float()).abs().max().item() < 2e-2 * rms
+    assert (fused.float() - comp.float()).abs().mean().item() < 2e-4 * rms     # identical up to rare rounding flips
+    T = aff[:, :4 * D].double() + ab[:4 * D].double().view(1, -1, 1, 1)
+    t = aff[:, 4 * D:6 * D].double() + ab[4 * D:6 * D].double().view(1, -1, 1, 1)
+    lg = aff[:, 6 * D:].double() + ab[6 * D:].double().view(1, -1, 1, 1)
+    ref = O.modulated_deform_conv2d(x.double(), O.affine_offsets(T, t, D), torch.sigmoid(lg), wgt.double(),
+                                    bias.double(), 1, 1, 1, 1, D)
+    assert ((fused.double().cpu() - ref).abs().max() / ref.pow(2).mean().sqrt()).item() < 3e-2
