@@ -130,6 +130,34 @@ def bench_dcn():
                 torch.cuda.empty_cache()
 
 
+def bench_dcn_affine():
+    """row f1: DCN with the offset expansion fused in vs expansion kernel + DCN."""
+    from eavsr_b200 import ops
+    h, w, D = 270, 480, 8
+    k = 4
+    xs = [torch.randn(1, 64, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) for _ in range(k)]
+    affs = []
+    for _ in range(k):
+        a = torch.randn(1, 15 * D, h, w, device=dev)
+        a[:, :4 * D] = a[:, :4 * D] * 0.2 + torch.tensor([1.0, 0.0, 0.0, 1.0], device=dev).repeat(D).view(1, -1, 1, 1)
+        affs.append(a.bfloat16().contiguous(memory_format=torch.channels_last))
+    ab = (torch.randn(15 * D, device=dev) * 0.1).bfloat16()
+    wgt = ((torch.rand(64, 64, 3, 3, device=dev) * 2 - 1) / 24).bfloat16()
+    bias = torch.zeros(64, device=dev, dtype=torch.bfloat16)
+    px = h * w
+    fl = 2.0 * px * 64 * 64 * 9
+    with torch.no_grad():
+        sec = timeit(lambda i: ops.dcn_affine(xs[i % k], affs[i % k], ab, wgt, bias, D, static_weight=True), 40)
+        rec(f"dcn_affine (fused offsets) bf16 dg=8 1x64x{h}x{w}", sec, px * (128 + 240 + 128), fl)
+
+        def two(i):
+            a = affs[i % k]
+            off, msk = ops.affine_offsets_mask(a[:, :4 * D], a[:, 4 * D:6 * D], a[:, 6 * D:], D, ab[:4 * D], ab[4 * D:6 * D], ab[6 * D:])
+            return E.modulated_deform_conv2d(xs[i % k], off, msk, wgt, bias, 1, 1, 1, 1, D, static_weight=True)
+        sec = timeit(two, 40)
+        rec(f"affine_offsets + dcn (unfused) bf16 dg=8 1x64x{h}x{w}", sec, px * (128 + 240 + 128), fl)
+
+
 def bench_corr():
     for n, c, h, w in ((30, 32, 80, 128), (30, 64, 40, 64), (30, 96, 20, 32), (30, 128, 10, 16), (30, 196, 5, 8),
                        (8, 32, 16, 16), (8, 196, 1, 1)):
