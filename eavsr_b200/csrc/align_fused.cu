@@ -236,17 +236,26 @@ ca_scale_residual_kernel(const T* __restrict__ res, const T* __restrict__ skip, 
                          float inv_hw, int chunks_per_img) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int CPP = C / VEC;
+  __shared__ float part[8];
   __shared__ float hid[R];
   __shared__ float scale[C];
   __shared__ float rb[C];                       // bias of the conv that produced `res` (0 if none)
+  static_assert(R * C == 256, "one thread per (hidden unit, channel) product");
   const int n = blockIdx.y;
-  if (threadIdx.x < C) rb[threadIdx.x] = res_bias ? to_f32<T>(res_bias[threadIdx.x]) : 0.f;
-  __syncthreads();
-  if (threadIdx.x < R) {
-    float a = to_f32<T>(b1[threadIdx.x]);
-    for (int i = 0; i < C; ++i) a += to_f32<T>(w1[threadIdx.x * C + i]) * (sums[n * C + i] * inv_hw + rb[i]);
-    hid[threadIdx.x] = fmaxf(a, 0.f);
+  // The squeeze-excite MLP is a prologue every CTA pays before it can stream: all 256 products of the
+  // first layer are loaded and multiplied in parallel (one global round trip) and reduced with shuffles,
+  // instead of four threads walking 64 dependent loads each (~3 us of a 12 us kernel).
+  {
+    const int r = threadIdx.x >> 6, i = threadIdx.x & 63;
+    const float bi = res_bias ? to_f32<T>(res_bias[i]) : 0.f;
+    if (r == 0) rb[i] = bi;
+    float p = to_f32<T>(w1[r * C + i]) * (sums[n * C + i] * inv_hw + bi);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = p;
   }
+  __syncthreads();
+  if (threadIdx.x < R) hid[threadIdx.x] = fmaxf(to_f32<T>(b1[threadIdx.x]) + part[2 * threadIdx.x] + part[2 * threadIdx.x + 1], 0.f);
   __syncthreads();
   if (threadIdx.x < C) {
     float a = to_f32<T>(b2[threadIdx.x]);
