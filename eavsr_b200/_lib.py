@@ -60,6 +60,8 @@ _SIGNATURES = {
     "eavsr_ca_scale_forward": (c_int, [c_void_p, c_void_p, _PF] + [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "eavsr_conv3x3_packed_weight_bytes": (c_size_t, []),
     "eavsr_conv3x3_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "eavsr_conv3x3_ca_forward": (c_int, [c_void_p, c_void_p, _PF] + [c_void_p] * 8 + [_PF] + [c_int] * 3 +
+                                 [c_float, c_int, c_uint, c_void_p]),
     "eavsr_conv3x3_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _PF] + [c_int] * 5 +
                               [c_float, c_int, c_uint, c_void_p]),
 }

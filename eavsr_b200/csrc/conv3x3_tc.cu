@@ -17,7 +17,7 @@
 // One MMA covers 128 consecutive halo positions = a 4 x 32 block of which 4 x 30 are real outputs
 // (the 2 wrap-around columns per row are computed and dropped: 6 % waste).
 //
-// Warp roles (416 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (544 threads, 1 CTA / SM, persistent over tiles):
 //   warps 0-3  producers: cp.async (zero-fill outside the image = conv padding) into a 3-stage ring
 //   warp  4    one lane issues 36 tcgen05.mma per tile (A: no-swizzle descriptors, B: 9 resident
 //              128B-swizzled 64x64 weight tiles) and commits to mbarriers
@@ -27,6 +27,9 @@
 //              ncu stall sampling of the single-group version (profiles/r1_conv3x3_tc_ncu.txt) showed the
 //              epilogue as the serial critical path: as many samples on the store-drain (WAR on the STG
 //              source registers, 30 half-filled sectors per STG.128) as on the wait for the MMAs.
+//   warps 13-16 helper producers, fused-input mode only (eavsr_conv3x3_ca_forward): the previous block's
+//              channel attention y = res * scale + skip is computed while the halo tile is staged (two
+//              warps per stage, 16 independent 16-byte loads in flight per lane) and y is written out once.
 // Two TMEM accumulators (2 x 64 columns) decouple the epilogues from the next tile's MMAs.
 #include <cstdlib>
 
@@ -44,15 +47,20 @@ constexpr int CV_ASTAGE = CV_ROWS * 128;        // 200 rows of 64 bf16 (25 x 102
 constexpr int CV_NS = 4;                        // one stage per producer warp
 constexpr int CV_BTILE = CV_CH * CV_CH * 2;     // 8 KB per tap
 constexpr int CV_PRODUCERS = 128;
-constexpr int CV_THREADS = 416;                 // 4 producer + 1 MMA + 2 x 4 epilogue warps
+// 4 producer + 1 MMA + 2 x 4 epilogue + 4 helper-producer warps.  17 warps put 5 on one SM sub-partition
+// (16 K registers each), so the kernel is held to 96 registers per thread -- 116 would compile for a
+// 64 K register file but fails to launch.
+constexpr int CV_THREADS = 544;
 constexpr int CV_TMEM = 128;
+constexpr int CV_MAXN = 8;                      // images per call in the fused channel-attention mode
 
 struct CvSmem {
   static constexpr int B_OFF = 0;                                  // 9 x 8 KB, 1024-aligned
   static constexpr int A_OFF = B_OFF + 9 * CV_BTILE;               // 3 stages
   static constexpr int BIAS_OFF = ((A_OFF + CV_NS * CV_ASTAGE + 15) / 16) * 16;   // 64 fp32
   static constexpr int RED_OFF = BIAS_OFF + CV_CH * 4;             // 64 fp32: per-CTA channel sums before the atomics
-  static constexpr int BAR_OFF = RED_OFF + CV_CH * 4;
+  static constexpr int SCALE_OFF = RED_OFF + CV_CH * 4;            // fused channel attention: CV_MAXN x 64 fp32 scales
+  static constexpr int BAR_OFF = SCALE_OFF + CV_MAXN * CV_CH * 4;
   // full[NS], empty[NS], accf[2], acce[2], wbar, tmem slot
   static constexpr int TOTAL = BAR_OFF + (2 * CV_NS + 5) * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
@@ -71,11 +79,23 @@ __global__ void conv_pack_weight(const __nv_bfloat16* __restrict__ w, uint8_t* _
       w[((size_t)o * CV_CH + c) * 9 + t];
 }
 
+// Fused input transform (the tail of the previous RCABlock, models/networks.py:449-465): when `res` is set,
+// the convolution's input is y = res * sigmoid(MLP(sums / HW)) + x, built by the producer warps while they
+// stage the halo tile; the interior of every tile is also written to `y_out` (the next block's skip).
+struct CaFuse {
+  const __nv_bfloat16* res;
+  const float* sums;               // (n, 64) channel sums of res
+  const __nv_bfloat16 *w1, *b1, *w2, *b2;
+  __nv_bfloat16* y_out;
+  float inv_hw;
+  int nimg;
+};
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ wpacked,
                   const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                   float* __restrict__ chan_sums, int H, int W, int tiles_x, int tiles_per_img, int total_tiles,
-                  float slope) {
+                  float slope, CaFuse ca) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -95,7 +115,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   }
   if (tid == 0) {
     for (int s = 0; s < CV_NS; ++s) {
-      mbar_init(bar_full + 8 * s, 32);
+      mbar_init(bar_full + 8 * s, ca.res ? 64 : 32);        // fused input transform: two warps fill a stage
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -129,7 +149,29 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
     }
     cp_async_commit();
   };
-  if (warp < 4 && warp < my_tiles) issue_tile(warp);         // first loads in flight before the set-up barrier
+  const bool fused = ca.res != nullptr;
+  if (!fused && warp < 4 && warp < my_tiles) issue_tile(warp);   // first loads in flight before the set-up barrier
+  if (fused && warp >= 5 && warp < 13) {
+    // squeeze-excite MLP of the previous block, once per CTA: 256 threads = 4 hidden units x 64 channels
+    float* scale = reinterpret_cast<float*>(smem + CvSmem::SCALE_OFF);
+    float* part = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);      // (free until the first flush)
+    const int e = tid - 5 * 32, r = e >> 6, i = e & 63;
+    for (int img = 0; img < ca.nimg; ++img) {
+      float pr = __bfloat162float(ca.w1[r * CV_CH + i]) * (ca.sums[img * CV_CH + i] * ca.inv_hw);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, off);
+      if ((e & 31) == 0) part[e >> 5] = pr;
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
+      if (e < CV_CH) {
+        float a = __bfloat162float(ca.b2[e]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          a += __bfloat162float(ca.w2[e * 4 + j]) * fmaxf(__bfloat162float(ca.b1[j]) + part[2 * j] + part[2 * j + 1], 0.f);
+        scale[img * CV_CH + e] = 1.f / (1.f + __expf(-a));
+      }
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
+    }
+  }
   if (warp == 4) tmem_alloc<CV_TMEM>(tmem_slot_addr);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -137,21 +179,73 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 4 || warp >= 13) {
     // ===================== producers =====================
+    // (warps 13-16 only work in the fused-input mode, where they build the second half of the halo tile of
+    // "their" stage: the transform is load-latency bound, two warps per stage keep enough loads in flight)
+    const int phalf = warp >= 13 ? 1 : 0;
+    const int warp_s = warp >= 13 ? warp - 13 : warp;         // stage / tile phase served by this warp
     // Warp w owns stage w and the tiles tl == w (mod 4): it waits for its stage to drain, streams the
     // halo tile in, waits for ITS copies only and publishes.  The four warps are independent, so up
     // to four tiles are in flight and a late MMA never delays the publication of a landed tile.
-    for (int tl = warp; tl < my_tiles; tl += CV_NS) {
+    const float* scale = reinterpret_cast<const float*>(smem + CvSmem::SCALE_OFF);
+    for (int tl = (phalf && !fused) ? my_tiles : warp_s; tl < my_tiles; tl += CV_NS) {
       const int u = tl / CV_NS;
-      if (u >= 1) {
-        mbar_wait(bar_empty + 8 * warp, (u - 1) & 1);
-        issue_tile(tl);                                      // (the first tile of this warp was issued in the prologue)
+      if (u >= 1) mbar_wait(bar_empty + 8 * warp_s, (u - 1) & 1);
+      if (!fused) {
+        if (u >= 1) issue_tile(tl);                          // (the first tile of this warp was issued in the prologue)
+        cp_async_wait<0>();
+      } else {
+        const int tile = first + tl * (int)gridDim.x;
+        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+        const size_t img = (size_t)n * H * W * CV_CH;
+        const uint32_t stage = sA + warp_s * CV_ASTAGE;
+        const float* sc = scale + n * CV_CH + (lane & 7) * 8;      // this lane always handles chunk lane & 7
+        float s8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s8[e] = sc[e];
+        // batches of 8 chunks per lane: 16 independent 16-byte loads in flight before the first use
+        constexpr int NB = 8;
+        static_assert((CV_HROWS * 4) % (32 * NB) == 0, "whole batches per half tile");
+#pragma unroll 1
+        for (int i0 = lane + phalf * (CV_HROWS * 4); i0 < (phalf + 1) * (CV_HROWS * 4); i0 += 32 * NB) {
+          uint4 rv[NB], sv[NB];
+          uint32_t off[NB];                                   // element offsets (n <= 8 images of < 2^24 pixels)
+          bool okv[NB];
+          // volatile asm: ptxas otherwise sinks every load pair down to its use (one round trip per chunk)
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const int p = (i0 + 32 * b) >> 3;
+            const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+            okv[b] = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+            off[b] = okv[b] ? (uint32_t)(img + ((size_t)gy * W + gx) * CV_CH) + (lane & 7) * 8 : 0u;
+            asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(rv[b].x), "=r"(rv[b].y), "=r"(rv[b].z), "=r"(rv[b].w) : "l"(ca.res + off[b]));
+            asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(sv[b].x), "=r"(sv[b].y), "=r"(sv[b].z), "=r"(sv[b].w) : "l"(x + off[b]));
+          }
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const int p = (i0 + 32 * b) >> 3, ch = lane & 7;
+            const int hr = p >> 5, hc = p & 31;
+            const uint32_t rw[4] = {rv[b].x, rv[b].y, rv[b].z, rv[b].w}, sw[4] = {sv[b].x, sv[b].y, sv[b].z, sv[b].w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              ow[e] = pack_bf16x2(bf16lo_to_f32(rw[e]) * s8[2 * e] + bf16lo_to_f32(sw[e]),
+                                  bf16hi_to_f32(rw[e]) * s8[2 * e + 1] + bf16hi_to_f32(sw[e]));
+            const uint4 yv = okv[b] ? make_uint4(ow[0], ow[1], ow[2], ow[3]) : make_uint4(0, 0, 0, 0);
+            if (okv[b] && hr >= 1 && hr <= CV_TR && hc >= 1 && hc <= CV_TC)      // this tile owns the pixel
+              *reinterpret_cast<uint4*>(ca.y_out + off[b]) = yv;
+            *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + warp_s * CV_ASTAGE + p * 128 + ((ch ^ (p & 7)) << 4)) = yv;
+          }
+        }
+        (void)stage;
       }
-      cp_async_wait<0>();
       fence_proxy_async_smem();
       __syncwarp();
-      mbar_arrive(bar_full + 8 * warp);
+      mbar_arrive(bar_full + 8 * warp_s);
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
@@ -183,7 +277,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 13) {
     // ===================== epilogue (warps 5..12 -> TMEM lane quadrants 1,2,3,0, 1,2,3,0) =====================
     const int q = warp & 3;                       // output row of the tile handled by this warp
     const int chalf = (warp - 5) >> 2;            // this group's 32 output channels
@@ -288,36 +382,65 @@ extern "C" int eavsr_conv3x3_pack_weight(const void* weight, void* packed, int c
   return check_launch("conv3x3_pack_weight");
 }
 
-extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
-                                     float* channel_sums, int n, int cin, int cout, int h, int w,
-                                     float negative_slope, int dtype, unsigned flags, void* stream) {
-  EAVSR_REQUIRE(x && packed_weight && out, "conv3x3_forward: null pointer");
-  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_forward: empty tensor");
+namespace eavsr {
+namespace {
+int conv3x3_launch(const void* x, const void* packed_weight, const void* bias, void* out, float* channel_sums, int n,
+                   int cin, int cout, int h, int w, float negative_slope, int dtype, unsigned flags, CaFuse ca,
+                   cudaStream_t st, const char* who) {
+  EAVSR_REQUIRE(x && packed_weight && out, "%s: null pointer", who);
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "%s: empty tensor", who);
   if (cin != CV_CH || cout != CV_CH || dtype != EAVSR_BF16) {
     set_error("conv3x3: only 64->64 bf16 is implemented (got %d->%d, dtype %d)", cin, cout, dtype);
     return EAVSR_ERR_UNSUPPORTED;
   }
   EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                   reinterpret_cast<uintptr_t>(packed_weight)) & 15u) == 0,
-                "conv3x3_forward: x / out / packed weights must be 16-byte aligned dense NHWC");
-  cudaStream_t st = (cudaStream_t)stream;
+                "%s: x / out / packed weights must be 16-byte aligned dense NHWC", who);
   const int tiles_x = ceil_div(w, CV_TC), tiles_y = ceil_div(h, CV_TR);
   const int tiles_per_img = tiles_x * tiles_y;
   const long long total = (long long)tiles_per_img * n;
-  EAVSR_REQUIRE(total < (1ll << 30), "conv3x3_forward: too many tiles");
+  EAVSR_REQUIRE(total < (1ll << 30), "%s: too many tiles", who);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(total < sms ? total : sms);
   if (channel_sums && !(flags & EAVSR_CONV_SUMS_PREZEROED)) {
     cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
-    if (em != cudaSuccess) { set_error("conv3x3_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
+    if (em != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
   }
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem::DYN);
-  if (e != cudaSuccess) { set_error("conv3x3_forward: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
   conv3x3_tc_kernel<<<grid, CV_THREADS, CvSmem::DYN, st>>>((const __nv_bfloat16*)x, (const uint8_t*)packed_weight,
                                                           (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
                                                           channel_sums, h, w, tiles_x, tiles_per_img, (int)total,
-                                                          negative_slope);
-  return check_launch("conv3x3_forward");
+                                                          negative_slope, ca);
+  return check_launch(who);
+}
+}  // namespace
+}  // namespace eavsr
+
+extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
+                                     float* channel_sums, int n, int cin, int cout, int h, int w,
+                                     float negative_slope, int dtype, unsigned flags, void* stream) {
+  CaFuse ca{};
+  return conv3x3_launch(x, packed_weight, bias, out, channel_sums, n, cin, cout, h, w, negative_slope, dtype, flags,
+                        ca, (cudaStream_t)stream, "conv3x3_forward");
+}
+
+extern "C" int eavsr_conv3x3_ca_forward(const void* skip, const void* res, const float* res_sums, const void* w1,
+                                        const void* b1, const void* w2, const void* b2, void* y_out,
+                                        const void* packed_weight, const void* bias, void* out, float* channel_sums,
+                                        int n, int h, int w, float negative_slope, int dtype, unsigned flags,
+                                        void* stream) {
+  EAVSR_REQUIRE(skip && res && res_sums && w1 && b1 && w2 && b2 && y_out, "conv3x3_ca_forward: null pointer");
+  if (n > CV_MAXN) {
+    set_error("conv3x3_ca_forward: at most %d images per call (got %d)", CV_MAXN, n);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y_out)) & 15u) == 0,
+                "conv3x3_ca_forward: res / y_out must be 16-byte aligned dense NHWC");
+  CaFuse ca{(const __nv_bfloat16*)res, res_sums, (const __nv_bfloat16*)w1, (const __nv_bfloat16*)b1,
+            (const __nv_bfloat16*)w2, (const __nv_bfloat16*)b2, (__nv_bfloat16*)y_out, 1.f / ((float)h * (float)w), n};
+  return conv3x3_launch(skip, packed_weight, bias, out, channel_sums, n, CV_CH, CV_CH, h, w, negative_slope, dtype,
+                        flags, ca, (cudaStream_t)stream, "conv3x3_ca_forward");
 }

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
-                  conv3x3_64, conv3x3_64_eligible, flow_warp, flow_warp_nhw2, fused_inference_ok,
+                  conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, flow_warp, flow_warp_nhw2, fused_inference_ok,
                   modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
@@ -74,12 +74,27 @@ class _RCAGroup(nn.Module):
         self.rg = nn.Sequential(*[_RCABlock(ch) for _ in range(nb)], nn.Conv2d(ch, ch, 3, 1, 1))
 
     def forward(self, x):
+        blocks = self.rg[:-1]
+        if conv3x3_64_eligible(self.rg[-1], x) and x.shape[0] <= 8 and len(blocks) > 0:
+            # tcgen05 chain with the channel attention of block i folded into the first convolution of block
+            # i+1 (and of the last block into the group's closing convolution): 2 launches per block,
+            # y_i = y_{i-1} + res_i * scale_i is produced by the consumer's loader warps.
+            pool = torch.zeros((len(blocks), x.shape[0], 64), dtype=torch.float32, device=x.device)
+            y, res, sums, prev = x, None, None, None
+            for i, blk in enumerate(blocks):
+                if prev is None:
+                    h = conv3x3_64(blk.res[0], y, 0.0)
+                else:
+                    du = prev.ca.conv_du
+                    h, y = conv3x3_64_ca(blk.res[0], y, res, sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 0.0)
+                res, sums = conv3x3_64(blk.res[2], h, 1.0, want_sums=True, sums_out=pool[i])
+                prev = blk
+            du = prev.ca.conv_du
+            out, _ = conv3x3_64_ca(self.rg[-1], y, res, sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 1.0)
+            return out + x
         y = x
-        pool = None
-        if conv3x3_64_eligible(self.rg[-1], x):      # one zeroed buffer for the channel sums of all blocks
-            pool = torch.zeros((len(self.rg) - 1, x.shape[0], 64), dtype=torch.float32, device=x.device)
-        for i, blk in enumerate(self.rg[:-1]):
-            y = blk(y, None if pool is None else pool[i])
+        for blk in blocks:
+            y = blk(y)
         if conv3x3_64_eligible(self.rg[-1], y):
             return conv3x3_64(self.rg[-1], y, 1.0) + x
         return conv2d_bias_act(self.rg[-1], y, 1.0) + x

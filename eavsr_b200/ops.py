@@ -37,7 +37,7 @@ __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
-    "conv3x3_64", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
+    "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
 ]
 
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
@@ -621,6 +621,35 @@ def conv3x3_64(conv: nn.Conv2d, x, negative_slope: float = 1.0, want_sums: bool 
                                           1 if (want_sums and sums_out is not None) else 0, _stream(xd)),
                 "conv3x3_forward")
     return (out, sums) if want_sums else out
+
+
+def conv3x3_64_ca(conv: nn.Conv2d, skip, res, res_sums, w1, b1, w2, b2, negative_slope: float = 1.0,
+                  want_sums: bool = False, sums_out=None):
+    """``y = res * sigmoid(MLP(mean(res))) + skip`` (the tail of the previous RCABlock) folded into
+    ``LeakyReLU_slope(conv(y))``: returns ``(out, y)`` or ``(out, y, sums)``.  ``res_sums`` are the channel
+    sums of ``res`` from the `conv3x3_64(..., want_sums=True)` call that produced it.  Same eligibility as
+    `conv3x3_64`, batch <= 8."""
+    lib = L.load()
+    n, c, h, w = skip.shape
+    with torch.cuda.device(skip.device):
+        sd = skip.contiguous(memory_format=torch.channels_last)
+        rd = res.contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(sd)
+        y = torch.empty_like(sd)
+        sums = None
+        if want_sums:
+            sums = sums_out if sums_out is not None else torch.empty((n, 64), dtype=torch.float32, device=skip.device)
+        packed = _packed_conv_weight(conv, skip.device)
+        bias = conv.bias.detach().to(torch.bfloat16).contiguous() if conv.bias is not None else None
+        dt = skip.dtype
+        L.check(lib.eavsr_conv3x3_ca_forward(sd.data_ptr(), rd.data_ptr(), res_sums.data_ptr(),
+                                             w1.to(dt).contiguous().data_ptr(), b1.to(dt).contiguous().data_ptr(),
+                                             w2.to(dt).contiguous().data_ptr(), b2.to(dt).contiguous().data_ptr(),
+                                             y.data_ptr(), packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(sums),
+                                             n, h, w, float(negative_slope), L.BF16,
+                                             1 if (want_sums and sums_out is not None) else 0, _stream(sd)),
+                "conv3x3_ca_forward")
+    return (out, y, sums) if want_sums else (out, y)
 
 
 def ca_scale(res, skip, sums, w1, b1, w2, b2, reduction: int = 16, res_bias=None):

@@ -208,6 +208,17 @@ int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* 
                           float* channel_sums, int n, int cin, int cout, int h, int w, float negative_slope,
                           int dtype, unsigned flags, void* stream);
 
+/* The same convolution with the tail of the previous RCABlock folded into its input
+ * (models/networks.py:449-465): the producer warps build y = res * sigmoid(W2 relu(W1 mean(res) + b1) + b2)
+ * + skip while staging the halo tile (res_sums = per-(n, channel) sums of res from the call that produced
+ * it, reduction 16), the convolution runs on y, and y itself is written to y_out (the next block's
+ * skip).  One launch and ~17 MB of HBM traffic less than eavsr_ca_scale_forward + eavsr_conv3x3_forward
+ * per block.  n <= 8; everything dense NHWC bf16. */
+int eavsr_conv3x3_ca_forward(const void* skip, const void* res, const float* res_sums, const void* w1,
+                             const void* b1, const void* w2, const void* b2, void* y_out,
+                             const void* packed_weight, const void* bias, void* out, float* channel_sums, int n,
+                             int h, int w, float negative_slope, int dtype, unsigned flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

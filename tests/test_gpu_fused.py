@@ -234,3 +234,25 @@ def test_dcn_affine_equals_expansion_then_dcn(cuda, shape):
     ref = O.modulated_deform_conv2d(x.double(), O.affine_offsets(T, t, D), torch.sigmoid(lg), wgt.double(),
                                     bias.double(), 1, 1, 1, 1, D)
     assert ((fused.double().cpu() - ref).abs().max() / ref.pow(2).mean().sqrt()).item() < 3e-2
+
+
+@pytest.mark.parametrize("shape", [(1, 24, 60), (2, 37, 53), (1, 272, 480)])
+def test_conv3x3_with_fused_channel_attention(cuda, shape):
+    """eavsr_conv3x3_ca_forward == eavsr_ca_scale_forward followed by eavsr_conv3x3_forward, bit for bit
+    (same MLP, same fp32 scale-and-add, same bf16 rounding of y), including the y it hands to the next block."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(51)
+    conv0 = torch.nn.Conv2d(64, 64, 3, 1, 1).to(cuda, torch.bfloat16)
+    conv1 = torch.nn.Conv2d(64, 64, 3, 1, 1).to(cuda, torch.bfloat16)
+    du = M._CALayer(64).to(cuda, torch.bfloat16).conv_du
+    skip = torch.randn(n, 64, h, w, generator=g).to(cuda, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    hin = torch.randn(n, 64, h, w, generator=g).to(cuda, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        res, sums = ops.conv3x3_64(conv0, hin, 1.0, want_sums=True)
+        y_ref = ops.ca_scale(res, skip, sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16)
+        out_ref, s_ref = ops.conv3x3_64(conv1, y_ref, 0.0, want_sums=True)
+        out, y, s2 = ops.conv3x3_64_ca(conv1, skip, res, sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias,
+                                       0.0, want_sums=True)
+    assert torch.equal(y, y_ref)
+    assert torch.equal(out, out_ref)
+    assert torch.allclose(s2, s_ref, rtol=1e-4, atol=1e-2)

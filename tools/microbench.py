@@ -194,6 +194,26 @@ def bench_conv():
             rec(f"cuDNN conv3x3 only (torch) bf16 {n}x64x{h}x{w}", sec, by, fl)
 
 
+def bench_convca():
+    """conv3x3 with the previous block's channel attention fused into its loader vs ca_scale + conv3x3."""
+    from eavsr_b200 import ops
+    import eavsr_b200.model as M
+    h, w = 272, 480
+    conv = torch.nn.Conv2d(64, 64, 3, 1, 1).to(dev, torch.bfloat16)
+    du = M._CALayer(64).to(dev, torch.bfloat16).conv_du
+    k = 6
+    mk = lambda: torch.randn(1, 64, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)   # noqa: E731
+    skips, ress = [mk() for _ in range(k)], [mk() for _ in range(k)]
+    sums = torch.randn(1, 64, device=dev) * 100
+    by = h * w * 64 * 2 * 4
+    fl = 2.0 * h * w * 64 * 64 * 9
+    with torch.no_grad():
+        sec = timeit(lambda i: ops.conv3x3_64_ca(conv, skips[i % k], ress[i % k], sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 0.0), 40)
+        rec(f"conv3x3 + fused channel attention input bf16 1x64x{h}x{w}", sec, by, fl)
+        sec = timeit(lambda i: ops.conv3x3_64(conv, ops.ca_scale(ress[i % k], skips[i % k], sums, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16), 0.0), 40)
+        rec(f"ca_scale + conv3x3 (2 launches) bf16 1x64x{h}x{w}", sec, by, fl)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["warp", "dcn", "corr", "conv"]
     for wname in which:
