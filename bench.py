@@ -259,6 +259,50 @@ def dcn_backward_us(device, dg, iters=5):
     return a.elapsed_time(b) * 1e3 / iters
 
 
+def dcn_affine_us(device, peaks, iters=40):
+    """SURVEY.md 8 row f1, the kernel the model's inference path actually launches: DCNv2 with the offset
+    expansion fused in (496 algorithmic B/px: x, the 120-channel bf16 affine block, out)."""
+    from eavsr_b200 import ops
+    h, w, D = LR_H, LR_W, 8
+    g = torch.Generator().manual_seed(2)
+    nbuf = 4
+    xs = [torch.randn(1, 64, h, w, generator=g).to(device, torch.bfloat16).contiguous(
+        memory_format=torch.channels_last) for _ in range(nbuf)]
+    affs = []
+    for _ in range(nbuf):
+        a = torch.randn(1, 15 * D, h, w, generator=g)
+        a[:, :4 * D] = a[:, :4 * D] * 0.2 + torch.tensor([1.0, 0.0, 0.0, 1.0]).repeat(D).view(1, -1, 1, 1)
+        affs.append(a.to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    ab = (torch.randn(15 * D, generator=g) * 0.1).to(device, torch.bfloat16)
+    wgt = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24).to(device, torch.bfloat16)
+    bias = torch.zeros(64, device=device, dtype=torch.bfloat16)
+
+    def call(i):
+        return ops.dcn_affine(xs[i % nbuf], affs[i % nbuf], ab, wgt, bias, D, static_weight=True)
+    for i in range(4):
+        call(i)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            keep = [call(i) for i in range(iters)]
+        graph.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        side.synchronize()
+        a.record(side)
+        graph.replay()
+        b.record(side)
+        side.synchronize()
+    del keep
+    sec = a.elapsed_time(b) / 1e3 / iters
+    bytes_alg = h * w * (64 * 2 + 15 * D * 2 + 64 * 2)
+    flops = 2.0 * h * w * 64 * 64 * 9
+    return {"kernel": "win::dcn_fwd_win_kernel<dg=8,bf16,fused offsets>", "us_per_launch": round(sec * 1e6, 2),
+            "algorithmic_bytes_per_launch": bytes_alg, "hbm_frac": round(bytes_alg / sec / 1e9 / peaks["hbm_gbs"], 4),
+            "tensor_frac": round(flops / sec / 1e12 / peaks["bf16_tflops"], 4)}
+
+
 def dcn_roofline(device, peaks, dg=8, iters=60, nested=True):
     import eavsr_b200 as E
     h, w = LR_H, LR_W
@@ -322,6 +366,10 @@ def dcn_roofline(device, peaks, dg=8, iters=60, nested=True):
                                    "bwd_us_dg8": round(dcn_backward_us(device, 8), 1)}
         except Exception as exc:  # an extra, never a reason to lose the bench line
             res["config2_dg16"] = {"failed": repr(exc)}
+        try:
+            res["fused_offsets_dg8"] = dcn_affine_us(device, peaks)
+        except Exception as exc:
+            res["fused_offsets_dg8"] = {"failed": repr(exc)}
     return res
 
 
