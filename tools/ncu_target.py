@@ -33,6 +33,17 @@ elif what in ("dcn", "dcn_bwd", "dcn_bwd_nox"):
         for _ in range(2):
             out = E.modulated_deform_conv2d(x, off, msk, wgt, bias, 1, 1, 1, 1, dg)
             out.backward(torch.ones_like(out))
+elif what == "warp_bwd":
+    x = torch.randn(1, 64, 270, 480, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
+    flow = (torch.randn(1, 2, 270, 480, generator=g) * 3).to(dev).requires_grad_()
+    for _ in range(3):
+        out = E.flow_warp(x, flow)
+        out.backward(torch.ones_like(out))
+    a = torch.randn(8, 32, 80, 128, generator=g).to(dev).requires_grad_()
+    b = torch.randn(8, 32, 80, 128, generator=g).to(dev).requires_grad_()
+    for _ in range(2):
+        o = E.FunctionCorrelation(tenFirst=a, tenSecond=b)
+        o.backward(torch.ones_like(o))
 elif what == "warp":
     x = torch.randn(8, 64, 270, 480, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
     flow = (torch.randn(8, 2, 270, 480, generator=g) * 3).to(dev)
