@@ -86,10 +86,14 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flow, int la
 // ------------------------------------------------------------------------------------------
 constexpr int LEAN_THREADS = 128;
 
-template <typename T, int CPP, int PAD>
+// DUAL: two feature maps warped with the same flow in one launch (nbr and feat_prop
+// in MultiAdSTN.forward, models/networks.py:621-623) -- the flow read and phase 1 are shared.
+template <typename T, int CPP, int PAD, bool DUAL = false>
 __global__ void __launch_bounds__(LEAN_THREADS)
 flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* __restrict__ out, int H, int W,
-                   int layout, int tiles_x, int tiles_y, long long xs_n, long long os_n) {
+                   int layout, int tiles_x, int tiles_y, long long xs_n, long long os_n,
+                   const T* __restrict__ x2 = nullptr, T* __restrict__ out2 = nullptr, long long xs2_n = 0,
+                   long long os2_n = 0) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int C = CPP * VEC;
   constexpr int PPI = 32 / CPP;          // pixels per phase-2 iteration
@@ -100,8 +104,8 @@ flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* _
   // warp patch origin inside the 8x16 CTA tile (2x2 patches of 4 rows x 8 cols)
   const int py0 = (tile / tiles_x) * TILE_H + (warp >> 1) * 4;
   const int px0 = (tile % tiles_x) * TILE_W + (warp & 1) * 8;
-  const T* __restrict__ xn = x + (size_t)n * xs_n;
-  T* __restrict__ on = out + (size_t)n * os_n;
+  const T* xn = x + (size_t)n * xs_n;
+  T* on = out + (size_t)n * os_n;
 
   // phase 1: lane <-> pixel (row = lane / 8, col = lane % 8)
   const int y = py0 + (lane >> 3), xq = px0 + (lane & 7);
@@ -142,6 +146,9 @@ flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* _
   constexpr int UN = CPP >= 4 ? 4 : CPP;
   constexpr int NW = RawVec<T, VEC>::NW;
 #pragma unroll 1
+  for (int pass = 0; pass < (DUAL ? 2 : 1); ++pass) {
+  if (DUAL && pass == 1) { xn = x2 + (size_t)n * xs2_n; on = out2 + (size_t)n * os2_n; }
+#pragma unroll 1
   for (int sub0 = 0; sub0 < CPP; sub0 += UN) {
     uint32_t raw[UN][4][NW];
     float a[UN][4];
@@ -171,6 +178,7 @@ flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* _
       const int oy = py0 + (src >> 3), ox = px0 + (src & 7);
       if ((live_mask >> src) & 1u) VecLoad<T, VEC>::st(on + (uint32_t)(oy * W + ox) * C + chunk * VEC, r);
     }
+  }
   }
 }
 
@@ -521,4 +529,36 @@ extern "C" int eavsr_flow_warp_backward(const void* gout, const int64_t gout_str
   if (dtype == EAVSR_BF16) return bwd_dispatch<__nv_bfloat16>(gout, gout_strides, x, x_strides, flow, flow_layout, gx32, gx_strides, gflow, n, c, h, w, padding_mode, st);
   set_error("flow_warp_backward: bad dtype %d", dtype);
   return EAVSR_ERR_INVALID;
+}
+
+extern "C" int eavsr_flow_warp2_forward(const void* x1, const int64_t x1_strides[4], const void* x2,
+                                        const int64_t x2_strides[4], const float* flow, int flow_layout, void* out1,
+                                        const int64_t out1_strides[4], void* out2, const int64_t out2_strides[4],
+                                        int n, int c, int h, int w, int dtype, int padding_mode, void* stream) {
+  EAVSR_REQUIRE(x1 && x2 && flow && out1 && out2 && x1_strides && x2_strides && out1_strides && out2_strides,
+                "flow_warp2_forward: null pointer");
+  EAVSR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "flow_warp2_forward: empty tensor");
+  EAVSR_REQUIRE(flow_layout == EAVSR_FLOW_N2HW || flow_layout == EAVSR_FLOW_NHW2, "flow_warp2_forward: bad flow_layout %d", flow_layout);
+  EAVSR_REQUIRE(padding_mode == EAVSR_PAD_ZEROS || padding_mode == EAVSR_PAD_BORDER, "flow_warp2_forward: bad padding_mode %d", padding_mode);
+  auto ok = [&](const void* p, const int64_t* s) {
+    return is_nhwc_dense(s, c, h, w) && aligned16(p) && (s[0] * 2) % 16 == 0;
+  };
+  if (dtype != EAVSR_BF16 || c != 64 || (long long)h * w * c >= (1ll << 31) || !ok(x1, x1_strides) ||
+      !ok(x2, x2_strides) || !ok(out1, out1_strides) || !ok(out2, out2_strides)) {
+    set_error("flow_warp2_forward: only dense NHWC bf16 64-channel maps are fused (call flow_warp_forward twice)");
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  using T = __nv_bfloat16;
+  const int tx = ceil_div(w, TILE_W), ty = ceil_div(h, TILE_H);
+  const long long blocks = (long long)n * tx * ty;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (padding_mode == EAVSR_PAD_ZEROS)
+    flow_warp_fwd_lean<T, 8, EAVSR_PAD_ZEROS, true><<<(unsigned)blocks, LEAN_THREADS, 0, st>>>(
+        (const T*)x1, flow, (T*)out1, h, w, flow_layout, tx, ty, x1_strides[0], out1_strides[0], (const T*)x2, (T*)out2,
+        x2_strides[0], out2_strides[0]);
+  else
+    flow_warp_fwd_lean<T, 8, EAVSR_PAD_BORDER, true><<<(unsigned)blocks, LEAN_THREADS, 0, st>>>(
+        (const T*)x1, flow, (T*)out1, h, w, flow_layout, tx, ty, x1_strides[0], out1_strides[0], (const T*)x2, (T*)out2,
+        x2_strides[0], out2_strides[0]);
+  return check_launch("flow_warp2_forward");
 }

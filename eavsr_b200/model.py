@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
-                  conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, flow_warp, flow_warp_nhw2, fused_inference_ok,
+                  conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, flow_warp, flow_warp2, flow_warp_nhw2, fused_inference_ok,
                   modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
@@ -270,8 +270,11 @@ class MultiAdSTN(ModulatedDeformConv2d):
         p2_up = _resize_flow(p2 + p1_up, 2)
         p3 = self._residual(1, flow_warp(nbr[0], flow + p2_up), ref[0])
         flow = p3 + p2_up + flow
-        nbr_w = flow_warp(nbr[0], flow)
-        feat = flow_warp(feat_prop, flow)
+        if fused_inference_ok(nbr[0], feat_prop, flow):
+            nbr_w, feat = flow_warp2(nbr[0], feat_prop, flow)     # one launch when eligible (row f2)
+        else:
+            nbr_w = flow_warp(nbr[0], flow)
+            feat = flow_warp(feat_prop, flow)
         if (self.fuse_offsets and fused_inference_ok(nbr_w, self.adastn.mask_conv.weight)
                 and nbr_w.dtype == torch.bfloat16 and tuple(self.weight.shape) == (64, 64, 3, 3)):
             y, yb = self.adastn.raw(nbr_w, ref[0])

@@ -171,6 +171,30 @@ def flow_warp_nhw2(x, flow, interpolation='bilinear', padding_mode='zeros', alig
     return _flow_warp("flow_warp", x, flow, L.FLOW_NHW2, interpolation, padding_mode, align_corners)
 
 
+def flow_warp2(x1, x2, flow, padding_mode='zeros'):
+    """``(flow_warp(x1, flow), flow_warp(x2, flow))`` in one launch when both are dense channels_last bf16
+    64-channel maps and no gradient is needed (``nbr`` and ``feat_prop`` share
+    one flow in MultiAdSTN.forward, models/networks.py:621-623); two ordinary calls otherwise."""
+    ok = (fused_inference_ok(x1, x2, flow) and x1.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16
+          and x1.shape == x2.shape and x1.dim() == 4 and x1.shape[1] == 64
+          and x1.is_contiguous(memory_format=torch.channels_last)
+          and x2.is_contiguous(memory_format=torch.channels_last)
+          and flow.dim() == 4 and flow.shape[1] == 2 and flow.shape[2:] == x1.shape[2:]
+          and padding_mode in ('zeros', 'border'))
+    if not ok:
+        return flow_warp(x1, flow, padding_mode=padding_mode), flow_warp(x2, flow, padding_mode=padding_mode)
+    lib = L.load()
+    n, c, h, w = x1.shape
+    with torch.cuda.device(x1.device):
+        f32 = flow.detach().to(torch.float32).contiguous()
+        o1, o2 = torch.empty_like(x1), torch.empty_like(x2)
+        L.check(lib.eavsr_flow_warp2_forward(x1.data_ptr(), _strides(x1), x2.data_ptr(), _strides(x2), f32.data_ptr(),
+                                             L.FLOW_N2HW, o1.data_ptr(), _strides(o1), o2.data_ptr(), _strides(o2),
+                                             n, c, h, w, L.BF16, L.PAD_ZEROS if padding_mode == 'zeros' else L.PAD_BORDER,
+                                             _stream(x1)), "flow_warp2_forward")
+    return o1, o2
+
+
 # ------------------------------------------------------------------------------------------
 # DCNv2
 # ------------------------------------------------------------------------------------------

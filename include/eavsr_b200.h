@@ -70,6 +70,14 @@ int eavsr_flow_warp_forward(const void* x, const int64_t x_strides[4], const flo
                             void* out, const int64_t out_strides[4], int n, int c, int h, int w, int dtype,
                             int padding_mode, void* stream);
 
+/* Two feature maps warped with the same flow in one launch (`nbr` and
+ * `feat_prop` in MultiAdSTN.forward, models/networks.py:621-623).  Dense NHWC bf16, c = 64 only; anything
+ * else returns EAVSR_ERR_UNSUPPORTED and the caller issues two eavsr_flow_warp_forward calls. */
+int eavsr_flow_warp2_forward(const void* x1, const int64_t x1_strides[4], const void* x2,
+                             const int64_t x2_strides[4], const float* flow, int flow_layout, void* out1,
+                             const int64_t out1_strides[4], void* out2, const int64_t out2_strides[4], int n, int c,
+                             int h, int w, int dtype, int padding_mode, void* stream);
+
 /* Gradients of the above.  gx32 is an fp32 accumulation buffer with strides gx_strides that
  * the call zero-fills and scatter-adds into (for dtype F32 it is the final gradient);
  * gflow (fp32, same layout as flow) may be NULL when the flow needs no gradient.

@@ -256,3 +256,19 @@ def test_conv3x3_with_fused_channel_attention(cuda, shape):
     assert torch.equal(y, y_ref)
     assert torch.equal(out, out_ref)
     assert torch.allclose(s2, s_ref, rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_flow_warp2_equals_two_warps(cuda, pad):
+    """Row f2: both 64-channel maps warped with one flow in one launch == two eavsr_flow_warp_forward calls."""
+    g = torch.Generator().manual_seed(61)
+    mk = lambda: torch.randn(2, 64, 37, 53, generator=g).to(cuda, torch.bfloat16).contiguous(memory_format=torch.channels_last)   # noqa: E731
+    a, b = mk(), mk()
+    flow = (torch.randn(2, 2, 37, 53, generator=g) * 3).to(cuda)
+    with torch.no_grad():
+        o1, o2 = ops.flow_warp2(a, b, flow, padding_mode=pad)
+        r1, r2 = ops.flow_warp(a, flow, padding_mode=pad), ops.flow_warp(b, flow, padding_mode=pad)
+    assert torch.equal(o1, r1) and torch.equal(o2, r2)
+    # not eligible (fp32): falls back to two calls
+    o1, o2 = ops.flow_warp2(a.float(), b.float(), flow)
+    assert torch.allclose(o1, ops.flow_warp(a.float(), flow)) and o2.dtype == torch.float32
