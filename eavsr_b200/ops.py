@@ -504,7 +504,7 @@ def dcn_affine_eligible(x, affine, weight, deform_groups: int) -> bool:
     return (deform_groups == 8 and x.dim() == 4 and x.shape[1] == 64 and x.dtype == torch.bfloat16
             and tuple(weight.shape) == (64, 64, 3, 3) and affine.dtype == torch.bfloat16
             and affine.shape[1] == 15 * deform_groups and affine.shape[0] == x.shape[0]
-            and affine.shape[2:] == x.shape[2:]
+            and affine.shape[2:] == x.shape[2:] and x.shape[2] * x.shape[3] <= (1 << 24)
             and affine.is_contiguous(memory_format=torch.channels_last) and affine.data_ptr() % 16 == 0
             and fused_inference_ok(x, affine, weight))
 
