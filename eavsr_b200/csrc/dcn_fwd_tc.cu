@@ -333,14 +333,14 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
       const bool b16 = !(flags & EAVSR_DCN_BLEND_FP32);
       void (*k)(const __nv_bfloat16*, const float*, const float*, const uint8_t*, const __nv_bfloat16*,
                 __nv_bfloat16*, int, int, long long, long long, int, int, int, const __nv_bfloat16*,
-                const __nv_bfloat16*) =
+                const __nv_bfloat16*, int) =
           vecw ? (b16 ? win::dcn_fwd_win_kernel<DG, true, true> : win::dcn_fwd_win_kernel<DG, true, false>)
                : (b16 ? win::dcn_fwd_win_kernel<DG, false, true> : win::dcn_fwd_win_kernel<DG, false, false>);
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, win::Cfg<DG>::DYN);
       if (e != cudaSuccess) { set_error("dcn_forward(win): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
       k<<<g3, win::THREADS, win::Cfg<DG>::DYN, st>>>((const __nv_bfloat16*)x, offset, mask, (const uint8_t*)workspace,
                                                  (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0], os[0],
-                                                 tiles_x, tpi, tot, nullptr, nullptr);
+                                                 tiles_x, tpi, tot, nullptr, nullptr, CH);
       return check_launch("dcn_forward(win)");
     }
   }
@@ -487,7 +487,8 @@ int launch_affine(const void* x, const int64_t* xs, const void* affine, const vo
   if (e != cudaSuccess) { set_error("dcn_affine_forward: smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
   k<<<grid, win::THREADS, C::DYN, st>>>((const __nv_bfloat16*)x, nullptr, nullptr, (const uint8_t*)workspace,
                                         (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0], os[0], tiles_x,
-                                        tpi, tot, (const __nv_bfloat16*)affine, (const __nv_bfloat16*)affine_bias);
+                                        tpi, tot, (const __nv_bfloat16*)affine, (const __nv_bfloat16*)affine_bias,
+                                        (int)os[3]);
   return check_launch("dcn_affine_forward");
 }
 }  // namespace
@@ -503,7 +504,10 @@ extern "C" int eavsr_dcn_affine_forward(const void* x, const int64_t x_strides[4
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool ok = dtype == EAVSR_BF16 &&
                   deform_groups == 8 &&   // 15*dg bf16 per pixel must be a multiple of 16 bytes
-                  nhwc_dense(x_strides, CH, h, w) && nhwc_dense(out_strides, CH, h, w) && al16(x) && al16(out) &&
+                  nhwc_dense(x_strides, CH, h, w) && al16(x) && al16(out) &&
+                  // out may be a 64-channel slice of a wider NHWC buffer (pixel stride >= 64, multiple of 8)
+                  out_strides[1] == 1 && out_strides[3] >= CH && out_strides[3] % 8 == 0 && out_strides[3] < (1 << 20) &&
+                  out_strides[2] == (int64_t)w * out_strides[3] && out_strides[0] >= (int64_t)h * w * out_strides[3] &&
                   al16(affine) && (x_strides[0] * 2) % 16 == 0 && (out_strides[0] * 2) % 16 == 0 &&
                   (long long)h * w <= (1ll << 24) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 3u) == 0);
   if (!ok) {

@@ -99,7 +99,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
                    long long xs_n, long long os_n, int tiles_x, int tiles_per_img, int total_tiles,
                    const __nv_bfloat16* __restrict__ aff = nullptr,
-                   const __nv_bfloat16* __restrict__ aff_bias = nullptr) {
+                   const __nv_bfloat16* __restrict__ aff_bias = nullptr, int os_pix = CH) {
   using C = Cfg<DG, AFF>;
   using Smem = Cfg<DG, AFF>;
   constexpr int NSUB = C::NSUB, PAD = C::PAD, WH = C::WH, WW = C::WW, WIN_BYTES = C::WIN_BYTES;
@@ -315,7 +315,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       const int m = qd * 32 + lane;
       const int gy = ty0 + (m >> 4), gx = tx0 + (m & 15);
       if (gy < H && gx < W) {
-        __nv_bfloat16* op = out + (size_t)n * os_n + ((size_t)gy * W + gx) * CH + cq * 16;
+        __nv_bfloat16* op = out + (size_t)n * os_n + ((size_t)gy * W + gx) * os_pix + cq * 16;
         float f[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(acc[e]) + (bias ? __bfloat162float(bias[cq * 16 + e]) : 0.f);

@@ -260,7 +260,9 @@ class MultiAdSTN(ModulatedDeformConv2d):
         off18 = getattr(self, f"flow_l{lvl}")(warped, ref)
         return getattr(self, f"trans_l{lvl}")(off18.to(warped.dtype)).float()
 
-    def forward(self, nbr, ref, feat_prop, flow):
+    def forward(self, nbr, ref, feat_prop, flow, out=None):
+        """`out`: optional 64-channel slice of a wider channels_last buffer that receives the result when the
+        fused-offset DCN runs (saves the torch.cat copy of the caller); the returned tensor is what to use."""
         flow = flow.float()
         f4 = _resize_flow(flow, 0.25)
         f2 = _resize_flow(flow, 0.5)
@@ -279,7 +281,8 @@ class MultiAdSTN(ModulatedDeformConv2d):
                 and nbr_w.dtype == torch.bfloat16 and tuple(self.weight.shape) == (64, 64, 3, 3)):
             y, yb = self.adastn.raw(nbr_w, ref[0])
             if dcn_affine_eligible(feat, y, self.weight, self.deform_groups):
-                return dcn_affine(feat, y, yb, self.weight, self.bias, self.deform_groups, static_weight=True)
+                return dcn_affine(feat, y, yb, self.weight, self.bias, self.deform_groups, static_weight=True,
+                                  out=out)
             D = self.deform_groups
             offset, mask = affine_offsets_mask(y[:, :4 * D], y[:, 4 * D:6 * D], y[:, 6 * D:], D, yb[:4 * D],
                                                yb[4 * D:6 * D], yb[6 * D:])
@@ -407,13 +410,29 @@ class EAVSRP(nn.Module):
             cur = feats["spatial"][idx]
             if i > 0:
                 flow1 = flows[:, idx if backward else idx - 1]
-                cond1 = align(pyr(idx + step), pyr(idx), prop, flow1)
+                # [cond1 | cur | cond2]: the aligned features are written straight into their slices of the
+                # fusion convolution's input when the fused-offset DCN runs (no torch.cat pass)
+                cat3 = None
+                if fused_inference_ok(cur, prop) and cur.dtype == torch.bfloat16:
+                    cat3 = torch.empty((n, 3 * self.n_feats, h, w), dtype=cur.dtype, device=cur.device,
+                                       memory_format=torch.channels_last)
+                nf = self.n_feats
+                cond1 = align(pyr(idx + step), pyr(idx), prop, flow1, out=None if cat3 is None else cat3[:, :nf])
                 if i > 1:
                     flow2 = flow1 + flow_warp_nhw2(prev_flow, flow1.permute(0, 2, 3, 1))
-                    cond2 = align(pyr(idx + 2 * step), pyr(idx), outs[-2], flow2)
+                    cond2 = align(pyr(idx + 2 * step), pyr(idx), outs[-2], flow2,
+                                  out=None if cat3 is None else cat3[:, 2 * nf:])
                 else:
                     cond2 = torch.zeros_like(cond1)
-                prop = conv2d_bias_act(fuse, torch.cat([cond1, cur, cond2], 1), 1.0)
+                if cat3 is not None:
+                    if cond1.data_ptr() != cat3.data_ptr():
+                        cat3[:, :nf].copy_(cond1)
+                    cat3[:, nf:2 * nf].copy_(cur)
+                    if cond2.data_ptr() != cat3[:, 2 * nf:].data_ptr():
+                        cat3[:, 2 * nf:].copy_(cond2)
+                    prop = conv2d_bias_act(fuse, cat3, 1.0)
+                else:
+                    prop = conv2d_bias_act(fuse, torch.cat([cond1, cur, cond2], 1), 1.0)
                 prev_flow = flow1
             x = torch.cat([cur] + [feats[k][idx] for k in others] + [prop], 1)
             prop = prop + body(x)

@@ -510,13 +510,14 @@ def dcn_affine_eligible(x, affine, weight, deform_groups: int) -> bool:
 
 
 def dcn_affine(x, affine, affine_bias, weight, bias, deform_groups: int = 8, static_weight: bool = False,
-               flags: int = 0):
+               flags: int = 0, out=None):
     """DCNv2 with the offset generation fused in: equals
     ``modulated_deform_conv2d(x, *affine_offsets_mask(T, t, m, dg, bT, bt, bm), weight, bias, 1, 1, 1, 1, dg)``
     with ``T, t, m = affine[:, :4dg], affine[:, 4dg:6dg], affine[:, 6dg:]`` (the raw outputs of
     AdaptBlockOffset's three convolutions, models/networks.py:302-315) and ``affine_bias`` their
     concatenated biases -- without the (n, 27*dg, h, w) fp32 offset / mask tensors in HBM.
-    Inference only; check `dcn_affine_eligible` first."""
+    Inference only; check `dcn_affine_eligible` first.  ``out`` may be a 64-channel slice (dim 1) of a wider
+    channels_last bf16 buffer: the result is written in place there (no torch.cat copy afterwards)."""
     _require_cuda("dcn_affine", x, affine, weight)
     lib = L.load()
     n, c, h, w = x.shape
@@ -525,7 +526,10 @@ def dcn_affine(x, affine, affine_bias, weight, bias, deform_groups: int = 8, sta
         wd = weight.detach().to(x.dtype).contiguous()
         bd = bias.detach().to(x.dtype).contiguous() if bias is not None else None
         ab = affine_bias.detach().to(x.dtype).contiguous() if affine_bias is not None else None
-        out = torch.empty_like(xd)
+        if out is None:
+            out = torch.empty_like(xd)
+        else:
+            assert out.shape == xd.shape and out.dtype == xd.dtype and out.stride(1) == 1, "dcn_affine: bad out view"
         code = _dtype_code("dcn_affine", xd)
         ws_bytes = lib.eavsr_dcn_forward_workspace(64, 64, 3, 3, 1, deform_groups, code)
         ws, packed = _dcn_workspace(weight, x.dtype, ws_bytes, static_weight)

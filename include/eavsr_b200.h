@@ -119,7 +119,10 @@ int eavsr_dcn_forward(const void* x, const int64_t x_strides[4], const float* of
  *   offset_x = T[g][2]*(i-1) + T[g][3]*(j-1) - (j-1) + t[g][1],   mask = sigmoid(logit[g*9+k]).
  * Only the tensor-core configuration is implemented (64 -> 64, 3x3, stride/pad/dilation 1, groups 1,
  * dg = 8 -- the model's configuration --, bf16 NHWC x / out): anything else returns EAVSR_ERR_UNSUPPORTED and the caller
- * composes eavsr_affine_offsets_forward + eavsr_dcn_forward.  workspace as for eavsr_dcn_forward. */
+ * composes eavsr_affine_offsets_forward + eavsr_dcn_forward.  workspace as for eavsr_dcn_forward.
+ * `out` may be a 64-channel slice of a wider NHWC buffer (out_strides[3] = its channel count, a multiple
+ * of 8): the aligned feature is then written straight into the concatenated input of the next convolution
+ * (torch.cat([cond1, cur, cond2]) in EAVSRP.propagate, models/eavsrp_model.py:271-324). */
 int eavsr_dcn_affine_forward(const void* x, const int64_t x_strides[4], const void* affine, const void* affine_bias,
                              const void* weight, const void* bias, void* out, const int64_t out_strides[4], int n,
                              int h, int w, int deform_groups, int dtype, void* workspace, size_t workspace_bytes,

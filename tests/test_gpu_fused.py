@@ -225,6 +225,12 @@ def test_dcn_affine_equals_expansion_then_dcn(cuda, shape):
                                            ab[4 * D:6 * D].to(cuda), ab[6 * D:].to(cuda))
         comp = ops.modulated_deform_conv2d(xd, off, msk, wgt.to(cuda), bias.to(cuda), 1, 1, 1, 1, D)
     assert fused.shape == comp.shape and fused.dtype == torch.bfloat16
+    # written in place into the middle 64 channels of a wider NHWC buffer (the caller's torch.cat input)
+    wide = torch.full((n, 192, h, w), 7.0, dtype=torch.bfloat16, device=cuda).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = ops.dcn_affine(xd, ad, ab.to(cuda), wgt.to(cuda), bias.to(cuda), D, out=wide[:, 64:128])
+    assert got.data_ptr() == wide[:, 64:128].data_ptr() and torch.equal(wide[:, 64:128], fused)
+    assert bool((wide[:, :64] == 7).all()) and bool((wide[:, 128:] == 7).all())
     rms = comp.float().pow(2).mean().sqrt().item()
     assert (fused.float() - comp.float()).abs().max().item() < 2e-2 * rms
     assert (fused.float() - comp.float()).abs().mean().item() < 2e-4 * rms     # identical up to rare rounding flips
