@@ -71,14 +71,18 @@ adapt_mix_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __re
   for (int i = tid; i < MX_C / 2; i += MX_THREADS) S.b2[i] = to_f32<T>(b2g[half * (MX_C / 2) + i]);
 
   // input tile with a 2-pixel halo, zero outside the image (conv zero padding)
+  // (cp.async: all 7-8 copies of a thread in flight at once -- with a load -> store loop the tile fill was a
+  // chain of dependent L2 round trips and 28 % of the kernel's stall samples sat on its STS)
   for (int i = tid; i < MX_IH * MX_IW * CPP; i += MX_THREADS) {
     const int p = i / CPP, ch = i % CPP;
     const int gy = y0 - 2 + p / MX_IW, gx = x0 - 2 + p % MX_IW;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)gy * W + gx) * MX_C) + ch);
-    *reinterpret_cast<uint4*>(&S.in[p][ch * VEC]) = v;
+    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const T* g = ok ? src + ((size_t)gy * W + gx) * MX_C + ch * VEC : src;
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(&S.in[p][ch * VEC])), "l"(g), "r"(sz));
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
 
   // Every thread works on ONE 8-channel chunk for the whole kernel (256 % 8 == 0), so its 9x8 weights
