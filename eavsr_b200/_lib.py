@@ -20,6 +20,10 @@ DCN_FORCE_GENERIC = 1
 DCN_FORCE_V1 = 2
 DCN_FORCE_WS = 4
 DCN_BLEND_FP32 = 8
+DCN_WS_PACKED = 16
+DCN_BWD_GENERIC_DATA = 32
+DCN_BWD_GENERIC_WEIGHT = 64
+CONV_SUMS_PREZEROED = 1
 
 Strides = c_int64 * 4
 _P64 = POINTER(c_int64)

@@ -218,7 +218,7 @@ def dcn_uses_tensor_cores(x, weight, stride=1, padding=0, dilation=1, groups=1, 
                                                         sh, sw, ph, pw, dh, dw, groups, deform_groups, 0))
 
 
-DCN_WS_PACKED = 16          # include/eavsr_b200.h EAVSR_DCN_WS_PACKED
+DCN_WS_PACKED = L.DCN_WS_PACKED
 _DCN_STATIC_WEIGHT = 1 << 20  # Python-side only: the caller promises `weight` is constant (see _dcn_workspace)
 _DCN_WS_CACHE = {}          # id(weight) -> (weakref(weight), version, dtype, workspace)
 
@@ -292,7 +292,7 @@ class _ModulatedDeformConv2dFn(Function):
                     "dcn_forward")
         ctx.save_for_backward(xd, off32, msk32, wd)
         ctx.geom = (sh, sw, ph, pw, dh, dw, groups, deform_groups)
-        ctx.bwd_flags = flags & (1 | 32 | 64)     # FORCE_GENERIC, BWD_GENERIC_DATA, BWD_GENERIC_WEIGHT
+        ctx.bwd_flags = flags & (L.DCN_FORCE_GENERIC | L.DCN_BWD_GENERIC_DATA | L.DCN_BWD_GENERIC_WEIGHT)
         ctx.has_bias = bias is not None
         ctx.in_dtypes = (offset.dtype, mask.dtype, weight.dtype, bias.dtype if bias is not None else None)
         return out
@@ -646,7 +646,8 @@ def conv3x3_64(conv: nn.Conv2d, x, negative_slope: float = 1.0, want_sums: bool 
         bias = conv.bias.detach().to(torch.bfloat16).contiguous() if conv.bias is not None else None
         L.check(lib.eavsr_conv3x3_forward(xd.data_ptr(), packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(sums),
                                           n, 64, 64, h, w, float(negative_slope), L.BF16,
-                                          1 if (want_sums and sums_out is not None) else 0, _stream(xd)),
+                                          L.CONV_SUMS_PREZEROED if (want_sums and sums_out is not None) else 0,
+                                          _stream(xd)),
                 "conv3x3_forward")
     return (out, sums) if want_sums else out
 
@@ -675,7 +676,8 @@ def conv3x3_64_ca(conv: nn.Conv2d, skip, res, res_sums, w1, b1, w2, b2, negative
                                              w2.to(dt).contiguous().data_ptr(), b2.to(dt).contiguous().data_ptr(),
                                              y.data_ptr(), packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(sums),
                                              n, h, w, float(negative_slope), L.BF16,
-                                             1 if (want_sums and sums_out is not None) else 0, _stream(sd)),
+                                             L.CONV_SUMS_PREZEROED if (want_sums and sums_out is not None) else 0,
+                                             _stream(sd)),
                 "conv3x3_ca_forward")
     return (out, y, sums) if want_sums else (out, y)
 

@@ -286,7 +286,7 @@ def _dcn_bf16_grads(cuda, n, h, w, dg, flags, seed=21, sigma=1.5):
     return (xb, off, mask, wb, bb, g), grads
 
 
-@pytest.mark.parametrize("flags", [0, 32, 64])     # tcgen05 data+weight / generic data / generic weight
+@pytest.mark.parametrize("flags", [0, L.DCN_BWD_GENERIC_DATA, L.DCN_BWD_GENERIC_WEIGHT])   # tcgen05 both / one half generic
 @pytest.mark.parametrize("dg", [8, 16, 4, 1])
 @pytest.mark.parametrize("shape", [(2, 19, 37), (1, 40, 72)])
 def test_dcn_backward_bf16_tensor_cores(cuda, shape, dg, flags):
@@ -307,7 +307,7 @@ def test_dcn_backward_bf16_tensor_cores(cuda, shape, dg, flags):
 def test_dcn_backward_tensor_cores_match_generic_at_full_size(cuda, dg):
     """1x64x270x480 (BASELINE config 2/3 size): tcgen05 backward == generic backward."""
     _, tc = _dcn_bf16_grads(cuda, 1, 270, 480, dg, 0, seed=23, sigma=2.0)
-    _, ge = _dcn_bf16_grads(cuda, 1, 270, 480, dg, 32 | 64, seed=23, sigma=2.0)
+    _, ge = _dcn_bf16_grads(cuda, 1, 270, 480, dg, L.DCN_BWD_GENERIC_DATA | L.DCN_BWD_GENERIC_WEIGHT, seed=23, sigma=2.0)
     tol = {"x": BF16_REL, "offset": 2e-3, "mask": 2e-3, "weight": BF16_REL, "bias": BF16_REL}
     for name, a, r in zip(("x", "offset", "mask", "weight", "bias"), tc, ge):
         assert rel_err(a, r) < tol[name], (name, rel_err(a, r))

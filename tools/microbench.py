@@ -116,8 +116,9 @@ def bench_dcn():
                     sec = timeit(lambda i: _ModulatedDeformConv2dFn.apply(xs[i % k], offs[i % k], msks[i % k], wgt, bias, 1, 1, 1, 1, dg, L.DCN_FORCE_GENERIC), 3, warm=1)
                     rec(f"dcn fwd generic {dt} dg={dg} {n}x64x{h}x{w}", sec, by, fl)
                     for flags, tag in ((0, "tc (data+weight)" if dt == torch.bfloat16 else "generic"),
-                                       (32, "generic data + tc weight"), (64, "tc data + generic weight"),
-                                       (96, "generic")):
+                                       (L.DCN_BWD_GENERIC_DATA, "generic data + tc weight"),
+                                       (L.DCN_BWD_GENERIC_WEIGHT, "tc data + generic weight"),
+                                       (L.DCN_BWD_GENERIC_DATA | L.DCN_BWD_GENERIC_WEIGHT, "generic")):
                         if dt != torch.bfloat16 and flags:
                             continue
                         xg = xs[0].clone().requires_grad_()
