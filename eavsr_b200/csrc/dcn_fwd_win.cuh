@@ -1,4 +1,4 @@
-// Third-generation tcgen05 DCNv2 forward (bf16 features, deform_groups <= 8): the gather reads a
+// Third-generation tcgen05 DCNv2 forward (bf16 features, deform_groups 1..16): the gather reads a
 // shared-memory WINDOW of x instead of going through L1.
 //
 // Why (ncu, profiles/r1_dcn_fwd_ws_ncu.txt): with per-group offsets every lane of a gather request
@@ -9,14 +9,16 @@
 // chunks, i.e. 8 distinct 16-byte bank groups whatever pixels they hit -> conflict-free LDS.128.
 //
 //   * tile = 8 x 16 output pixels (M = 128); window = the tile plus a 5-pixel apron (18 x 26 pixels,
-//     58.5 KB), double buffered, filled by one lane with cp.async.bulk row copies (TMA engine) for the
-//     NEXT tile while this one is gathered.  Out-of-image rows/columns are never loaded: corners
-//     outside the image have weight 0 and their clamped address is inside the loaded part.
-//   * a sample whose four corners are not all inside the window (|offset| > ~3 px) falls back to the
-//     global-memory gather of the previous kernel -- correct for any offset, fast for real ones.
-//   * 16 producer warps (2 items per thread per tap) + 1 MMA/loader warp; bf16x2 HFMA2 blend
-//     (template BLEND16) or fp32 blend; per-warp cp.async staging of offsets/masks; A ring of 2
-//     stages; per-tap weight tiles through a 3-stage bulk-copy ring; 2 TMEM accumulators.
+//     58.5 KB; 4 pixels for deform_groups = 16 and the fused-offset variant), double buffered, filled by
+//     one elected lane with cp.async.bulk row copies (TMA engine) for the NEXT tile while this one is
+//     gathered.  Out-of-image cells are zeroed once per border tile, so an outside corner reads 0 -- DCNv2's
+//     zero padding and its "p <= -1 or p >= size -> 0" rule at once, without per-corner tests.
+//   * a sample whose four corners are not all inside the window (|offset| > ~4 px) falls back to a
+//     global-memory gather with explicit validity -- correct for any offset, fast for real ones.
+//   * 16 producer warps (2 items per thread and tap, advanced in lock step) + 1 MMA / loader warp;
+//     bf16x2 HFMA2 blend (template BLEND16) or fp32 blend; per-warp cp.async staging of the offset / mask
+//     planes (3-deep ring), or -- AFF -- of the raw affine block once per tile; A ring of 3 stages; per-tap
+//     weight tiles through a 2-stage bulk-copy ring refilled behind the queued MMAs; 2 TMEM accumulators.
 #pragma once
 #include "common.cuh"
 
