@@ -352,3 +352,39 @@ def test_launch_counter_counts_native_kernels(cuda):
     x, flow = warp_inputs(1, 64, 8, 8)
     E.flow_warp(_cl(x.to(cuda)), flow.to(cuda))
     assert L.launch_count() == before + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full sizes (no oracle needed)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(cuda):
+    """1x64x270x480 (configs 2-4): DCNv2 is linear in x for fixed offsets / masks; a zero flow is the
+    identity; the centre displacement of corr(f, f) is mean_c f^2 and corr is symmetric under swapping the
+    arguments and negating the displacement (interior pixels)."""
+    g = torch.Generator().manual_seed(71)
+    h, w = 270, 480
+    x1, off, mask, wgt, _ = dcn_inputs(1, 64, h, w, 64, 8, seed=72)
+    x2 = torch.randn(1, 64, h, w, generator=g)
+    a, b = 0.75, -1.25
+    args = (off.to(cuda), mask.to(cuda), wgt.to(cuda), None, 1, 1, 1, 1, 8)
+    with torch.no_grad():
+        f = lambda t: E.modulated_deform_conv2d(_cl(t.to(cuda)), *args)       # noqa: E731
+        lhs = f(a * x1 + b * x2)
+        rhs = a * f(x1) + b * f(x2)
+    assert max_err(lhs, rhs) < 2e-4 * max(1.0, rhs.abs().max().item())
+    xb = _cl(x1.bfloat16().to(cuda))
+    zero = torch.zeros(1, 2, h, w, device=cuda)
+    assert torch.equal(E.flow_warp(xb, zero), xb)
+    assert torch.equal(E.flow_warp(_cl(x1.to(cuda)), zero), _cl(x1.to(cuda)))
+    fa = torch.randn(2, 32, 80, 128, generator=g).to(cuda)
+    fb = torch.randn(2, 32, 80, 128, generator=g).to(cuda)
+    c_aa = E.FunctionCorrelation(tenFirst=fa, tenSecond=fa)
+    assert max_err(c_aa[:, 40], fa.pow(2).mean(1)) < 1e-5
+    c_ab = E.FunctionCorrelation(tenFirst=fa, tenSecond=fb)
+    c_ba = E.FunctionCorrelation(tenFirst=fb, tenSecond=fa)
+    # c_ab[k(dy,dx)][y,x] == c_ba[k(-dy,-dx)][y+dy,x+dx]
+    for dy, dx in ((1, -2), (-4, 4), (3, 0)):
+        k, kn = (dy + 4) * 9 + (dx + 4), (-dy + 4) * 9 + (-dx + 4)
+        lhs = c_ab[:, k, 8:-8, 8:-8]
+        rhs = c_ba[:, kn, 8 + dy:c_ba.shape[2] - 8 + dy, 8 + dx:c_ba.shape[3] - 8 + dx]
+        assert max_err(lhs, rhs) < 1e-5
