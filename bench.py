@@ -438,10 +438,20 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner to STDOUT when the communicator is created (NCCL_DEBUG >= VERSION in
+        # this image): send fd 1 to stderr until the first collective is through, so that stdout carries the
+        # one JSON line and nothing else
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     peaks = load_peaks()
     T_FRAMES = args.frames
