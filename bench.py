@@ -157,39 +157,54 @@ class HotpathWorkload:
         return None
 
 
+NUM_CLIPS = 64      # BASELINE.json config 4: 64 synthetic 30-frame clips sharded over the GPUs
+
+
 class ModelWorkload:
-    """Full EAVSR+ x4 forward of one synthetic 30-frame 270x480 clip per step (BASELINE.json config 3).
+    """Full EAVSR+ x4 forward of one synthetic 30-frame 270x480 clip per step and GPU (BASELINE.json configs 3
+    and 4).  The clip set is the 64 seeded clips of config 4 (`clip_inputs(seed=1234 + clip_id)`), sharded
+    round-robin over the ranks by `eavsr_b200.clip_parallel.shard`; every step takes the next clip of this
+    rank's shard (already resident in HBM for `step`, in pinned host memory for `e2e_step`).
     Seeded weights (all checkpoints are stripped from the reference), bf16 channels_last features,
     fp32 flows/offsets/masks; the clip is replicate-padded 270 -> 272 and the SR cropped back to
     1080x1920.  The forward is captured once into a CUDA graph (the reference issues
     ~20k launches per clip from one Python thread) and replayed per step."""
     name = "eavsrp_x4_full_clip_30x270x480_bf16"
 
-    def __init__(self, device, t=T_FRAMES, h=LR_H, w=LR_W, dtype=torch.bfloat16, graph=True):
+    def __init__(self, device, t=T_FRAMES, h=LR_H, w=LR_W, dtype=torch.bfloat16, graph=True, rank=0, world=1,
+                 distinct=8, clips_per_step=1):
+        from eavsr_b200.clip_parallel import shard
         from eavsr_b200.model import EAVSRP, pad_clip
         from eavsr_b200.synthetic import clip_inputs, seeded_parameters
-        self.device, self.t, self.h, self.w = device, t, h, w
+        self.device, self.t, self.h, self.w, self.cps = device, t, h, w, clips_per_step
         net = EAVSRP(4).eval()
         seeded_parameters(net)
         self.net = net.to(device).prepare(dtype)
-        clip = clip_inputs(1, t, h, w, seed=1234)
-        self.host_clip = clip.pin_memory()
         self.pad = lambda x: pad_clip(x, 4)
-        self.static_in = self.pad(clip.to(device))
-        self.frames_per_step = t
-        self.h2d_bytes = clip.numel() * 4
-        self.host_out = torch.empty((1, t, 3, 4 * h, 4 * w), dtype=torch.uint8).pin_memory()
+        # this rank's clips of the 64-clip set; `distinct` of them are materialised (47 MB each on the device)
+        self.clip_ids = shard(NUM_CLIPS, rank, world)[:max(1, distinct) * clips_per_step]
+        self.host_clips, self.dev_clips = [], []
+        for j in range(0, len(self.clip_ids), clips_per_step):
+            c = torch.cat([clip_inputs(1, t, h, w, seed=1234 + i) for i in self.clip_ids[j:j + clips_per_step]])
+            self.host_clips.append(c.pin_memory())
+            self.dev_clips.append(self.pad(c.to(device)))
+        self.cursor = self.e2e_cursor = 0
+        self.static_in = self.dev_clips[0].clone()
+        self.frames_per_step = t * clips_per_step
+        self.h2d_bytes = self.host_clips[0].numel() * 4
+        self.host_out = torch.empty((clips_per_step, t, 3, 4 * h, 4 * w), dtype=torch.uint8).pin_memory()
         self.d2h_bytes = self.host_out.numel()
         self.graph = None
         self.launches_per_step = None
         self.use_graph = graph and os.environ.get("EAVSR_BENCH_GRAPH", "1") == "1"
         self.out = None
+        self.last_clip = 0
 
     def _forward(self):
         sr = self.net(self.static_in)
         return sr[..., : 4 * self.h, : 4 * self.w]
 
-    def step(self):
+    def _replay(self):
         from eavsr_b200 import _lib
         if not self.use_graph:
             self.out = self._forward()
@@ -210,22 +225,70 @@ class ModelWorkload:
         self.graph.replay()
         return self.out
 
+    def step(self):
+        """Device-resident clip -> SR (device).  The 47 MB device-to-device copy into the graph's input
+        buffer is part of the step."""
+        self.last_clip = self.cursor % len(self.dev_clips)
+        self.cursor += 1
+        self.static_in.copy_(self.dev_clips[self.last_clip])
+        return self._replay()
+
     def e2e_step(self):
         """Host clip in (pinned) -> H2D -> forward -> clamp*255 round (the reference's visuals,
         models/base_model.py:146-150) -> D2H uint8 frames."""
-        self.static_in.copy_(self.pad(self.host_clip.to(self.device, non_blocking=True)))
-        sr = self.step()
+        self.last_clip = self.e2e_cursor % len(self.host_clips)
+        self.e2e_cursor += 1
+        self.static_in.copy_(self.pad(self.host_clips[self.last_clip].to(self.device, non_blocking=True)))
+        sr = self._replay()
         vis = torch.clamp(sr.float() * 255, 0, 255).round().to(torch.uint8)
         self.host_out.copy_(vis, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.host_out
 
+    def parity(self):
+        """What the timed path computes against the fp32 path of the same kernels (itself pinned to the
+        reference's golden vectors at 64x64 and to the CPU oracle, tests/test_gpu_model.py), on the LAST
+        TIMED CLIP, outside the timed region.  Errors are reported on the SR frames ([0,1] range; north_star
+        bound 1e-2 for bf16), on the learned residual sr - bilinear(lr) -- the part the network actually
+        computes -- and as the PSNR delta against the synthetic HR (bicubic x4 of the clip)."""
+        import copy
+        import torch.nn.functional as F
+        self.static_in.copy_(self.dev_clips[self.last_clip])
+        sr16 = self._replay().float().clone()
+        lr = self.dev_clips[self.last_clip][..., : self.h, : self.w]
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            net32 = copy.deepcopy(self.net).float()
+            net32.prepare(torch.float32)
+            # the bf16 weights are the weights: the fp32 path runs on their exact values
+            sr32 = net32(self.dev_clips[self.last_clip])[..., : 4 * self.h, : 4 * self.w].float()
+            del net32
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        n, t = lr.shape[:2]
+        flat = lr.reshape(n * t, 3, self.h, self.w).float()
+        base = F.interpolate(flat, scale_factor=4, mode="bilinear", align_corners=False).view_as(sr32)
+        hr = F.interpolate(flat, scale_factor=4, mode="bicubic", align_corners=False).clamp(0, 1).view_as(sr32)
+        r16, r32 = sr16 - base, sr32 - base
+        vis = lambda x: torch.clamp(x * 255, 0, 255).round()                              # noqa: E731
+        psnr = lambda a: (-10 * torch.log10(((vis(a) - vis(hr)) / 255).pow(2).mean())).item()   # noqa: E731
+        rms32 = r32.pow(2).mean().sqrt().item()
+        return {"against": "fp32 path of the same kernels on the timed clip (golden-pinned in tests/test_gpu_model.py)",
+                "clip_id": int(self.clip_ids[self.last_clip * self.cps]),
+                "sr_max_abs": round((sr16 - sr32).abs().max().item(), 6), "sr_max_abs_bound": 1e-2,
+                "residual_rms": round(rms32, 6),
+                "residual_rel_rms": round((r16 - r32).pow(2).mean().sqrt().item() / max(rms32, 1e-12), 5),
+                "psnr_delta_db": round(abs(psnr(sr16) - psnr(sr32)), 5), "psnr_delta_bound_db": 0.01}
 
-def make_workload(name, device):
+
+def make_workload(name, device, rank=0, world=1, args=None):
     if name == "hotpath":
         return HotpathWorkload(device, t=T_FRAMES)
     if name == "model":
-        return ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W)
+        distinct = min(NUM_CLIPS // world, (args.steps + args.warmup) if args else 8, 16)
+        return ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W, rank=rank, world=world, distinct=distinct,
+                             clips_per_step=args.clips_per_step if args else 1)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -387,25 +450,48 @@ def cpu_hotpath_frames_per_s(budget_s=20.0):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU path for the same workload (oracle port: the reference is
+    Python + mmcv + cupy and /root/reference does not travel) on all host threads.  One step = the complete x4
+    forward of a 6-frame clip at the stated 272x480 geometry (~70 s on 16 cores); as many of the requested
+    steps as fit ~4 minutes are run and `steps` reports the number actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "model":
         from oracle import eavsrp_cpu as R
-        torch.set_num_threads(os.cpu_count() or 1)
-        fps, sample = R.time_model_sample(budget_s=60.0)
-        name = ModelWorkload.name
+        sd = R._seeded_state_dict()
+        t_s, hs, ws, est = R.plan_sample(120.0, PAD_H, LR_W, sd, frames=(6, 4, 3))
+        steps = max(1, min(args.steps, int(240.0 // max(est, 1.0))))
+        secs = [R.time_clip_forward(t_s, hs, ws, sd, seed=1234 + i) for i in range(steps)]
+        el = sum(secs) / len(secs)
+        fps = t_s / el * (hs * ws) / (PAD_H * LR_W)
+        geo = f"{hs}x{ws}" + ("" if (hs, ws) == (PAD_H, LR_W) else f" (extrapolated by LR pixels to {PAD_H}x{LR_W})")
+        sample = (f"{steps} step(s) of {args.steps} requested; a step = full x4 forward of a {t_s}-frame {geo} clip "
+                  f"({el:.1f} s) on {torch.get_num_threads()} threads, fp32, ATen grid_sample + torchvision CPU DCNv2; "
+                  f"no warm-up steps beyond a 3x64x96 probe clip; frames/s of the short clip (the 30-frame clip of the "
+                  f"metric does 1.9 alignments per frame against {(2 * t_s - 3) / t_s:.1f} here: favours the CPU)")
+        name, ms = ModelWorkload.name, el * 1e3
     else:
-        fps, sample = cpu_hotpath_frames_per_s(20.0 * max(1, args.steps))
-        name = HotpathWorkload.name
+        fps, sample = cpu_hotpath_frames_per_s(20.0 * max(1, min(args.steps, 6)))
+        name, ms, steps = HotpathWorkload.name, None, args.steps
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "steps": steps, "steps_requested": args.steps, "warmup": 0, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "clip": f"{T_FRAMES}x3x{LR_H}x{LR_W}"},
+            "config": bench_config(name, world),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def bench_config(workload, world, clips_per_gpu_step=1):
+    """The `config` object of the JSON line -- identical for both arms (`--impl reference` times the same
+    workload on the host cores)."""
+    return {"workload": workload, "clip": f"{T_FRAMES}x3x{LR_H}x{LR_W}", "clips_per_step": world * clips_per_gpu_step,
+            "parallelism": f"clip-parallel x{world} (no collective)",
+            "l2": "working set per step >> 126 MB L2 (a different HBM-resident clip every step)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -420,6 +506,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per clip (profiling runs only; default 30)")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--clips-per-step", type=int, default=1,
+                    help="clips batched into one forward per GPU (config 4 gives every GPU 8+ clips); default 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -455,7 +544,7 @@ def main():
 
     peaks = load_peaks()
     T_FRAMES = args.frames
-    wl = make_workload(args.workload, device)
+    wl = make_workload(args.workload, device, rank, world, args)
 
     def barrier():
         if world > 1:
@@ -510,6 +599,12 @@ def main():
             e2e = {"value": round(world * wl.frames_per_step * args.steps / (ems / 1e3), 3), "unit": "frames/s",
                    "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes}
 
+        parity = None
+        if rank == 0 and not args.no_parity and hasattr(wl, "parity"):
+            try:
+                parity = wl.parity()
+            except Exception as exc:   # reported, never a reason to lose the bench line
+                parity = {"failed": repr(exc)}
         roof = dcn_roofline(device, peaks) if (rank == 0 and not args.no_roofline) else None
 
     cpu = None
@@ -518,7 +613,7 @@ def main():
             if args.workload == "model":
                 from oracle import eavsrp_cpu as R
                 torch.set_num_threads(os.cpu_count() or 1)
-                fps, sample = R.time_model_sample(budget_s=25.0)
+                fps, sample, _, _ = R.time_model_sample(budget_s=40.0, h=PAD_H, w=LR_W, frames=(3,))
             else:
                 fps, sample = cpu_hotpath_frames_per_s(15.0)
             cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -533,11 +628,11 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": wl.name, "clip": f"{T_FRAMES}x3x{LR_H}x{LR_W}",
-                           "clips_per_step": world, "parallelism": f"clip-parallel x{world} (no collective)",
-                           "l2": "working set per step >> 126 MB L2 (rotating HBM-resident buffers)"},
+                "config": bench_config(wl.name, world, getattr(wl, "cps", 1)),
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "parity": parity,
+                "clips": {"set": NUM_CLIPS, "seeds": "1234 + clip_id", "this_run_per_rank": len(getattr(wl, "dev_clips", [])),
+                          "sharding": "clip i -> rank i mod N (eavsr_b200.clip_parallel.shard)"}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -8,12 +8,15 @@ from .ops import (  # noqa: F401
     FunctionCorrelation,
     ModuleCorrelation,
     ModulatedDeformConv2d,
+    backwarp,
     dcn_affine,
     dcn_affine_eligible,
     dcn_uses_tensor_cores,
     flow_warp,
     flow_warp_nhw2,
+    get_backwarp,
+    invalidate_caches,
     modulated_deform_conv2d,
 )
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

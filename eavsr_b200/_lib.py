@@ -44,6 +44,9 @@ _SIGNATURES = {
                                          c_int, c_int, c_int, c_int, c_void_p]),
     "eavsr_flow_warp2_forward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, c_int, c_void_p, _P64, c_void_p, _P64] +
                                  [c_int] * 6 + [c_void_p]),
+    "eavsr_backwarp_forward": (c_int, [c_void_p, _P64, _PF, c_void_p, _P64, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "eavsr_backwarp_backward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, _PF, _P64, _PF] + [c_int] * 5 +
+                                [c_void_p]),
     "eavsr_dcn_forward_workspace": (c_size_t, [c_int] * 7),
     "eavsr_dcn_forward_uses_tensor_cores": (c_int, [_P64, _P64] + [c_int] * 12 + [c_uint]),
     "eavsr_dcn_forward": (c_int, [c_void_p, _P64, _PF, _PF, c_void_p, c_void_p, c_void_p, _P64] + [c_int] * 16 +

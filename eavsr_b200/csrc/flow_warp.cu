@@ -71,6 +71,10 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flow, int la
     fx = f.x;
     fy = f.y;
   }
+  // the reference normalises with 2 / max(size - 1, 1) (models/networks.py:728-729) and grid_sample maps back
+  // with (size - 1) / 2: along a size-1 dimension the sample coordinate is 0 whatever the flow says
+  if (W == 1) fx = 0.f;
+  if (H == 1) fy = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -83,6 +87,10 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flow, int la
 // weights ONCE; phase 2 walks the patch 32/CPP pixels at a time, lane <-> (pixel, 16-byte chunk),
 // fetching those 7 values with warp shuffles.  Loads are unconditional (out-of-image corners read
 // a clamped in-image address with weight 0), offsets are 32-bit.  CTA = 4 warps = an 8x16 tile.
+// Two documented divergences from F.grid_sample, both outside anything EAVSR produces: (i) an Inf / NaN
+// feature value next to the image border can reach an out-of-image corner's load (0 * Inf = NaN) where
+// grid_sample never reads it -- the general kernels below select per corner instead; (ii) a NaN flow is
+// clamped to the out-of-image sentinel and yields 0 (ATen's float->int cast of NaN is undefined).
 // ------------------------------------------------------------------------------------------
 constexpr int LEAN_THREADS = 128;
 
@@ -284,8 +292,8 @@ flow_warp_bwd_nhwc(const T* __restrict__ gout, const T* __restrict__ x, const fl
           dfx += g[j] * ((v[1][j] - v[0][j]) * (1.f - c.ly) + (v[3][j] - v[2][j]) * c.ly);
           dfy += g[j] * ((v[2][j] - v[0][j]) * (1.f - c.lx) + (v[3][j] - v[1][j]) * c.lx);
         }
-        dfx *= c.gxm;
-        dfy *= c.gym;
+        dfx *= (W == 1) ? 0.f : c.gxm;
+        dfy *= (H == 1) ? 0.f : c.gym;
       }
     }
     if (gflow) {
@@ -378,8 +386,8 @@ flow_warp_bwd_strided(const T* __restrict__ gout, Strides4 gs, const T* __restri
     dfy += g * ((v[2] - v[0]) * (1.f - c.lx) + (v[3] - v[1]) * c.lx);
   }
   if (gflow) {
-    dfx *= c.gxm;
-    dfy *= c.gym;
+    dfx *= (W == 1) ? 0.f : c.gxm;
+    dfy *= (H == 1) ? 0.f : c.gym;
     if (layout == EAVSR_FLOW_N2HW) {
       size_t b = ((size_t)n * 2) * H * W + (size_t)y * W + xq;
       gflow[b] = dfx;
@@ -387,6 +395,87 @@ flow_warp_bwd_strided(const T* __restrict__ gout, Strides4 gs, const T* __restri
     } else {
       reinterpret_cast<float2*>(gflow)[((size_t)n * H + y) * W + xq] = make_float2(dfx, dfy);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backwarp: BaseModel.backwarp / get_backwarp (models/base_model.py:321-354) and
+// PWCNET.Decoder.backwarp (models/pwc_net.py:184-207).  The reference appends a ones channel,
+// calls grid_sample(align_corners=False, zeros) on a cached grid + flow / ((size-1)/2) and thresholds
+// the warped ones (> 0.999) into a validity mask that multiplies the result.  Un-normalising that grid
+// gives the sample point (y + fy*H/(H-1), x + fx*W/(W-1)); the warped ones channel is the sum of the
+// in-image bilinear weights, so no ones channel, no grid and no cat ever exist here.
+// One thread per pixel, channel loop over arbitrary strides (the callers are NCHW fp32: 3-channel HR
+// frames and PWC pyramid features).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+backwarp_fwd_kernel(const T* __restrict__ x, Strides4 xs, const float* __restrict__ flow, T* __restrict__ out,
+                    Strides4 os, T* __restrict__ mask, int N, int C, int H, int W, float ky, float kx) {
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  int xq = (int)(pix % W);
+  int y = (int)((pix / W) % H);
+  int n = (int)(pix / ((long long)W * H));
+  float fx, fy;
+  load_flow(flow, EAVSR_FLOW_N2HW, n, y, xq, H, W, fx, fy);
+  Corner c = make_corner<EAVSR_PAD_ZEROS>((float)y + fy * ky, (float)xq + fx * kx, H, W);
+  const float ones = c.wgt[0] + c.wgt[1] + c.wgt[2] + c.wgt[3];
+  const float m = ones > 0.999f ? 1.f : 0.f;
+  if (mask) mask[pix] = from_f32<T>(m);
+  const T* xn = x + n * xs.n;
+  long long o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = (long long)(c.off[k] / W) * xs.h + (long long)(c.off[k] % W) * xs.w;
+  T* op = out + n * os.n + y * os.h + xq * os.w;
+  for (int ch = 0; ch < C; ++ch) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c.ok[k]) r += c.wgt[k] * to_f32<T>(xn[o[k] + ch * xs.c]);
+    op[ch * os.c] = from_f32<T>(r * m);
+  }
+}
+
+// Gradient of out = warp(x) * mask wrt x (scatter into the zero-filled fp32 gx32) and wrt flow.  The mask
+// is piecewise constant (the reference overwrites it in place with 0 / 1), so it carries no gradient.
+template <typename T>
+__global__ void __launch_bounds__(256)
+backwarp_bwd_kernel(const T* __restrict__ gout, Strides4 gs, const T* __restrict__ x, Strides4 xs,
+                    const float* __restrict__ flow, float* __restrict__ gx32, Strides4 gxs,
+                    float* __restrict__ gflow, int N, int C, int H, int W, float ky, float kx) {
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  int xq = (int)(pix % W);
+  int y = (int)((pix / W) % H);
+  int n = (int)(pix / ((long long)W * H));
+  float fx, fy;
+  load_flow(flow, EAVSR_FLOW_N2HW, n, y, xq, H, W, fx, fy);
+  Corner c = make_corner<EAVSR_PAD_ZEROS>((float)y + fy * ky, (float)xq + fx * kx, H, W);
+  const float ones = c.wgt[0] + c.wgt[1] + c.wgt[2] + c.wgt[3];
+  const float m = ones > 0.999f ? 1.f : 0.f;
+  const T* xn = x + n * xs.n;
+  const T* gp = gout + n * gs.n + y * gs.h + xq * gs.w;
+  float dfx = 0.f, dfy = 0.f;
+  if (m != 0.f) {
+    for (int ch = 0; ch < C; ++ch) {
+      float g = to_f32<T>(gp[ch * gs.c]);
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int cy = c.off[k] / W, cx = c.off[k] % W;
+        v[k] = c.ok[k] ? to_f32<T>(xn[(long long)cy * xs.h + (long long)cx * xs.w + ch * xs.c]) : 0.f;
+        if (gx32 && c.ok[k])
+          atomicAdd(gx32 + n * gxs.n + (long long)cy * gxs.h + (long long)cx * gxs.w + ch * gxs.c, c.wgt[k] * g);
+      }
+      dfx += g * ((v[1] - v[0]) * (1.f - c.ly) + (v[3] - v[2]) * c.ly);
+      dfy += g * ((v[2] - v[0]) * (1.f - c.lx) + (v[3] - v[1]) * c.lx);
+    }
+  }
+  if (gflow) {
+    size_t b = ((size_t)n * 2) * H * W + (size_t)y * W + xq;
+    gflow[b] = dfx * kx;
+    gflow[b + (size_t)H * W] = dfy * ky;
   }
 }
 
@@ -561,4 +650,54 @@ extern "C" int eavsr_flow_warp2_forward(const void* x1, const int64_t x1_strides
         (const T*)x1, flow, (T*)out1, h, w, flow_layout, tx, ty, x1_strides[0], out1_strides[0], (const T*)x2, (T*)out2,
         x2_strides[0], out2_strides[0]);
   return check_launch("flow_warp2_forward");
+}
+
+extern "C" int eavsr_backwarp_forward(const void* x, const int64_t x_strides[4], const float* flow, void* out,
+                                      const int64_t out_strides[4], void* mask, int n, int c, int h, int w,
+                                      int dtype, void* stream) {
+  EAVSR_REQUIRE(x && flow && out && x_strides && out_strides, "backwarp_forward: null pointer");
+  EAVSR_REQUIRE(n > 0 && c > 0, "backwarp_forward: empty tensor (n=%d c=%d)", n, c);
+  EAVSR_REQUIRE(h > 1 && w > 1, "backwarp_forward: h and w must be > 1 (the reference divides by (size-1)/2), got %dx%d", h, w);
+  EAVSR_REQUIRE((long long)h * w < (1ll << 31), "backwarp_forward: image too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float ky = (float)h / (float)(h - 1), kx = (float)w / (float)(w - 1);
+  Strides4 a{x_strides[0], x_strides[1], x_strides[2], x_strides[3]};
+  Strides4 b{out_strides[0], out_strides[1], out_strides[2], out_strides[3]};
+  const long long blocks = ((long long)n * h * w + 255) / 256;
+  if (dtype == EAVSR_F32)
+    backwarp_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, a, flow, (float*)out, b, (float*)mask,
+                                                                 n, c, h, w, ky, kx);
+  else if (dtype == EAVSR_BF16)
+    backwarp_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)x, a, flow, (__nv_bfloat16*)out, b, (__nv_bfloat16*)mask, n, c, h, w, ky, kx);
+  else { set_error("backwarp_forward: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("backwarp_forward");
+}
+
+extern "C" int eavsr_backwarp_backward(const void* gout, const int64_t gout_strides[4], const void* x,
+                                       const int64_t x_strides[4], const float* flow, float* gx32,
+                                       const int64_t gx_strides[4], float* gflow, int n, int c, int h, int w,
+                                       int dtype, void* stream) {
+  EAVSR_REQUIRE(gout && x && flow && gout_strides && x_strides, "backwarp_backward: null pointer");
+  EAVSR_REQUIRE(!gx32 || gx_strides, "backwarp_backward: gx32 without strides");
+  EAVSR_REQUIRE(n > 0 && c > 0 && h > 1 && w > 1, "backwarp_backward: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!gx32 && !gflow) return EAVSR_OK;
+  if (gx32) {
+    cudaError_t e = cudaMemsetAsync(gx32, 0, strided_extent(gx_strides, n, c, h, w) * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("backwarp_backward: memset: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  }
+  const float ky = (float)h / (float)(h - 1), kx = (float)w / (float)(w - 1);
+  Strides4 a{gout_strides[0], gout_strides[1], gout_strides[2], gout_strides[3]};
+  Strides4 b{x_strides[0], x_strides[1], x_strides[2], x_strides[3]}, g{0, 0, 0, 0};
+  if (gx32) g = Strides4{gx_strides[0], gx_strides[1], gx_strides[2], gx_strides[3]};
+  const long long blocks = ((long long)n * h * w + 255) / 256;
+  if (dtype == EAVSR_F32)
+    backwarp_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)gout, a, (const float*)x, b, flow, gx32,
+                                                                 g, gflow, n, c, h, w, ky, kx);
+  else if (dtype == EAVSR_BF16)
+    backwarp_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)gout, a, (const __nv_bfloat16*)x, b, flow, gx32, g, gflow, n, c, h, w, ky, kx);
+  else { set_error("backwarp_backward: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("backwarp_backward");
 }

@@ -29,7 +29,7 @@ import torch.nn as nn
 
 from . import ops
 
-__all__ = ["install", "rebind_flow_warp", "uninstall"]
+__all__ = ["install", "rebind_flow_warp", "rebind_backwarp", "uninstall"]
 
 _installed: dict = {}
 
@@ -119,6 +119,33 @@ def rebind_flow_warp() -> list:
         if mod is not None and hasattr(mod, "flow_warp"):
             mod.flow_warp = fn
             done.append(name)
+    return done
+
+
+def rebind_backwarp(model=None) -> list:
+    """Point the reference's train-time backwarp helpers at the CUDA op:
+    ``BaseModel.get_backwarp`` (models/base_model.py:344-354; the flow-estimation branch is kept) on the
+    class, and -- because ``Decoder`` is a class local to ``PWCNET.__init__`` (models/pwc_net.py:97-207) --
+    the bound ``backwarp`` of every Decoder instance below ``model``.  Returns what was patched."""
+    done = []
+    bm = sys.modules.get("models.base_model")
+    if bm is not None and hasattr(bm, "BaseModel"):
+        import torch.nn.functional as F
+
+        def get_backwarp(self, tenFirst, tenSecond, net, flow=None, scale=1):
+            if flow is None:
+                second = F.interpolate(tenSecond, scale_factor=1 / scale, mode='bilinear', align_corners=True)
+                flow = self.get_flow(tenFirst, second, net)
+                flow = F.interpolate(flow, scale_factor=scale, mode='nearest') * scale
+            return ops.get_backwarp(tenSecond, flow)
+
+        bm.BaseModel.get_backwarp = get_backwarp
+        done.append("models.base_model.BaseModel.get_backwarp")
+    if model is not None:
+        for name, m in model.named_modules():
+            if type(m).__name__ == "Decoder" and hasattr(m, "backwarp"):
+                m.backwarp = ops.backwarp
+                done.append(f"{name}.backwarp")
     return done
 
 

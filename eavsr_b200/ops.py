@@ -23,6 +23,7 @@ from __future__ import annotations
 import math
 from typing import Optional, Tuple, Union
 
+import threading
 import weakref
 
 import torch
@@ -35,6 +36,7 @@ from . import _lib as L
 
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
+    "backwarp", "get_backwarp", "invalidate_caches",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
@@ -196,6 +198,70 @@ def flow_warp2(x1, x2, flow, padding_mode='zeros'):
 
 
 # ------------------------------------------------------------------------------------------
+# backwarp (train-time PWC-Net path)
+# ------------------------------------------------------------------------------------------
+class _BackwarpFn(Function):
+    @staticmethod
+    def forward(ctx, x, flow):
+        lib = L.load()
+        with torch.cuda.device(x.device):
+            xd = _dense(x)
+            flow32 = flow.detach().to(torch.float32).contiguous()
+            n, c, h, w = xd.shape
+            out = _empty_like_layout(xd)
+            mask = torch.empty((n, 1, h, w), dtype=xd.dtype, device=xd.device)
+            L.check(lib.eavsr_backwarp_forward(xd.data_ptr(), _strides(xd), flow32.data_ptr(), out.data_ptr(),
+                                               _strides(out), mask.data_ptr(), n, c, h, w,
+                                               _dtype_code("backwarp", xd), _stream(xd)), "backwarp_forward")
+        ctx.save_for_backward(xd, flow32)
+        ctx.flow_dtype = flow.dtype
+        ctx.mark_non_differentiable(mask)
+        return out, mask
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, _gmask):
+        xd, flow32 = ctx.saved_tensors
+        lib = L.load()
+        need_x, need_f = ctx.needs_input_grad
+        gx32 = gflow = None
+        with torch.cuda.device(xd.device):
+            g = _dense(gout.to(xd.dtype))
+            if need_x:
+                gx32 = _empty_like_layout(xd, dtype=torch.float32)
+            if need_f:
+                gflow = torch.empty_like(flow32)
+            n, c, h, w = xd.shape
+            L.check(lib.eavsr_backwarp_backward(g.data_ptr(), _strides(g), xd.data_ptr(), _strides(xd),
+                                                flow32.data_ptr(), _ptr(gx32),
+                                                _strides(gx32) if gx32 is not None else None, _ptr(gflow), n, c, h, w,
+                                                _dtype_code("backwarp", xd), _stream(xd)), "backwarp_backward")
+        return (gx32.to(xd.dtype) if gx32 is not None else None,
+                gflow.to(ctx.flow_dtype) if gflow is not None else None)
+
+
+def _backwarp(name, tenInput, tenFlow):
+    _require_cuda(name, tenInput, tenFlow)
+    if tenInput.dim() != 4 or tenFlow.dim() != 4 or tenFlow.shape[1] != 2 or tenFlow.shape[0] != tenInput.shape[0] \
+            or tenFlow.shape[2:] != tenInput.shape[2:]:
+        raise ValueError(f"eavsr_b200.{name}: expected input (n,c,h,w) and flow (n,2,h,w), got "
+                         f"{tuple(tenInput.shape)} / {tuple(tenFlow.shape)}")
+    return _BackwarpFn.apply(tenInput, tenFlow)
+
+
+def backwarp(tenInput, tenFlow):
+    """Drop-in for ``PWCNET.Decoder.backwarp`` (models/pwc_net.py:184-207): bilinear warp with
+    ``align_corners=False`` semantics, multiplied by the validity mask (warped ones > 0.999)."""
+    return _backwarp("backwarp", tenInput, tenFlow)[0]
+
+
+def get_backwarp(tenSecond, flow):
+    """The ``flow is not None`` branch of ``BaseModel.get_backwarp`` (models/base_model.py:344-354):
+    returns ``(backwarp(tenSecond, flow) * mask, mask)`` with ``mask`` (n,1,h,w) in {0,1}."""
+    return _backwarp("get_backwarp", tenSecond, flow)
+
+
+# ------------------------------------------------------------------------------------------
 # DCNv2
 # ------------------------------------------------------------------------------------------
 def _dcn_prepare_x(x: torch.Tensor, weight: torch.Tensor, groups: int) -> torch.Tensor:
@@ -220,31 +286,54 @@ def dcn_uses_tensor_cores(x, weight, stride=1, padding=0, dilation=1, groups=1, 
 
 DCN_WS_PACKED = L.DCN_WS_PACKED
 _DCN_STATIC_WEIGHT = 1 << 20  # Python-side only: the caller promises `weight` is constant (see _dcn_workspace)
-_DCN_WS_CACHE = {}          # id(weight) -> (weakref(weight), version, dtype, workspace)
+_DCN_WS_CACHE = {}          # (id(weight), stream) -> (weakref(weight), version, dtype, workspace)
+_DCN_WS_LOCK = threading.Lock()   # nn.DataParallel calls the ops from one thread per GPU
 
 
 def _dcn_workspace(weight, dtype, ws_bytes, static):
     """Workspace for eavsr_dcn_forward.  Weights the caller declares constant (``static_weight=True``,
-    inference only) keep their packed
-    image: the entry is valid only while it is the same tensor object at the same version counter,
-    so an optimizer step / load_state_dict / in-place edit re-packs.  Returns (workspace, already_packed)."""
+    inference only) keep their packed image: an entry is valid only while it is the same tensor object at the
+    same version counter on the same stream (the pack kernel is ordered against later launches by stream
+    order only), so an optimizer step / load_state_dict / in-place edit re-packs; writes through ``.data``
+    do not bump the version counter -- call `invalidate_caches` after those.
+    Returns (workspace, already_packed, commit); ``commit()`` records the entry and must be called only
+    after the launch that packed the workspace succeeded."""
+    nothing = lambda: None      # noqa: E731
     if not static or (torch.is_grad_enabled() and weight.requires_grad):
-        return torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=weight.device), False
-    key = id(weight)
-    hit = _DCN_WS_CACHE.get(key)
+        return torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=weight.device), False, nothing
+    key = (id(weight), torch.cuda.current_stream(weight.device).cuda_stream)
+    with _DCN_WS_LOCK:
+        hit = _DCN_WS_CACHE.get(key)
     if hit is not None:
         ref, version, dt, ws = hit
         if ref() is weight and version == weight._version and dt == dtype and ws.numel() >= ws_bytes \
                 and ws.device == weight.device:
-            return ws, True
-    if len(_DCN_WS_CACHE) > 256:
-        for k in [k for k, v in _DCN_WS_CACHE.items() if v[0]() is None]:
-            del _DCN_WS_CACHE[k]
-        if len(_DCN_WS_CACHE) > 256:
-            _DCN_WS_CACHE.clear()
+            return ws, True, nothing
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=weight.device)
-    _DCN_WS_CACHE[key] = (weakref.ref(weight), weight._version, dtype, ws)
-    return ws, False
+
+    def commit():
+        with _DCN_WS_LOCK:
+            if len(_DCN_WS_CACHE) > 256:
+                for k in [k for k, v in _DCN_WS_CACHE.items() if v[0]() is None]:
+                    del _DCN_WS_CACHE[k]
+                if len(_DCN_WS_CACHE) > 256:
+                    _DCN_WS_CACHE.clear()
+            _DCN_WS_CACHE[key] = (weakref.ref(weight), weight._version, dtype, ws)
+    return ws, False, commit
+
+
+def invalidate_caches(module: Optional[nn.Module] = None) -> None:
+    """Drop every cached packed-weight image (DCN workspaces, tcgen05 conv3x3 tiles, merged offset-conv
+    weights).  The caches are keyed on the parameters' version counters, which writes through ``param.data``
+    (EMA swaps, ``init_weights``) do not bump: call this after such a write.  ``module``: also clear the
+    per-module entries below it."""
+    with _DCN_WS_LOCK:
+        _DCN_WS_CACHE.clear()
+    if module is not None:
+        for m in module.modules():
+            for attr in ("_eavsr_packed", "_merged", "_merged_bias"):
+                if attr in m.__dict__:
+                    del m.__dict__[attr]
 
 
 class _ModulatedDeformConv2dFn(Function):
@@ -281,7 +370,7 @@ class _ModulatedDeformConv2dFn(Function):
             bd = bias.detach().to(input.dtype).contiguous() if bias is not None else None
             out = _empty_like_layout(xd, channels=cout, hw=(ho, wo))
             ws_bytes = lib.eavsr_dcn_forward_workspace(cin, cout, kh, kw, groups, deform_groups, code)
-            ws, packed = _dcn_workspace(weight, input.dtype, ws_bytes, bool(flags & _DCN_STATIC_WEIGHT))
+            ws, packed, commit = _dcn_workspace(weight, input.dtype, ws_bytes, bool(flags & _DCN_STATIC_WEIGHT))
             flags &= ~_DCN_STATIC_WEIGHT
             if packed:
                 flags |= DCN_WS_PACKED
@@ -290,6 +379,10 @@ class _ModulatedDeformConv2dFn(Function):
                                           cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, deform_groups, code,
                                           ws.data_ptr(), ws.numel(), flags, _stream(xd)),
                     "dcn_forward")
+            if ws_bytes and lib.eavsr_dcn_forward_uses_tensor_cores(
+                    _strides(xd), _strides(out), cin, cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, deform_groups,
+                    flags):
+                commit()        # only a tensor-core launch has packed the workspace
         ctx.save_for_backward(xd, off32, msk32, wd)
         ctx.geom = (sh, sw, ph, pw, dh, dw, groups, deform_groups)
         ctx.bwd_flags = flags & (L.DCN_FORCE_GENERIC | L.DCN_BWD_GENERIC_DATA | L.DCN_BWD_GENERIC_WEIGHT)
@@ -443,12 +536,21 @@ def _b(bias, like):
     return None if bias is None else bias.detach().to(like.dtype).contiguous()
 
 
+def _as(t, dtype):
+    """Detached contiguous `dtype` view / copy of a parameter.  Keep the result in a local until the launch
+    has been issued (see adapt_mix)."""
+    return t.detach().to(dtype).contiguous()
+
+
 def fused_inference_ok(*tensors) -> bool:
-    """True when the fused (non-differentiable) kernels may be used for these tensors."""
+    """True when the fused (non-differentiable) kernels may be used: autograd is off (``torch.no_grad()`` /
+    ``inference_mode``) and every tensor is a CUDA fp32 / bf16 tensor."""
+    if torch.is_grad_enabled():
+        # the fused kernels have no backward; callers only see a subset of the parameters a fused op consumes,
+        # so "none of these requires grad" would not be a safe test (frozen encoder, trainable alignment)
+        return False
     ts = [t for t in tensors if t is not None]
     if not all(t.is_cuda for t in ts):
-        return False
-    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
         return False
     return all(t.dtype in _DTYPES for t in ts)
 
@@ -463,12 +565,14 @@ def adapt_mix(a, b, w1, b1, w2, b2, negative_slope: float = 0.2):
         ad = a.contiguous(memory_format=torch.channels_last)
         bd = b.to(a.dtype).contiguous(memory_format=torch.channels_last)
         out = torch.empty_like(ad)
-        dt = a.dtype
-        L.check(lib.eavsr_adapt_mix_forward(ad.data_ptr(), bd.data_ptr(), w1.to(dt).contiguous().data_ptr(),
-                                            b1.to(dt).contiguous().data_ptr(), w2.to(dt).contiguous().data_ptr(),
-                                            b2.to(dt).contiguous().data_ptr(), out.data_ptr(), n, c, h, w,
+        # converted parameters are bound to locals that outlive the launch: `.data_ptr()` of a temporary
+        # would be handed back to the caching allocator before the next conversion in the argument list
+        w1d, b1d, w2d, b2d = (_as(t, a.dtype) for t in (w1, b1, w2, b2))
+        L.check(lib.eavsr_adapt_mix_forward(ad.data_ptr(), bd.data_ptr(), w1d.data_ptr(), b1d.data_ptr(),
+                                            w2d.data_ptr(), b2d.data_ptr(), out.data_ptr(), n, c, h, w,
                                             float(negative_slope), _dtype_code("adapt_mix", ad), _stream(ad)),
                 "adapt_mix")
+        del w1d, b1d, w2d, b2d
     return out
 
 
@@ -488,13 +592,14 @@ def affine_offsets_mask(transform, translation, mask_logits, deform_groups: int,
         if mask_logits is not None:
             mask_logits = mask_logits.to(transform.dtype)
             mask = torch.empty((n, 9 * D, h, w), dtype=torch.float32, device=transform.device)
+        bT, bt, bm = _b(transform_bias, transform), _b(translation_bias, transform), _b(mask_bias, transform)
         L.check(lib.eavsr_affine_offsets_forward(
             transform.data_ptr(), _strides(transform), translation.data_ptr(), _strides(translation),
             _ptr(mask_logits), _strides(mask_logits) if mask_logits is not None else None,
-            _ptr(_b(transform_bias, transform)), _ptr(_b(translation_bias, transform)),
-            _ptr(_b(mask_bias, transform)), offset.data_ptr(),
+            _ptr(bT), _ptr(bt), _ptr(bm), offset.data_ptr(),
             _ptr(mask), n, D, h, w, _dtype_code("affine_offsets_mask", transform), _stream(transform)),
             "affine_offsets")
+        del bT, bt, bm
     return offset, mask
 
 
@@ -532,12 +637,13 @@ def dcn_affine(x, affine, affine_bias, weight, bias, deform_groups: int = 8, sta
             assert out.shape == xd.shape and out.dtype == xd.dtype and out.stride(1) == 1, "dcn_affine: bad out view"
         code = _dtype_code("dcn_affine", xd)
         ws_bytes = lib.eavsr_dcn_forward_workspace(64, 64, 3, 3, 1, deform_groups, code)
-        ws, packed = _dcn_workspace(weight, x.dtype, ws_bytes, static_weight)
+        ws, packed, commit = _dcn_workspace(weight, x.dtype, ws_bytes, static_weight)
         if packed:
             flags |= DCN_WS_PACKED
         L.check(lib.eavsr_dcn_affine_forward(xd.data_ptr(), _strides(xd), affine.data_ptr(), _ptr(ab), wd.data_ptr(),
                                              _ptr(bd), out.data_ptr(), _strides(out), n, h, w, deform_groups, code,
                                              ws.data_ptr(), ws.numel(), flags, _stream(xd)), "dcn_affine_forward")
+        commit()
     return out
 
 
@@ -553,14 +659,14 @@ def ca_residual(res, skip, w1, b1, w2, b2, reduction: int = 16, res_bias=None):
         sd = skip.to(res.dtype).contiguous(memory_format=torch.channels_last)
         out = torch.empty_like(rd)
         sums = torch.empty((n, c), dtype=torch.float32, device=res.device)
-        dt = res.dtype
-        L.check(lib.eavsr_ca_residual_forward(rd.data_ptr(), sd.data_ptr(), w1.to(dt).contiguous().data_ptr(),
-                                              b1.to(dt).contiguous().data_ptr(), w2.to(dt).contiguous().data_ptr(),
-                                              b2.to(dt).contiguous().data_ptr(),
-                                              _ptr(res_bias.to(dt).contiguous()) if res_bias is not None else None,
+        w1d, b1d, w2d, b2d = (_as(t, res.dtype) for t in (w1, b1, w2, b2))
+        rb = _b(res_bias, res)
+        L.check(lib.eavsr_ca_residual_forward(rd.data_ptr(), sd.data_ptr(), w1d.data_ptr(), b1d.data_ptr(),
+                                              w2d.data_ptr(), b2d.data_ptr(), _ptr(rb),
                                               out.data_ptr(), sums.data_ptr(),
                                               n, c, h, w, reduction, _dtype_code("ca_residual", rd), _stream(rd)),
                 "ca_residual")
+        del w1d, b1d, w2d, b2d, rb
     return out
 
 
@@ -573,9 +679,11 @@ def bias_act_(x, bias, negative_slope: float = 1.0):
     if not x.is_contiguous(memory_format=torch.channels_last):
         raise ValueError("bias_act_: x must be dense channels_last")
     with torch.cuda.device(x.device):
-        L.check(lib.eavsr_bias_act_forward(x.data_ptr(), bias.to(x.dtype).contiguous().data_ptr(), c, n * h * w,
+        bd = _as(bias, x.dtype)
+        L.check(lib.eavsr_bias_act_forward(x.data_ptr(), bd.data_ptr(), c, n * h * w,
                                            float(negative_slope), _dtype_code("bias_act_", x), _stream(x)),
                 "bias_act")
+        del bd
     return x
 
 
@@ -670,15 +778,15 @@ def conv3x3_64_ca(conv: nn.Conv2d, skip, res, res_sums, w1, b1, w2, b2, negative
             sums = sums_out if sums_out is not None else torch.empty((n, 64), dtype=torch.float32, device=skip.device)
         packed = _packed_conv_weight(conv, skip.device)
         bias = conv.bias.detach().to(torch.bfloat16).contiguous() if conv.bias is not None else None
-        dt = skip.dtype
+        w1d, b1d, w2d, b2d = (_as(t, skip.dtype) for t in (w1, b1, w2, b2))
         L.check(lib.eavsr_conv3x3_ca_forward(sd.data_ptr(), rd.data_ptr(), res_sums.data_ptr(),
-                                             w1.to(dt).contiguous().data_ptr(), b1.to(dt).contiguous().data_ptr(),
-                                             w2.to(dt).contiguous().data_ptr(), b2.to(dt).contiguous().data_ptr(),
+                                             w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(),
                                              y.data_ptr(), packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(sums),
                                              n, h, w, float(negative_slope), L.BF16,
                                              L.CONV_SUMS_PREZEROED if (want_sums and sums_out is not None) else 0,
                                              _stream(sd)),
                 "conv3x3_ca_forward")
+        del w1d, b1d, w2d, b2d
     return (out, y, sums) if want_sums else (out, y)
 
 
@@ -691,12 +799,13 @@ def ca_scale(res, skip, sums, w1, b1, w2, b2, reduction: int = 16, res_bias=None
         rd = res.contiguous(memory_format=torch.channels_last)
         sd = skip.to(res.dtype).contiguous(memory_format=torch.channels_last)
         out = torch.empty_like(rd)
-        dt = res.dtype
+        w1d, b1d, w2d, b2d = (_as(t, res.dtype) for t in (w1, b1, w2, b2))
+        rb = _b(res_bias, res)
         L.check(lib.eavsr_ca_scale_forward(rd.data_ptr(), sd.data_ptr(), sums.data_ptr(),
-                                           w1.to(dt).contiguous().data_ptr(), b1.to(dt).contiguous().data_ptr(),
-                                           w2.to(dt).contiguous().data_ptr(), b2.to(dt).contiguous().data_ptr(),
-                                           _ptr(_b(res_bias, res)), out.data_ptr(), n, c, h, w, reduction,
+                                           w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(),
+                                           _ptr(rb), out.data_ptr(), n, c, h, w, reduction,
                                            _dtype_code("ca_scale", rd), _stream(rd)), "ca_scale")
+        del w1d, b1d, w2d, b2d, rb
     return out
 
 
@@ -718,7 +827,9 @@ def conv2d_bias_act_shuffle(conv: nn.Conv2d, x, negative_slope: float = 1.0):
     with torch.cuda.device(x.device):
         out = torch.empty((n, cout // 4, 2 * h, 2 * w), dtype=y.dtype, device=y.device,
                           memory_format=torch.channels_last)
-        L.check(lib.eavsr_bias_act_shuffle_forward(y.data_ptr(), _ptr(_b(conv.bias, y)), out.data_ptr(), n, cout // 4,
+        bd = _b(conv.bias, y)
+        L.check(lib.eavsr_bias_act_shuffle_forward(y.data_ptr(), _ptr(bd), out.data_ptr(), n, cout // 4,
                                                    h, w, float(negative_slope), _dtype_code("bias_act_shuffle", y),
                                                    _stream(y)), "bias_act_shuffle")
+        del bd
     return out

@@ -87,6 +87,23 @@ int eavsr_flow_warp_backward(const void* gout, const int64_t gout_strides[4], co
                              const int64_t gx_strides[4], float* gflow, int n, int c, int h, int w, int dtype,
                              int padding_mode, void* stream);
 
+/* ---- backwarp ---------------------------------------------------------------------------
+ * Replaces BaseModel.backwarp + the masking of get_backwarp (models/base_model.py:321-354) and
+ * PWCNET.Decoder.backwarp (models/pwc_net.py:184-207): F.grid_sample(cat[x, ones], cached_grid +
+ * flow / ((size-1)/2), bilinear, zeros, align_corners=False), mask = warped_ones > 0.999, out = warp * mask.
+ * The sample point is (y + flow_y * H/(H-1), x + flow_x * W/(W-1)).  flow: (n,2,h,w) fp32 contiguous,
+ * channel 0 = x.  out: (n,c,h,w) `dtype` by strides; mask: (n,1,h,w) contiguous `dtype` (values 0 / 1) or
+ * NULL.  h, w must be > 1 (the reference divides by (size-1)/2). */
+int eavsr_backwarp_forward(const void* x, const int64_t x_strides[4], const float* flow, void* out,
+                           const int64_t out_strides[4], void* mask, int n, int c, int h, int w, int dtype,
+                           void* stream);
+/* Gradients of out wrt x (fp32 accumulation buffer gx32, zero-filled by the call) and wrt flow (fp32
+ * (n,2,h,w)); either may be NULL.  The mask is piecewise constant and carries no gradient. */
+int eavsr_backwarp_backward(const void* gout, const int64_t gout_strides[4], const void* x,
+                            const int64_t x_strides[4], const float* flow, float* gx32,
+                            const int64_t gx_strides[4], float* gflow, int n, int c, int h, int w, int dtype,
+                            void* stream);
+
 /* ---- modulated deformable convolution (DCNv2) --------------------------------------------
  * Replaces mmcv.ops.modulated_deform_conv2d as called at models/networks.py:627-630
  * (ext_module.modulated_deform_conv_forward / _backward of mmcv-full 1.x).

@@ -139,6 +139,12 @@ def flow_warp(x, flow, flow_layout="n2hw", padding_mode="zeros"):
         fx, fy = flow[..., 0], flow[..., 1]
     else:
         raise ValueError(flow_layout)
+    # normalisation by 2/max(size-1, 1) (networks.py:730-731) and grid_sample's (g+1)/2*(size-1): along a
+    # size-1 dimension the sample coordinate collapses to 0 whatever the flow is
+    if w == 1:
+        fx = fx * 0
+    if h == 1:
+        fy = fy * 0
     gy = torch.arange(h, dtype=x.dtype).view(1, h, 1)
     gx = torch.arange(w, dtype=x.dtype).view(1, 1, w)
     py = (gy + fy).reshape(n, h * w)

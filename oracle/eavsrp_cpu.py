@@ -160,26 +160,56 @@ def eavsrp_forward(sd, lrs, scale=4, ops_kind="restatement", dg=8, nb=30):
     return torch.stack(frames, 1)
 
 
-def time_model_sample(budget_s=25.0, h=272, w=480, t_full=30, state_dict=None):
-    """CPU baseline for the full-clip metric on a BOUNDED sample: the complete x4 forward of a short
-    clip at a reduced frame size, extrapolated by LR pixel-frames.  Returns
-    (LR frames/s at h x w, description)."""
+def _seeded_state_dict():
     from eavsr_b200.model import EAVSRP
-    from eavsr_b200.synthetic import clip_inputs, seeded_parameters
-    if state_dict is None:
-        net = EAVSRP(4)
-        seeded_parameters(net)
-        state_dict = {k: v.float() for k, v in net.state_dict().items()}
-    t_s, hs, ws = 6, 128, 192              # ~20 s on 16 cores; budget_s only guards slower hosts
-    if budget_s < 15:
-        t_s, hs, ws = 4, 64, 96
-    lrs = clip_inputs(1, t_s, hs, ws, seed=1234)
+    from eavsr_b200.synthetic import seeded_parameters
+    net = EAVSRP(4)
+    seeded_parameters(net)
+    return {k: v.float() for k, v in net.state_dict().items()}
+
+
+def time_clip_forward(t_s, h, w, state_dict=None, seed=1234):
+    """Seconds for the complete x4 forward of one `t_s`-frame h x w clip through the reference's CPU operators
+    (ATen grid_sample + torchvision CPU DCNv2 = what `--gpu_ids -1` executes), fp32, all host threads."""
+    from eavsr_b200.synthetic import clip_inputs
+    sd = state_dict or _seeded_state_dict()
+    lrs = clip_inputs(1, t_s, h, w, seed=seed)
     with torch.no_grad():
         t0 = time.time()
-        eavsrp_forward(state_dict, lrs, 4, "aten")
-        el = time.time() - t0
-    # the reference's cost is ~linear in LR pixels x frames; a T=30 clip does (2T-3)/T = 1.9
-    # alignments per frame against 1.5 at T=6, so this extrapolation slightly FAVOURS the CPU.
-    fps = 1.0 / (el / (t_s * hs * ws) * h * w)
-    return fps, (f"full x4 forward of a {t_s}-frame {hs}x{ws} clip in {el:.1f} s on {torch.get_num_threads()} threads "
-                 f"(fp32, ATen grid_sample + torchvision CPU DCNv2), extrapolated by LR pixel-frames to {h}x{w}")
+        eavsrp_forward(sd, lrs, 4, "aten")
+        return time.time() - t0
+
+
+def plan_sample(budget_s, h=272, w=480, state_dict=None, frames=(6, 4, 3)):
+    """Pick the largest sample that fits `budget_s` on this host: a tiny probe clip gives seconds per LR
+    pixel-frame; prefer the stated geometry (h x w) with as many frames as fit, fall back to a reduced frame
+    size only when even 3 frames at h x w do not fit.  Returns (t_s, hs, ws, estimated seconds)."""
+    time_clip_forward(3, 64, 64, state_dict)                   # pays the lazy initialisations (~20 s of oneDNN set-up)
+    probe = time_clip_forward(3, 64, 96, state_dict)
+    per_pxf = probe / (3 * 64 * 96) * 0.8                      # large frames thread better than the probe (measured)
+    for t_s in frames:
+        est = per_pxf * t_s * h * w
+        if est <= budget_s:
+            return t_s, h, w, est
+    hs, ws = h, w
+    while per_pxf * 3 * hs * ws > budget_s and hs > 64:
+        hs, ws = (hs // 2 + 3) // 4 * 4, (ws // 2 + 3) // 4 * 4
+    return 3, hs, ws, per_pxf * 3 * hs * ws
+
+
+def time_model_sample(budget_s=30.0, h=272, w=480, t_full=30, state_dict=None, steps=1, frames=(6, 4, 3)):
+    """CPU baseline for the full-clip metric on a BOUNDED sample: `steps` complete x4 forwards of a short clip
+    at the stated frame size (272x480) when the host is fast enough for `budget_s` per step.
+    Returns (LR frames/s at h x w, description, seconds per step list, (t_s, hs, ws))."""
+    sd = state_dict or _seeded_state_dict()
+    t_s, hs, ws, _ = plan_sample(budget_s, h, w, sd, frames)
+    secs = [time_clip_forward(t_s, hs, ws, sd, seed=1234 + i) for i in range(max(1, steps))]
+    el = sum(secs) / len(secs)
+    # a T=30 clip does (2T-3)/T = 1.9 alignments per frame against 1.5 at T=6 / 1.0 at T=3, so per-frame
+    # numbers from a short clip FAVOUR the CPU; so does the pixel extrapolation of a reduced frame
+    fps = t_s / el * (hs * ws) / (h * w)
+    geo = f"{hs}x{ws}" + ("" if (hs, ws) == (h, w) else f" (extrapolated by LR pixels to {h}x{w})")
+    what = (f"full x4 forward of a {t_s}-frame {geo} clip, {len(secs)} x {el:.1f} s on {torch.get_num_threads()} "
+            f"threads (fp32, ATen grid_sample + torchvision CPU DCNv2; frames/s of the short clip: the 30-frame clip "
+            f"of the metric costs more per frame)")
+    return fps, what, secs, (t_s, hs, ws)

@@ -60,6 +60,18 @@ def gen_flow_warp():
         save("flow_warp_" + tag, x=x, flow=flow, out=out, g=g, gx=gx, gflow=gf)
 
 
+def gen_flow_warp_size1():
+    """size-1 dimensions: the reference's 2/max(size-1,1) normalisation makes the flow irrelevant there."""
+    import models.networks as N
+    import models.eavsrp_model as M
+    out = {}
+    for tag, fn, layout, shape in (("n_row", N.flow_warp, "n2hw", (1, 4, 1, 5)), ("n_col", N.flow_warp, "n2hw", (1, 4, 6, 1)),
+                                   ("m_px", M.flow_warp, "nhw2", (2, 3, 1, 1))):
+        x, flow = warp_inputs(*shape, seed=108, sigma=0.7, layout=layout)
+        out[tag + "_x"], out[tag + "_flow"], out[tag + "_out"] = x, flow, fn(x, flow)
+    save("flow_warp_size1", **out)
+
+
 def gen_backwarp():
     from models.base_model import BaseModel
     dummy = types.SimpleNamespace(backwarp_tenGrid={}, backwarp_tenPartial={})
@@ -169,6 +181,6 @@ def gen_model():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["flow_warp", "backwarp", "dcn", "adastn", "correlation", "model"]
+    which = sys.argv[1:] or ["flow_warp", "flow_warp_size1", "backwarp", "dcn", "adastn", "correlation", "model"]
     for w in which:
         globals()["gen_" + w]()

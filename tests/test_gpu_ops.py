@@ -1,6 +1,9 @@
 """GPU parity tests: the CUDA path (through the ctypes/C-ABI binding) against the CPU oracle on
 the same seeded inputs.  Tolerances: fp32 path max-abs <= 1e-3 (BASELINE.json north_star; the
 kernels are far inside it), bf16 path relative to the output RMS."""
+import os
+
+import numpy as np
 import pytest
 import torch
 
@@ -12,6 +15,7 @@ from oracle import alignment as O
 from helpers import dcn_inputs, max_err, rel_err, smooth_flow_mask, warp_inputs
 
 pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 FP32_TOL = 1e-3     # north_star: max abs error <= 1e-3 fp32
 BF16_REL = 3e-2     # bf16 storage rounding (2^-9) relative to output RMS, worst element
@@ -92,6 +96,83 @@ def test_flow_warp_errors(cuda):
         E.flow_warp(x, torch.zeros(1, 2, 8, 8, device=cuda), padding_mode="reflection")
     with pytest.raises(NotImplementedError):
         E.flow_warp(x.cpu(), torch.zeros(1, 2, 8, 8))
+
+
+def test_flow_warp_size1_matches_reference_golden(cuda):
+    d = np.load(os.path.join(GOLD, "flow_warp_size1.npz"))
+    for tag, fn in (("n_row", E.flow_warp), ("n_col", E.flow_warp), ("m_px", E.flow_warp_nhw2)):
+        x, flow, ref = (torch.from_numpy(d[f"{tag}_{k}"]) for k in ("x", "flow", "out"))
+        xg = x.to(cuda).requires_grad_()
+        fg = flow.to(cuda).requires_grad_()
+        out = fn(xg, fg)
+        assert max_err(out, ref) < 1e-5, tag
+        out.sum().backward()
+        assert torch.isfinite(fg.grad).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# backwarp (BaseModel.get_backwarp, models/base_model.py:321-354; PWCNET.Decoder.backwarp,
+# models/pwc_net.py:184-207)
+# ---------------------------------------------------------------------------------------------
+def test_backwarp_matches_reference_golden(cuda):
+    d = np.load(os.path.join(GOLD, "backwarp.npz"))
+    x, flow, ref, mref = (torch.from_numpy(d[k]) for k in ("x", "flow", "out", "mask"))
+    out, mask = E.get_backwarp(x.to(cuda), flow.to(cuda))
+    assert mask.shape == mref.shape and torch.equal(mask.cpu(), mref)
+    assert max_err(out, ref) < 2e-4
+    assert max_err(E.backwarp(x.to(cuda), flow.to(cuda)), ref) < 2e-4
+
+
+@pytest.mark.parametrize("shape,cl,dtype", [((2, 3, 64, 48), False, torch.float32), ((1, 196, 2, 2), False, torch.float32),
+                                            ((2, 32, 16, 16), False, torch.float32), ((1, 64, 17, 23), True, torch.float32),
+                                            ((1, 3, 256, 256), False, torch.float32), ((2, 16, 12, 20), True, torch.bfloat16)])
+def test_backwarp_vs_oracle(cuda, shape, cl, dtype):
+    x, flow = warp_inputs(*shape, seed=21, sigma=1.5)
+    x = x.to(dtype)
+    ref, mref = O.backwarp(x.double(), flow.double())
+    xg = x.to(cuda)
+    xg = _cl(xg) if cl else xg
+    out, mask = E.get_backwarp(xg, flow.to(cuda))
+    assert out.dtype == dtype and out.shape == ref.shape
+    # the threshold (warped ones > 0.999) is discontinuous: compare away from it
+    py = torch.arange(shape[2]).view(1, -1, 1) + flow[:, 1].double() * shape[2] / (shape[2] - 1)
+    px = torch.arange(shape[3]).view(1, 1, -1) + flow[:, 0].double() * shape[3] / (shape[3] - 1)
+    edge = ((py.abs() < 2e-3) | ((py - (shape[2] - 1)).abs() < 2e-3) | (px.abs() < 2e-3) |
+            ((px - (shape[3] - 1)).abs() < 2e-3)).unsqueeze(1)
+    keep = (~edge).double()
+    assert keep.mean() > 0.9
+    assert ((mask.double().cpu() - mref) * keep).abs().max() == 0
+    err = ((out.double().cpu() - ref) * keep).abs().max().item()
+    assert err < (1e-4 if dtype == torch.float32 else BF16_REL * ref.pow(2).mean().sqrt().item())
+
+
+def test_backwarp_backward(cuda):
+    shape = (2, 6, 14, 18)
+    x, flow = warp_inputs(*shape, seed=22, sigma=1.5)
+    g = torch.randn(shape, generator=torch.Generator().manual_seed(23))
+    xr = x.double().requires_grad_()
+    fr = flow.double().requires_grad_()
+    ref, _ = O.backwarp(xr, fr)
+    gx_ref, gf_ref = torch.autograd.grad(ref, [xr, fr], g.double())
+    xg = x.to(cuda).requires_grad_()
+    fg = flow.to(cuda).requires_grad_()
+    out, mask = E.get_backwarp(xg, fg)
+    assert not mask.requires_grad
+    gx, gf = torch.autograd.grad(out, [xg, fg], g.to(cuda))
+    assert max_err(gx, gx_ref) < 1e-4
+    sc = torch.tensor([shape[3] / (shape[3] - 1), shape[2] / (shape[2] - 1)]).view(1, 2, 1, 1)
+    m = smooth_flow_mask(flow * sc)
+    assert max_err(gf.cpu().double() * m, gf_ref * m) < 2e-3 * max(1.0, gf_ref.abs().max().item())
+
+
+def test_backwarp_errors(cuda):
+    x = torch.zeros(1, 3, 8, 8, device=cuda)
+    with pytest.raises(ValueError):
+        E.backwarp(x, torch.zeros(1, 2, 8, 9, device=cuda))
+    with pytest.raises(NotImplementedError):
+        E.backwarp(x.cpu(), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(L.EavsrError):
+        E.backwarp(x[:, :, :1], torch.zeros(1, 2, 1, 8, device=cuda))
 
 
 # ---------------------------------------------------------------------------------------------

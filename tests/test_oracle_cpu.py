@@ -34,6 +34,13 @@ def test_flow_warp_matches_reference(tag, layout, pad):
     assert ((gf - g["gflow"]) * m).abs().max() < 2e-3 * max(1.0, g["gflow"].abs().max().item())
 
 
+def test_flow_warp_size1_matches_reference():
+    g = gold("flow_warp_size1")
+    for tag, layout in (("n_row", "n2hw"), ("n_col", "n2hw"), ("m_px", "nhw2")):
+        out = O.flow_warp(g[tag + "_x"].double(), g[tag + "_flow"].double(), layout)
+        assert (out - g[tag + "_out"]).abs().max() < 1e-5, tag
+
+
 def test_flow_warp_inputs_are_the_seeded_ones():
     g = gold("flow_warp_networks_zeros")
     x, flow = warp_inputs(2, 6, 11, 14, seed=100)
