@@ -282,7 +282,85 @@ class ModelWorkload:
                 "psnr_delta_db": round(abs(psnr(sr16) - psnr(sr32)), 5), "psnr_delta_bound_db": 0.01}
 
 
+class TrainWorkload:
+    """BASELINE config 5: one EAVSR+ x4 training step per step -- forward, L1 loss, backward through the DCNv2 /
+    flow_warp kernels, Adam with the reference's two parameter groups (eavsr_b200.train.Trainer mirrors
+    models/eavsrp_model.py:45-59,82-119) -- on 8 synthetic 15-frame 64x64 LR crops per GPU (train_x4.sh:17
+    batch_size 8, patch_size 64), data-parallel over the ranks with NCCL DistributedDataParallel: the gradient
+    all-reduce (12.28 M fp32 = 49.1 MB) is the collective.  bf16 = autocast with fp32 master weights."""
+    name = "eavsrp_x4_train_step_8x15x64x64_bf16"
+
+    def __init__(self, device, rank=0, world=1, batch=8, t=15, size=64, dtype=torch.bfloat16, distinct=4, pwc=False):
+        import torch.nn.functional as F
+        from eavsr_b200.model import EAVSRP
+        from eavsr_b200.synthetic import clip_inputs, seeded_parameters
+        from eavsr_b200.train import Trainer, trainable_bytes
+        self.device, self.world, self.batch, self.t = device, world, batch, t
+        net = EAVSRP(4)
+        seeded_parameters(net)
+        net = net.to(device).to(memory_format=torch.channels_last)
+        pwcnet = None
+        if pwc:
+            from eavsr_b200.pwc import PWCNET
+            pwcnet = PWCNET()
+            seeded_parameters(pwcnet)
+            pwcnet = pwcnet.to(device)
+        self.trainer = Trainer(net, lr=1e-4, dtype=dtype, ddp=world > 1, device_ids=[device.index], pwcnet=pwcnet,
+                               npost=0 if pwc else 350)
+        self.grad_bytes = trainable_bytes(net)
+        self.host, self.dev = [], []
+        for k in range(distinct):
+            lr = torch.cat([clip_inputs(1, t, size, size, seed=5000 + 1000 * rank + 10 * k + i) for i in range(batch)])
+            hr = F.interpolate(lr.view(batch * t, 3, size, size), scale_factor=4, mode="bicubic",
+                               align_corners=False).clamp(0, 1).view(batch, t, 3, 4 * size, 4 * size)
+            self.host.append((lr.pin_memory(), hr.pin_memory()))
+            self.dev.append((lr.to(device), hr.to(device)))
+        self.cursor = 0
+        self.frames_per_step = batch * t
+        self.h2d_bytes = (self.host[0][0].numel() + self.host[0][1].numel()) * 4
+        self.d2h_bytes = 4
+        self.launches_per_step = None
+        self.loss = None
+        self.epoch = 0
+
+    def step(self, sync=True):
+        lr, hr = self.dev[self.cursor % len(self.dev)]
+        self.cursor += 1
+        with torch.enable_grad():
+            self.loss = self.trainer.step(lr, hr, epoch=self.epoch, sync=sync)
+        return self.loss
+
+    def e2e_step(self):
+        lr, hr = self.host[self.cursor % len(self.host)]
+        self.cursor += 1
+        with torch.enable_grad():
+            loss = self.trainer.step(lr.to(self.device, non_blocking=True), hr.to(self.device, non_blocking=True),
+                                     epoch=self.epoch)
+        return loss.item()                      # D2H read of the step's result
+
+    def collective(self, steps, time_steps):
+        """What the gradient all-reduce costs: the same steps without it (DDP no_sync), the all-reduce alone on a
+        flat buffer of the same size, and the part of it the backward pass does not hide."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return {"op": "none (1 GPU)", "bytes_per_step": self.grad_bytes}
+        t_sync = time_steps(lambda: self.step(True), steps)
+        t_nosync = time_steps(lambda: self.step(False), steps)
+        flat = torch.zeros(self.grad_bytes // 4, device=self.device)
+        buckets = list(flat.split(25 * 1024 * 1024 // 4))
+        t_alone = time_steps(lambda: [dist.all_reduce(b) for b in buckets], max(steps, 5))
+        exposed = max(0.0, t_sync - t_nosync)
+        return {"op": "all_reduce (NCCL, DistributedDataParallel buckets of 25 MB, gradient_as_bucket_view)",
+                "bytes_per_step": self.grad_bytes, "alone_ms": round(t_alone, 3), "step_ms": round(t_sync, 3),
+                "step_without_allreduce_ms": round(t_nosync, 3), "exposed_ms": round(exposed, 3),
+                "overlap_frac": round(1.0 - min(1.0, exposed / max(t_alone, 1e-9)), 4),
+                "busbw_GBps_alone": round(2 * (self.world - 1) / self.world * self.grad_bytes / (t_alone / 1e3) / 1e9, 1)}
+
+
 def make_workload(name, device, rank=0, world=1, args=None):
+    if name == "train":
+        return TrainWorkload(device, rank, world, dtype=torch.float32 if (args and args.train_dtype == "f32") else torch.bfloat16,
+                             pwc=bool(args and args.train_pwc))
     if name == "hotpath":
         return HotpathWorkload(device, t=T_FRAMES)
     if name == "model":
@@ -507,6 +585,9 @@ def main():
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per clip (profiling runs only; default 30)")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--train-dtype", default="bf16", choices=["bf16", "f32"], help="--workload train: compute dtype")
+    ap.add_argument("--train-pwc", action="store_true",
+                    help="--workload train: run the epoch >= npost branch too (PWC-Net cost volume + backwarp)")
     ap.add_argument("--clips-per-step", type=int, default=1,
                     help="clips batched into one forward per GPU (config 4 gives every GPU 8+ clips); default 1")
     args = ap.parse_args()
@@ -599,13 +680,30 @@ def main():
             e2e = {"value": round(world * wl.frames_per_step * args.steps / (ems / 1e3), 3), "unit": "frames/s",
                    "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes}
 
+        collective = None
+        if hasattr(wl, "collective"):          # every rank takes part
+            def time_steps(fn, k):
+                fn()
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(k):
+                    fn()
+                b.record()
+                barrier()
+                tt = torch.tensor([a.elapsed_time(b) / k], device=device)
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return tt.item()
+            collective = wl.collective(args.steps, time_steps)
+
         parity = None
         if rank == 0 and not args.no_parity and hasattr(wl, "parity"):
             try:
                 parity = wl.parity()
             except Exception as exc:   # reported, never a reason to lose the bench line
                 parity = {"failed": repr(exc)}
-        roof = dcn_roofline(device, peaks) if (rank == 0 and not args.no_roofline) else None
+        roof = dcn_roofline(device, peaks) if (rank == 0 and not args.no_roofline and args.workload != "train") else None
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -614,6 +712,10 @@ def main():
                 from oracle import eavsrp_cpu as R
                 torch.set_num_threads(os.cpu_count() or 1)
                 fps, sample, _, _ = R.time_model_sample(budget_s=40.0, h=PAD_H, w=LR_W, frames=(3,))
+            elif args.workload == "train":
+                from oracle import eavsrp_cpu as R
+                torch.set_num_threads(os.cpu_count() or 1)
+                fps, sample = R.time_train_sample()
             else:
                 fps, sample = cpu_hotpath_frames_per_s(15.0)
             cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -622,7 +724,22 @@ def main():
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {exc!r}"}
 
-    if rank == 0:
+    if rank == 0 and args.workload == "train":
+        value = world * wl.frames_per_step * args.steps / (ms / 1e3)
+        line = {"metric": "LR frames/s, EAVSR+ x4 training step, 15-frame 64x64 LR crops", "value": round(value, 3),
+                "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.train_dtype, "data": "synthetic",
+                "config": {"workload": wl.name if args.train_dtype == "bf16" else wl.name.replace("bf16", "f32"),
+                           "crops_per_gpu": wl.batch, "global_batch": wl.batch * world, "frames": wl.t,
+                           "optimizer": "Adam, 2 groups (deform_align lr 1e-5)", "loss": "L1",
+                           "npost_branch": bool(args.train_pwc),
+                           "parallelism": f"ddp x{world} (NCCL all-reduce of {wl.grad_bytes / 1e6:.1f} MB gradients)",
+                           "l2": "activations per step >> 126 MB L2"},
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "collective": collective,
+                "loss": float(wl.loss), "cpu_baseline": cpu}
+        print(json.dumps(line))
+    elif rank == 0:
         value = world * wl.frames_per_step * args.steps / (ms / 1e3)
         line = {"metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),

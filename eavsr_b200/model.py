@@ -389,8 +389,10 @@ class EAVSRP(nn.Module):
         a = lrs[:, :-1].reshape(-1, c, h, w)
         b = lrs[:, 1:].reshape(-1, c, h, w)
         m = a.shape[0]
-        # both directions in one batch: [backward (a<-b); forward (b<-a)]
-        flows = self.spynet(torch.cat([a, b]).float(), torch.cat([b, a]).float())
+        # both directions in one batch: [backward (a<-b); forward (b<-a)].  Flows are coordinates: SPyNet stays
+        # fp32 even when the caller trains under torch.autocast
+        with torch.autocast(lrs.device.type, enabled=False):
+            flows = self.spynet(torch.cat([a, b]).float(), torch.cat([b, a]).float())
         return flows[m:].view(n, t - 1, 2, h, w), flows[:m].view(n, t - 1, 2, h, w)   # forward, backward
 
     # -- one propagation branch ----------------------------------------------------------------

@@ -213,3 +213,24 @@ def time_model_sample(budget_s=30.0, h=272, w=480, t_full=30, state_dict=None, s
             f"threads (fp32, ATen grid_sample + torchvision CPU DCNv2; frames/s of the short clip: the 30-frame clip "
             f"of the metric costs more per frame)")
     return fps, what, secs, (t_s, hs, ws)
+
+
+def time_train_sample(t_s=5, size=64, state_dict=None):
+    """CPU baseline of the training step on a BOUNDED sample: forward + L1 + backward (autograd through ATen
+    grid_sample and torchvision's CPU DCNv2, what `--gpu_ids -1` training would execute) of ONE `t_s`-frame
+    64x64 crop, fp32, all host threads.  Returns (LR frames/s, description)."""
+    from eavsr_b200.synthetic import clip_inputs
+    sd = state_dict or _seeded_state_dict()
+    leaves = [v.requires_grad_() for k, v in sd.items() if v.is_floating_point() and not k.startswith("spynet.")
+              and not k.endswith(("mean", "std", "regular_matrix"))]
+    lrs = clip_inputs(1, t_s, size, size, seed=77)
+    hr = F.interpolate(lrs[0], scale_factor=4, mode="bicubic", align_corners=False).clamp(0, 1).unsqueeze(0)
+    eavsrp_forward(sd, clip_inputs(1, 3, size, size, seed=78), 4, "aten").mean().backward()         # lazy inits
+    t0 = time.time()
+    loss = (eavsrp_forward(sd, lrs, 4, "aten") - hr).abs().mean()
+    loss.backward()
+    el = time.time() - t0
+    assert all(v.grad is not None for v in leaves[:4])
+    return t_s / el, (f"forward + L1 + backward of one {t_s}-frame {size}x{size} crop in {el:.1f} s on "
+                      f"{torch.get_num_threads()} threads (fp32 autograd, ATen grid_sample + torchvision CPU DCNv2); the "
+                      f"15-frame crops of the metric cost more per frame")

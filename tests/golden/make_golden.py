@@ -161,6 +161,48 @@ def gen_correlation():
         save("correlation_" + tag, first=first, second=second, out=out, gout=gout, gfirst=g1, gsecond=g2)
 
 
+def gen_pwc():
+    """The reference's PWCNET (models/pwc_net.py) and BaseModel.estimate / get_backwarp (models/base_model.py:
+    294-360) on CPU: the cupy cost volume cannot run here, so `correlation.FunctionCorrelation` is replaced by
+    the oracle's restatement (itself pinned to the reference's kernel strings by gen_correlation); everything
+    else -- Extractor / Decoder / Refiner, Decoder.backwarp, estimate, get_backwarp -- is the reference's code."""
+    import models.pwc_net as P
+    from models.base_model import BaseModel
+    from oracle import alignment as O
+    P.correlation.FunctionCorrelation = lambda tenFirst, tenSecond: O.correlation(tenFirst, tenSecond)
+    # the constructor's last statement loads ./pwc/pwc-default (models/pwc_net.py:249-251), a stripped blob
+    orig_load, orig_lsd = torch.load, P.PWCNET.load_state_dict
+    torch.load = lambda *a, **k: {}
+    P.PWCNET.load_state_dict = lambda self, *a, **k: None
+    try:
+        net = P.PWCNET()
+    finally:
+        torch.load, P.PWCNET.load_state_dict = orig_load, orig_lsd
+    net.eval()
+    seeded_parameters(net)
+    a = clip_inputs(1, 2, 64, 64, seed=110)[0]                      # two related frames (1, 3, 64, 64) each
+    first, second = a[0:1], a[1:2]
+    with torch.no_grad():
+        flow_net = net(first, second)
+    dummy = types.SimpleNamespace(backwarp_tenGrid={}, backwarp_tenPartial={})
+    for name in ("backwarp", "estimate", "get_flow", "get_backwarp"):
+        setattr(dummy, name, types.MethodType(getattr(BaseModel, name), dummy))
+    lr = clip_inputs(1, 1, 40, 56, seed=111)[0]                     # not a multiple of 64: estimate() resizes
+    hr = F_interp(clip_inputs(1, 1, 40, 56, seed=112)[0], 2)
+    with torch.no_grad():
+        flow_est = dummy.estimate(lr, F_interp(hr, 0.5, True), net)
+        out, mask = dummy.get_backwarp(lr, hr, net, scale=2)
+    keys = sorted(net.state_dict().keys())
+    save("pwc_net", first=first, second=second, flow_net=flow_net, lr=lr, hr=hr, flow_est=flow_est, out=out, mask=mask,
+         keys=np.array(keys), key_shapes=np.array([str(tuple(net.state_dict()[k].shape)) for k in keys]))
+    print("  pwc flow", float(flow_net.abs().mean()), "est", float(flow_est.abs().mean()), "mask", float(mask.mean()))
+
+
+def F_interp(x, s, ac=False):
+    import torch.nn.functional as F
+    return F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=ac)
+
+
 def gen_model():
     import importlib
     for scale, modname, t in ((4, "models.eavsrp_model", 4), (2, "models.eavsrpx2_model", 3)):
@@ -181,6 +223,6 @@ def gen_model():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["flow_warp", "flow_warp_size1", "backwarp", "dcn", "adastn", "correlation", "model"]
+    which = sys.argv[1:] or ["flow_warp", "flow_warp_size1", "backwarp", "dcn", "adastn", "correlation", "pwc", "model"]
     for w in which:
         globals()["gen_" + w]()

@@ -117,7 +117,7 @@ def _feature_lists(net, lrs):
 
 
 def test_config3_bf16_graph_path_vs_fp32_and_cpu_oracle(cuda):
-    """(i) bf16 CUDA-graph replay of the full 30x270(->272)x480 clip == eager bf16 run, bit for bit;
+    """(i) bf16 CUDA-graph replay of the full 30x270(->272)x480 clip == eager bf16 run (to rounding);
     (ii) against the fp32 path of the same kernels (golden-pinned above): SR max-abs <= 1e-2, PSNR delta
     <= 0.01 dB, learned residual within 3 % relative RMS, every branch feature list within 3 % relative RMS
     with a stated worst-element bound; (iii) a T=6 272x480 clip against the CPU oracle (fp32 <= 1e-3 on SR
@@ -147,11 +147,16 @@ def test_config3_bf16_graph_path_vs_fp32_and_cpu_oracle(cuda):
         graph.replay()
         torch.cuda.synchronize()
         sr16 = out.float().clone()
-    assert torch.equal(sr16, eager.float())                                      # (i)
-    del graph, out, eager
+    # (i) the channel-attention sums are accumulated with floating-point atomics (order varies run to run), so two
+    # runs of the same clip agree to rounding, not bit for bit: compare on the learned residual
+    eager = eager.float()
+    r_g, r_e = _residual(sr16, lrs), _residual(eager, lrs)
+    assert (sr16 - eager).abs().max().item() < 1e-3
+    assert (r_g - r_e).pow(2).mean().sqrt().item() <= 0.01 * r_e.pow(2).mean().sqrt().item()
+    del graph, out, eager, r_g, r_e
 
     sr16b, f16 = _feature_lists(net, lrs)
-    assert torch.equal(sr16b.float(), sr16)
+    assert (sr16b.float() - sr16).abs().max().item() < 1e-3
     net32 = copy.deepcopy(net).float().prepare(torch.float32)      # the bf16-rounded weights, evaluated in fp32
     sr32, f32 = _feature_lists(net32, lrs)
     sr32 = sr32.float()
@@ -187,3 +192,24 @@ def test_config3_bf16_graph_path_vs_fp32_and_cpu_oracle(cuda):
     rrms = rr.pow(2).mean().sqrt().item()
     assert (_residual(o32, lr6.cpu()) - rr).pow(2).mean().sqrt().item() <= 0.02 * rrms
     assert (_residual(o16, lr6.cpu()) - rr).pow(2).mean().sqrt().item() <= 0.03 * rrms
+
+
+# ---------------------------------------------------------------------------------------------
+# PWC-Net (train-time caller of the cost volume and of backwarp) against the reference's own modules
+# ---------------------------------------------------------------------------------------------
+def test_pwcnet_estimate_and_get_backwarp_match_reference_golden(cuda):
+    from eavsr_b200 import pwc
+    g = np.load(os.path.join(GOLD, "pwc_net.npz"))
+    t = {k: torch.from_numpy(g[k]).to(cuda) for k in ("first", "second", "flow_net", "lr", "hr", "flow_est", "out", "mask")}
+    net = pwc.PWCNET().eval()
+    seeded_parameters(net)
+    net = net.to(cuda)
+    with torch.no_grad():
+        flow = net(t["first"], t["second"])
+        est = pwc.estimate(t["lr"], F.interpolate(t["hr"], scale_factor=0.5, mode="bilinear", align_corners=True), net)
+        out, mask = pwc.get_backwarp(t["lr"], t["hr"], net, scale=2)
+    assert (flow - t["flow_net"]).abs().max().item() < 1e-3 * max(1.0, t["flow_net"].abs().max().item())
+    assert (est - t["flow_est"]).abs().max().item() < 2e-3 * max(1.0, t["flow_est"].abs().max().item())
+    agree = (mask == t["mask"])
+    assert agree.float().mean().item() > 0.995          # the 0.999 threshold is discontinuous in the flow
+    assert ((out - t["out"]) * agree).abs().max().item() < 2e-3
