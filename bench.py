@@ -172,11 +172,16 @@ class ModelWorkload:
     name = "eavsrp_x4_full_clip_30x270x480_bf16"
 
     def __init__(self, device, t=T_FRAMES, h=LR_H, w=LR_W, dtype=torch.bfloat16, graph=True, rank=0, world=1,
-                 distinct=8, clips_per_step=1):
+                 distinct=8, clips_per_step=1, streams=1):
         from eavsr_b200.clip_parallel import shard
         from eavsr_b200.model import EAVSRP, pad_clip
         from eavsr_b200.synthetic import clip_inputs, seeded_parameters
         self.device, self.t, self.h, self.w, self.cps = device, t, h, w, clips_per_step
+        # `streams` > 1: the clips of a step run as independent forwards on that many CUDA streams (parallel branches
+        # of the captured graph) instead of one batched forward: the tail of one clip's kernel overlaps the head of
+        # the other's (every kernel here is a one-CTA-per-SM persistent grid of ~15 us)
+        self.streams = max(1, min(streams, clips_per_step))
+        assert clips_per_step % self.streams == 0
         net = EAVSRP(4).eval()
         seeded_parameters(net)
         self.net = net.to(device).prepare(dtype)
@@ -201,8 +206,20 @@ class ModelWorkload:
         self.last_clip = 0
 
     def _forward(self):
-        sr = self.net(self.static_in)
-        return sr[..., : 4 * self.h, : 4 * self.w]
+        if self.streams == 1:
+            sr = self.net(self.static_in)
+            return sr[..., : 4 * self.h, : 4 * self.w]
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream() for _ in range(self.streams)]
+        outs = []
+        for st, part in zip(self._side, self.static_in.chunk(self.streams)):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(self.net(part)[..., : 4 * self.h, : 4 * self.w])
+        for st in self._side:
+            cur.wait_stream(st)
+        return outs            # one SR tensor per stream (no concatenation copy inside the timed forward)
 
     def _replay(self):
         from eavsr_b200 import _lib
@@ -240,8 +257,12 @@ class ModelWorkload:
         self.e2e_cursor += 1
         self.static_in.copy_(self.pad(self.host_clips[self.last_clip].to(self.device, non_blocking=True)))
         sr = self._replay()
-        vis = torch.clamp(sr.float() * 255, 0, 255).round().to(torch.uint8)
-        self.host_out.copy_(vis, non_blocking=True)
+        parts = sr if isinstance(sr, list) else [sr]
+        k = 0
+        for part in parts:
+            vis = torch.clamp(part.float() * 255, 0, 255).round().to(torch.uint8)
+            self.host_out[k:k + vis.shape[0]].copy_(vis, non_blocking=True)
+            k += vis.shape[0]
         torch.cuda.current_stream().synchronize()
         return self.host_out
 
@@ -254,15 +275,16 @@ class ModelWorkload:
         import copy
         import torch.nn.functional as F
         self.static_in.copy_(self.dev_clips[self.last_clip])
-        sr16 = self._replay().float().clone()
-        lr = self.dev_clips[self.last_clip][..., : self.h, : self.w]
+        sr16 = self._replay()
+        sr16 = (sr16[0] if isinstance(sr16, list) else sr16)[:1].float().clone()       # first clip of the step
+        lr = self.dev_clips[self.last_clip][:1, ..., : self.h, : self.w]
         tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
         try:
             net32 = copy.deepcopy(self.net).float()
             net32.prepare(torch.float32)
             # the bf16 weights are the weights: the fp32 path runs on their exact values
-            sr32 = net32(self.dev_clips[self.last_clip])[..., : 4 * self.h, : 4 * self.w].float()
+            sr32 = net32(self.dev_clips[self.last_clip][:1])[..., : 4 * self.h, : 4 * self.w].float()
             del net32
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -366,7 +388,7 @@ def make_workload(name, device, rank=0, world=1, args=None):
     if name == "model":
         distinct = min(NUM_CLIPS // world, (args.steps + args.warmup) if args else 8, 16)
         return ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W, rank=rank, world=world, distinct=distinct,
-                             clips_per_step=args.clips_per_step if args else 1)
+                             clips_per_step=args.clips_per_step if args else 1, streams=args.streams if args else 1)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -568,6 +590,7 @@ def bench_config(workload, world, clips_per_gpu_step=1):
     """The `config` object of the JSON line -- identical for both arms (`--impl reference` times the same
     workload on the host cores)."""
     return {"workload": workload, "clip": f"{T_FRAMES}x3x{LR_H}x{LR_W}", "clips_per_step": world * clips_per_gpu_step,
+            "clips_in_flight_per_gpu": clips_per_gpu_step,
             "parallelism": f"clip-parallel x{world} (no collective)",
             "l2": "working set per step >> 126 MB L2 (a different HBM-resident clip every step)"}
 
@@ -588,6 +611,8 @@ def main():
     ap.add_argument("--train-dtype", default="bf16", choices=["bf16", "f32"], help="--workload train: compute dtype")
     ap.add_argument("--train-pwc", action="store_true",
                     help="--workload train: run the epoch >= npost branch too (PWC-Net cost volume + backwarp)")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="run the clips of a step as this many concurrent forwards (CUDA streams) instead of one batch")
     ap.add_argument("--clips-per-step", type=int, default=1,
                     help="clips batched into one forward per GPU (config 4 gives every GPU 8+ clips); default 1")
     args = ap.parse_args()

@@ -372,11 +372,13 @@ int launch_tc_dg(int dg, const void* x, const int64_t* xs, const float* offset, 
                  const void* weight, const void* bias, void* out, const int64_t* os, int n, int h, int w,
                  void* workspace, unsigned flags, cudaStream_t st) {
   switch (dg) {
+#ifndef EAVSR_ONLY_DG8   // (development builds: tools/abl_build.sh compiles the deform_groups = 8 kernels only)
     case 1: return launch_tc<XT, SPLIT, 1>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
     case 2: return launch_tc<XT, SPLIT, 2>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
     case 4: return launch_tc<XT, SPLIT, 4>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
-    case 8: return launch_tc<XT, SPLIT, 8>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
     case 16: return launch_tc<XT, SPLIT, 16>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
+#endif
+    case 8: return launch_tc<XT, SPLIT, 8>(x, xs, offset, mask, weight, bias, out, os, n, h, w, workspace, flags, st);
   }
   set_error("dcn_forward(tc): deform_groups %d", dg);
   return EAVSR_ERR_INVALID;

@@ -22,6 +22,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef EAVSR_ABL
+#define EAVSR_ABL 0   // development only (tools/abl_build.sh): bit mask of pipeline pieces to leave out for TIMING
+#endif               // 1 fence, 2 offset prefetch, 4 blend, 8 window loads, 16 A-tile stores, 32 coordinate math
+
 namespace eavsr {
 namespace win {
 
@@ -31,7 +35,16 @@ constexpr int TH = 8, TW = 16;               // tile
 constexpr int CH = 64, TAPS = 9;
 constexpr int A_TILE = 128 * CH * 2;         // 16 KB
 constexpr int B_TILE = CH * CH * 2;          // 8 KB
-constexpr int NSA = 3, NSB = 2;
+#ifndef EAVSR_WIN_NSA
+#define EAVSR_WIN_NSA 3
+#endif
+#ifndef EAVSR_WIN_NSB
+#define EAVSR_WIN_NSB 2
+#endif
+#ifndef EAVSR_WIN_NOB
+#define EAVSR_WIN_NOB 3
+#endif
+constexpr int NSA = EAVSR_WIN_NSA, NSB = EAVSR_WIN_NSB;   // A-stage ring, weight-tile ring
 constexpr int PLW = 8;                       // staged offset plane: 8 pixels, XOR-swizzled (no padding)
 constexpr int TMEM_COLS = 128;
 
@@ -53,7 +66,7 @@ template <int DG, bool AFF = false> struct Cfg {
   static constexpr int PAD = (DG == 16 || AFF) ? 4 : 5;
   static constexpr int WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 18 x 26 (16 x 24) window
   static constexpr int WIN_BYTES = WH * WW * 128;              // 59 904 (49 152)
-  static constexpr int NOB = (DG == 16 || AFF) ? 2 : 3;
+  static constexpr int NOB = (DG == 16 || AFF) ? 2 : EAVSR_WIN_NOB;
   static constexpr int MAX_PLANES = DG == 16 ? 48 : 24;
   static constexpr int APX = 15 * DG * 2;                      // AFF: bytes per pixel of the affine block
   static constexpr int OFF_WARP_BUF = AFF ? PLW * APX : MAX_PLANES * PLW * 4;    // 768 B (1 536 B; AFF: 1 920 B)
@@ -261,7 +274,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         const uint32_t dst0 = offBase + p_ring * OFF_WARP_BUF;
 #pragma unroll
         for (int k = 0; k < NCOPY; ++k) {
-          if (pref.ok & (1u << k)) {
+          if (!(EAVSR_ABL & 2) && (pref.ok & (1u << k))) {
             const float* src = (cp_mask[k] ? pref.mb : pref.ob) + (cp_rel[k] + (uint32_t)p_tap * cp_step[k]);
             if (VEC_OFF) cp_async_16(dst0 + cp_dst[k], src); else cp_async_4(dst0 + cp_dst[k], src);
           }
@@ -428,6 +441,7 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
             dx = so[(1 * DG + g) * PLW + col];
             mk = so[(2 * DG + g) * PLW + col];
           }
+          if (EAVSR_ABL & 32) { dy = 0.25f; dx = 0.25f; mk = 0.5f; }
           const float py = (pyb[j] + (float)ti) + dy;
           const float px = (pxb[j] + (float)tj) + dx;
           // floor via a saturating float->int conversion (NaN -> 0, +-huge -> INT_MIN/MAX: such cells fail
@@ -442,6 +456,13 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         }
         uint32_t v[NI][4][CW];               // [sample][corner][words]
         auto load_win = [&](int u) {
+          if (EAVSR_ABL & 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int e = 0; e < CW; ++e) v[u][c][e] = (uint32_t)(ry[u] + c + e);
+            return;
+          }
           const uint32_t a00 = win + (uint32_t)(ry[u] * WW + rx[u]) * 128u + (u % NSUB) * 8u;
           const uint32_t ad[4] = {a00, a00 + 128u, a00 + WW * 128u, a00 + WW * 128u + 128u};
 #pragma unroll
@@ -492,7 +513,10 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         for (int u = 0; u < NI; ++u) {
           const int j = u / NSUB, sb = u % NSUB;
           const float w00 = wy0f[u] * wx0f[u], w01 = wy0f[u] * wx1f[u], w10 = wy1f[u] * wx0f[u], w11 = wy1f[u] * wx1f[u];
-          if (BLEND16) {
+          if (EAVSR_ABL & 4) {
+#pragma unroll
+            for (int e = 0; e < CW; ++e) res[j][sb * CW + e] = v[u][0][e] ^ v[u][1][e] ^ v[u][2][e] ^ v[u][3][e] ^ __float_as_uint(w00 + w11);
+          } else if (BLEND16) {
             const uint32_t p00 = pack_bf16x2(w00, w00), p01 = pack_bf16x2(w01, w01);
             const uint32_t p10 = pack_bf16x2(w10, w10), p11 = pack_bf16x2(w11, w11);
 #pragma unroll
@@ -515,10 +539,11 @@ dcn_fwd_win_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         for (int j = 0; j < 2; ++j) {
           const int m = wrow * 16 + wcol + j * 4 + q;
           const uint32_t dst = aStage + sw128_offset(m, l * 16);
+          if (!(EAVSR_ABL & 16) || res[j][0] == 0x12345678u)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(res[j][0]), "r"(res[j][1]),
                        "r"(res[j][2]), "r"(res[j][3]));
         }
-        fence_proxy_async_smem();
+        if (!(EAVSR_ABL & 1)) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar_full + 8 * ring);
