@@ -34,6 +34,14 @@ class EavsrError(RuntimeError):
     pass
 
 
+class ConvLayer(ctypes.Structure):
+    """EavsrConvLayer of include/eavsr_b200.h (one convolution of eavsr_conv3x3_chain_forward)."""
+    _fields_ = [("x", c_void_p), ("packed_weight", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+                ("channel_sums", c_void_p), ("res", c_void_p), ("res_sums", c_void_p), ("w1", c_void_p),
+                ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p), ("y_out", c_void_p),
+                ("negative_slope", c_float)]
+
+
 _SIGNATURES = {
     "eavsr_version": (c_int, []),
     "eavsr_last_error": (c_char_p, []),
@@ -71,6 +79,7 @@ _SIGNATURES = {
     "eavsr_conv3x3_pack_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "eavsr_conv3x3_ca_forward": (c_int, [c_void_p, c_void_p, _PF] + [c_void_p] * 8 + [_PF] + [c_int] * 3 +
                                  [c_float, c_int, c_uint, c_void_p]),
+    "eavsr_conv3x3_chain_forward": (c_int, [POINTER(ConvLayer), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "eavsr_conv3x3_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _PF] + [c_int] * 5 +
                               [c_float, c_int, c_uint, c_void_p]),
 }

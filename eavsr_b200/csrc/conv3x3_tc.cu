@@ -61,8 +61,10 @@ struct CvSmem {
   static constexpr int RED_OFF = BIAS_OFF + CV_CH * 4;             // 64 fp32: per-CTA channel sums before the atomics
   static constexpr int SCALE_OFF = RED_OFF + CV_CH * 4;            // fused channel attention: CV_MAXN x 64 fp32 scales
   static constexpr int BAR_OFF = SCALE_OFF + CV_MAXN * CV_CH * 4;
-  // full[NS], empty[NS], accf[2], acce[2], wbar, tmem slot
-  static constexpr int TOTAL = BAR_OFF + (2 * CV_NS + 5) * 8 + 16;
+  // two sets (layers alternate; the idle set is re-initialised off the critical path) of
+  // full[NS], empty[NS], accf[2], acce[2], wbar; then the tmem slot
+  static constexpr int NBARS = 2 * CV_NS + 5;
+  static constexpr int TOTAL = BAR_OFF + 2 * NBARS * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
 };
 
@@ -79,283 +81,372 @@ __global__ void conv_pack_weight(const __nv_bfloat16* __restrict__ w, uint8_t* _
       w[((size_t)o * CV_CH + c) * 9 + t];
 }
 
-// Fused input transform (the tail of the previous RCABlock, models/networks.py:449-465): when `res` is set,
-// the convolution's input is y = res * sigmoid(MLP(sums / HW)) + x, built by the producer warps while they
-// stage the halo tile; the interior of every tile is also written to `y_out` (the next block's skip).
-struct CaFuse {
-  const __nv_bfloat16* res;
-  const float* sums;               // (n, 64) channel sums of res
+// One convolution of a chain.  Fused input transform (the tail of the previous RCABlock, models/networks.py:
+// 449-465): when `res` is set, the convolution's input is y = res * sigmoid(MLP(res_sums / HW)) + x, built by the
+// producer warps while they stage the halo tile; the interior of every tile is also written to `y_out` (the next
+// block's skip).
+struct ConvLayerDev {
+  const __nv_bfloat16* x;          // input (the skip tensor in the fused mode)
+  const uint8_t* wpacked;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* out;
+  float* chan_sums;                // (n, 64) or null
+  const __nv_bfloat16* res;        // fused mode: residual branch of the previous block, or null
+  const float* res_sums;           // (n, 64) channel sums of res
   const __nv_bfloat16 *w1, *b1, *w2, *b2;
   __nv_bfloat16* y_out;
+  float slope;
+  int pad_;
+};
+// A whole residual group in ONE launch (RCAGroup = 61 chained 64->64 convolutions,
+// models/networks.py:467-482): the persistent CTAs walk the layers, separated by a grid-wide barrier (every layer
+// reads what all CTAs of the previous one wrote).  What a launch per convolution pays 61 times -- launch gap, TMEM
+// allocation, a cold 72 KB weight load in front of the first MMA, pipeline drain -- is paid once or hidden: the next
+// layer's weights stream in while the CTA waits at the barrier.  Kernel parameters are the layer table itself
+// (<= 64 layers, 6.7 KB of the 32 KB parameter space), so nothing has to be staged in device memory.
+constexpr int CV_MAXL = 64;
+struct ChainParams {
+  int nlayers, H, W, tiles_x, tiles_per_img, total_tiles, nimg;
   float inv_hw;
-  int nimg;
+  unsigned* sync;                  // grid-barrier counter, zero at launch (only read when nlayers > 1)
+  ConvLayerDev L[CV_MAXL];
 };
 
+#ifdef EAVSR_CONV_TRACE   // development only: per-phase timestamps of CTA 0 (tools/abl_build.sh, tools/prof_chain.py)
+__device__ unsigned long long g_conv_trace[CV_MAXL * 16];
+#define CV_TRACE(li, slot) do { if (blockIdx.x == 0) g_conv_trace[(li) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define CV_TRACE(li, slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ void mbar_inval(uint32_t bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ wpacked,
-                  const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                  float* __restrict__ chan_sums, int H, int W, int tiles_x, int tiles_per_img, int total_tiles,
-                  float slope, CaFuse ca) {
+conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sB = base + CvSmem::B_OFF, sA = base + CvSmem::A_OFF, bars = base + CvSmem::BAR_OFF;
-  const uint32_t bar_full = bars, bar_empty = bars + CV_NS * 8, bar_accf = bars + 2 * CV_NS * 8;
-  const uint32_t bar_acce = bar_accf + 16, bar_w = bar_acce + 16, tmem_slot_addr = bar_w + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CvSmem::BAR_OFF + (2 * CV_NS + 5) * 8);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // The 72 KB of packed weights start streaming before anything else is set up (the launch is short --
-  // ~8 tiles per CTA -- so every microsecond of prologue counts).
-  if (warp == 4 && elect_one()) {
-    mbar_init(bar_w, 1);
-    fence_mbar_init();
-    mbar_arrive_expect_tx(bar_w, 9 * CV_BTILE);
-    for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
-  }
-  if (tid == 0) {
+  const uint32_t sB = base + CvSmem::B_OFF, sA = base + CvSmem::A_OFF, bars0 = base + CvSmem::BAR_OFF;
+  const uint32_t tmem_slot_addr = bars0 + 2 * CvSmem::NBARS * 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CvSmem::BAR_OFF + 2 * CvSmem::NBARS * 8);
+  auto init_bar_set = [&](uint32_t b0, bool fused_layer) {
     for (int s = 0; s < CV_NS; ++s) {
-      mbar_init(bar_full + 8 * s, ca.res ? 64 : 32);        // fused input transform: two warps fill a stage
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(b0 + 8 * s, fused_layer ? 64 : 32);           // full: fused input transform = two warps fill a stage
+      mbar_init(b0 + (CV_NS + s) * 8, 1);                     // empty
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_accf + 8 * b, 1);
-      mbar_init(bar_acce + 8 * b, 8);
+      mbar_init(b0 + (2 * CV_NS + b) * 8, 1);                 // accf
+      mbar_init(b0 + (2 * CV_NS + 2 + b) * 8, 8);             // acce
     }
-    fence_mbar_init();
-  }
-  if (tid < CV_CH) reinterpret_cast<float*>(smem + CvSmem::BIAS_OFF)[tid] = bias ? __bfloat162float(bias[tid]) : 0.f;
+    mbar_init(b0 + (2 * CV_NS + 4) * 8, 1);                   // weights
+  };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = P.H, W = P.W, tiles_x = P.tiles_x, tiles_per_img = P.tiles_per_img;
+  const int first = blockIdx.x;
+  const int my_tiles = (P.total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
+
   // zero the padding rows of every stage once (they only feed dropped wrap-around outputs)
   for (int i = tid; i < CV_NS * (CV_ROWS - CV_HROWS) * 8; i += CV_THREADS) {
     const int s = i / ((CV_ROWS - CV_HROWS) * 8), r = i % ((CV_ROWS - CV_HROWS) * 8);
     *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + s * CV_ASTAGE + CV_HROWS * 128 + r * 16) = make_uint4(0, 0, 0, 0);
   }
-  const int first = blockIdx.x;
-  const int my_tiles = (total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
-  // producer warp w streams the halo tile of tile tl (== w mod 4) into stage w
-  auto issue_tile = [&](int tl) {
-    const int tile = first + tl * (int)gridDim.x;
-    const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-    const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
-    const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
-    const uint32_t stage = sA + warp * CV_ASTAGE;
-#pragma unroll 4
-    for (int i = lane; i < CV_HROWS * 8; i += 32) {
-      const int p = i >> 3, ch = i & 7;
-      const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
-      const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-      const __nv_bfloat16* src = ok ? xn + ((size_t)gy * W + gx) * CV_CH + ch * 8 : xn;
-      cp_async_16_zfill(stage + p * 128 + ((ch ^ (p & 7)) << 4), src, ok);
-    }
-    cp_async_commit();
-  };
-  const bool fused = ca.res != nullptr;
-  if (!fused && warp < 4 && warp < my_tiles) issue_tile(warp);   // first loads in flight before the set-up barrier
-  if (fused && warp >= 5 && warp < 13) {
-    // squeeze-excite MLP of the previous block, once per CTA: 256 threads = 4 hidden units x 64 channels
-    float* scale = reinterpret_cast<float*>(smem + CvSmem::SCALE_OFF);
-    float* part = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);      // (free until the first flush)
-    const int e = tid - 5 * 32, r = e >> 6, i = e & 63;
-    for (int img = 0; img < ca.nimg; ++img) {
-      float pr = __bfloat162float(ca.w1[r * CV_CH + i]) * (ca.sums[img * CV_CH + i] * ca.inv_hw);
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, off);
-      if ((e & 31) == 0) part[e >> 5] = pr;
-      asm volatile("bar.sync 2, 256;\n" ::: "memory");
-      if (e < CV_CH) {
-        float a = __bfloat162float(ca.b2[e]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          a += __bfloat162float(ca.w2[e * 4 + j]) * fmaxf(__bfloat162float(ca.b1[j]) + part[2 * j] + part[2 * j + 1], 0.f);
-        scale[img * CV_CH + e] = 1.f / (1.f + __expf(-a));
-      }
-      asm volatile("bar.sync 2, 256;\n" ::: "memory");
-    }
-  }
   if (warp == 4) tmem_alloc<CV_TMEM>(tmem_slot_addr);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  uint32_t tmem_d = 0;
 
-  if (warp < 4 || warp >= 13) {
-    // ===================== producers =====================
-    // (warps 13-16 only work in the fused-input mode, where they build the second half of the halo tile of
-    // "their" stage: the transform is load-latency bound, two warps per stage keep enough loads in flight)
-    const int phalf = warp >= 13 ? 1 : 0;
-    const int warp_s = warp >= 13 ? warp - 13 : warp;         // stage / tile phase served by this warp
-    // Warp w owns stage w and the tiles tl == w (mod 4): it waits for its stage to drain, streams the
-    // halo tile in, waits for ITS copies only and publishes.  The four warps are independent, so up
-    // to four tiles are in flight and a late MMA never delays the publication of a landed tile.
-    const float* scale = reinterpret_cast<const float*>(smem + CvSmem::SCALE_OFF);
-    for (int tl = (phalf && !fused) ? my_tiles : warp_s; tl < my_tiles; tl += CV_NS) {
-      const int u = tl / CV_NS;
-      if (u >= 1) mbar_wait(bar_empty + 8 * warp_s, (u - 1) & 1);
-      if (!fused) {
-        if (u >= 1) issue_tile(tl);                          // (the first tile of this warp was issued in the prologue)
-        cp_async_wait<0>();
-      } else {
-        const int tile = first + tl * (int)gridDim.x;
-        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-        const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
-        const size_t img = (size_t)n * H * W * CV_CH;
-        const uint32_t stage = sA + warp_s * CV_ASTAGE;
-        const float* sc = scale + n * CV_CH + (lane & 7) * 8;      // this lane always handles chunk lane & 7
-        float s8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s8[e] = sc[e];
-        // batches of 8 chunks per lane: 16 independent 16-byte loads in flight before the first use
-        constexpr int NB = 8;
-        static_assert((CV_HROWS * 4) % (32 * NB) == 0, "whole batches per half tile");
 #pragma unroll 1
-        for (int i0 = lane + phalf * (CV_HROWS * 4); i0 < (phalf + 1) * (CV_HROWS * 4); i0 += 32 * NB) {
-          uint4 rv[NB], sv[NB];
-          uint32_t off[NB];                                   // element offsets (n <= 8 images of < 2^24 pixels)
-          bool okv[NB];
-          // volatile asm: ptxas otherwise sinks every load pair down to its use (one round trip per chunk)
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const int p = (i0 + 32 * b) >> 3;
-            const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
-            okv[b] = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-            off[b] = okv[b] ? (uint32_t)(img + ((size_t)gy * W + gx) * CV_CH) + (lane & 7) * 8 : 0u;
-            asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n"
-                         : "=r"(rv[b].x), "=r"(rv[b].y), "=r"(rv[b].z), "=r"(rv[b].w) : "l"(ca.res + off[b]));
-            asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n"
-                         : "=r"(sv[b].x), "=r"(sv[b].y), "=r"(sv[b].z), "=r"(sv[b].w) : "l"(x + off[b]));
-          }
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const int p = (i0 + 32 * b) >> 3, ch = lane & 7;
-            const int hr = p >> 5, hc = p & 31;
-            const uint32_t rw[4] = {rv[b].x, rv[b].y, rv[b].z, rv[b].w}, sw[4] = {sv[b].x, sv[b].y, sv[b].z, sv[b].w};
-            uint32_t ow[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              ow[e] = pack_bf16x2(bf16lo_to_f32(rw[e]) * s8[2 * e] + bf16lo_to_f32(sw[e]),
-                                  bf16hi_to_f32(rw[e]) * s8[2 * e + 1] + bf16hi_to_f32(sw[e]));
-            const uint4 yv = okv[b] ? make_uint4(ow[0], ow[1], ow[2], ow[3]) : make_uint4(0, 0, 0, 0);
-            if (okv[b] && hr >= 1 && hr <= CV_TR && hc >= 1 && hc <= CV_TC)      // this tile owns the pixel
-              *reinterpret_cast<uint4*>(ca.y_out + off[b]) = yv;
-            *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + warp_s * CV_ASTAGE + p * 128 + ((ch ^ (p & 7)) << 4)) = yv;
-          }
-        }
-        (void)stage;
+  for (int li = 0; li < P.nlayers; ++li) {
+    const ConvLayerDev& Ly = P.L[li];
+    const bool fused = Ly.res != nullptr;
+    const __nv_bfloat16* __restrict__ x = Ly.x;
+    // ---------------- layer prologue ----------------
+    // Layers alternate between two mbarrier sets: this layer's set was initialised while the previous layer ran.
+    const uint32_t bars = bars0 + (li & 1) * CvSmem::NBARS * 8;
+    const uint32_t bar_full = bars, bar_empty = bars + CV_NS * 8, bar_accf = bars + 2 * CV_NS * 8;
+    const uint32_t bar_acce = bar_accf + 16, bar_w = bar_acce + 16;
+    if (li == 0) {
+      if (tid == 0) {
+        init_bar_set(bars, fused);
+        fence_mbar_init();
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      mbar_arrive(bar_full + 8 * warp_s);
+      fence_proxy_async_smem();                                 // the zeroed padding rows, before any MMA reads them
     }
-  } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      mbar_wait(bar_w, 0);
-      constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_CH);
-      const uint64_t b_base = umma_desc_sw128_kmajor(sB);
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        const int s = tl % CV_NS, buf = tl & 1;
-        if (tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
-        mbar_wait(bar_full + 8 * s, (tl / CV_NS) & 1);
-        tc_fence_after();
-        const uint64_t a_base = umma_desc_sw128_kmajor(sA + s * CV_ASTAGE);
-        const uint32_t d = tmem_d + buf * CV_CH;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // tap view: start (r*32 + s) rows further; K step = 32 B.  The swizzle XOR is taken from the
-            // absolute shared-memory address bits, so the shifted view needs no base_offset (measured:
-            // base_offset = s gives wrong results, 0 is exact).
-            const uint64_t adesc = a_base + (uint64_t)((((t / 3) * CV_PW + (t % 3)) * 128) >> 4) + 2 * k;
-            const uint64_t bdesc = b_base + (uint64_t)((t * CV_BTILE) >> 4) + 2 * k;
-            umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
-          }
+    // (A) every role has left layer li-1 (its global writes are issued, its MMAs have retired); layer 0: set-up
+    __syncthreads();
+    if (tid == 0) CV_TRACE(li, 0);
+    if (li > 0 && tid == 0)                                     // grid barrier, arrive: this CTA's layer li-1 is out
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(P.sync) : "memory");
+    // The 72 KB of packed weights start streaming before anything else (they do not depend on the other CTAs):
+    // in a chain they land while this CTA waits at the grid barrier.
+    if (warp == 4 && elect_one()) {
+      mbar_arrive_expect_tx(bar_w, 9 * CV_BTILE);
+      for (int t = 0; t < 9; ++t) bulk_g2s(sB + t * CV_BTILE, Ly.wpacked + (size_t)t * CV_BTILE, CV_BTILE, bar_w);
+    }
+    if (tid < CV_CH) reinterpret_cast<float*>(smem + CvSmem::BIAS_OFF)[tid] = Ly.bias ? __bfloat162float(Ly.bias[tid]) : 0.f;
+    if (li > 0) {
+      if (tid == 0) {                                           // grid barrier, wait: all CTAs finished layer li-1
+        const unsigned want = (unsigned)li * gridDim.x;
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(P.sync) < want) {
+          if (clock64() - t0 > 4000000000ll) __trap();         // a lost CTA must fail, not hang the GPU
         }
-        umma_commit(bar_empty + 8 * s);
-        umma_commit(bar_accf + 8 * buf);
+      }
+      __syncthreads();                                          // (C)
+    }
+    if (tid == 0) CV_TRACE(li, 1);
+    if (tid == 32 && li + 1 < P.nlayers) {                      // the other set is quiescent: re-arm it for layer li+1
+      const uint32_t nb = bars0 + ((li + 1) & 1) * CvSmem::NBARS * 8;
+      if (li > 0)
+        for (int b = 0; b < CvSmem::NBARS; ++b) mbar_inval(nb + 8 * b);
+      init_bar_set(nb, P.L[li + 1].res != nullptr);
+      fence_mbar_init();
+    }
+
+    // producer warp w streams the halo tile of tile tl (== w mod 4) into stage w
+    auto issue_tile = [&](int tl) {
+      const int tile = first + tl * (int)gridDim.x;
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+      const __nv_bfloat16* xn = x + (size_t)n * H * W * CV_CH;
+      const uint32_t stage = sA + warp * CV_ASTAGE;
+#pragma unroll 4
+      for (int i = lane; i < CV_HROWS * 8; i += 32) {
+        const int p = i >> 3, ch = i & 7;
+        const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+        const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const __nv_bfloat16* src = ok ? xn + ((size_t)gy * W + gx) * CV_CH + ch * 8 : xn;
+        cp_async_16_zfill(stage + p * 128 + ((ch ^ (p & 7)) << 4), src, ok);
+      }
+      cp_async_commit();
+    };
+    // First loads in flight before the set-up barrier -- tile 0 only: right after the grid barrier all 148 SMs
+    // start at once, and four tiles per SM (14 MB) in one burst delay the first tile, the one the MMA warp is
+    // waiting for, by ~1.5 us of L2 bandwidth (phase timestamps, tools/prof_chain.py).  Warps 1-3 start their
+    // tiles when tile 0 has landed; those land while tile 0 is being multiplied.
+    if (!fused && warp == 0 && my_tiles > 0) issue_tile(0);
+    if (fused && warp >= 5 && warp < 13) {
+      // squeeze-excite MLP of the previous block, once per CTA: 256 threads = 4 hidden units x 64 channels
+      float* scale = reinterpret_cast<float*>(smem + CvSmem::SCALE_OFF);
+      float* part = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);      // (free until the first flush)
+      const int e = tid - 5 * 32, r = e >> 6, i = e & 63;
+      for (int img = 0; img < P.nimg; ++img) {
+        float pr = __bfloat162float(Ly.w1[r * CV_CH + i]) * (__ldcg(Ly.res_sums + img * CV_CH + i) * P.inv_hw);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, off);
+        if ((e & 31) == 0) part[e >> 5] = pr;
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        if (e < CV_CH) {
+          float a = __bfloat162float(Ly.b2[e]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            a += __bfloat162float(Ly.w2[e * 4 + j]) * fmaxf(__bfloat162float(Ly.b1[j]) + part[2 * j] + part[2 * j + 1], 0.f);
+          scale[img * CV_CH + e] = 1.f / (1.f + __expf(-a));
+        }
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
       }
     }
-    __syncwarp();
-  } else if (warp < 13) {
-    // ===================== epilogue (warps 5..12 -> TMEM lane quadrants 1,2,3,0, 1,2,3,0) =====================
-    const int q = warp & 3;                       // output row of the tile handled by this warp
-    const int chalf = (warp - 5) >> 2;            // this group's 32 output channels
-    constexpr int HC = CV_CH / 2;
-    float csum[HC];                               // this thread's running channel sums (its pixels)
+    tc_fence_before();
+    __syncthreads();                                            // (D) bias / scales / re-armed barriers are visible
+    tc_fence_after();
+    tmem_d = *tmem_slot;
+    if (tid == 0) CV_TRACE(li, 2);
+
+    if (warp < 4 || warp >= 13) {
+      // ===================== producers =====================
+      // (warps 13-16 only work in the fused-input mode, where they build the second half of the halo tile of
+      // "their" stage: the transform is load-latency bound, two warps per stage keep enough loads in flight)
+      const int phalf = warp >= 13 ? 1 : 0;
+      const int warp_s = warp >= 13 ? warp - 13 : warp;         // stage / tile phase served by this warp
+      // Warp w owns stage w and the tiles tl == w (mod 4): it waits for its stage to drain, streams the
+      // halo tile in, waits for ITS copies only and publishes.  The four warps are independent, so up
+      // to four tiles are in flight and a late MMA never delays the publication of a landed tile.
+      const float* scale = reinterpret_cast<const float*>(smem + CvSmem::SCALE_OFF);
+      for (int tl = (phalf && !fused) ? my_tiles : warp_s; tl < my_tiles; tl += CV_NS) {
+        const int u = tl / CV_NS;
+        if (u >= 1) mbar_wait(bar_empty + 8 * warp_s, (u - 1) & 1);
+        if (!fused) {
+          if (u == 0 && warp_s > 0) mbar_wait(bar_full, 0);      // tile 0 first (see the prologue)
+          if (u >= 1 || warp_s > 0) issue_tile(tl);            // (tile 0 was issued in the prologue)
+          cp_async_wait<0>();
+        } else {
+          const int tile = first + tl * (int)gridDim.x;
+          const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+          const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+          const size_t img = (size_t)n * H * W * CV_CH;
+          const float* sc = scale + n * CV_CH + (lane & 7) * 8;      // this lane always handles chunk lane & 7
+          float s8[8];
 #pragma unroll
-    for (int c = 0; c < HC; ++c) csum[c] = 0.f;
-    const float* bsm = reinterpret_cast<const float*>(smem + CvSmem::BIAS_OFF) + chalf * HC;
-    int cur_n = -1;
-    auto flush = [&]() {
-      if (chan_sums && cur_n >= 0) {
-        // transpose-reduce over the 32 lanes: 31 shuffles leave lane l with the sum of channel l of this half
-        // (step k adds (16 >> k) to the channel base when lane bit (16 >> k) is set: base = lane)
+          for (int e = 0; e < 8; ++e) s8[e] = sc[e];
+          // batches of 8 chunks per lane: 16 independent 16-byte loads in flight before the first use
+          constexpr int NB = 8;
+          static_assert((CV_HROWS * 4) % (32 * NB) == 0, "whole batches per half tile");
+#pragma unroll 1
+          for (int i0 = lane + phalf * (CV_HROWS * 4); i0 < (phalf + 1) * (CV_HROWS * 4); i0 += 32 * NB) {
+            uint4 rv[NB], sv[NB];
+            uint32_t off[NB];                                   // element offsets (n <= 8 images of < 2^24 pixels)
+            bool okv[NB];
+            // volatile asm: ptxas otherwise sinks every load pair down to its use (one round trip per chunk).
+            // .cg (L2 only): in a chain these buffers were written by other SMs earlier in this same launch and
+            // are recycled from layer to layer, so a line this SM cached two layers ago must not be hit.
 #pragma unroll
-        for (int step = 0; step < 5; ++step) {
-          const int m = 16 >> step, len = 16 >> step;
-          const bool up = (lane & m) != 0;
+            for (int b = 0; b < NB; ++b) {
+              const int p = (i0 + 32 * b) >> 3;
+              const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+              okv[b] = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+              off[b] = okv[b] ? (uint32_t)(img + ((size_t)gy * W + gx) * CV_CH) + (lane & 7) * 8 : 0u;
+              asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                           : "=r"(rv[b].x), "=r"(rv[b].y), "=r"(rv[b].z), "=r"(rv[b].w) : "l"(Ly.res + off[b]));
+              asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                           : "=r"(sv[b].x), "=r"(sv[b].y), "=r"(sv[b].z), "=r"(sv[b].w) : "l"(x + off[b]));
+            }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (i < len) {
-              const float send = up ? csum[i] : csum[i + len];
-              const float keep = up ? csum[i + len] : csum[i];
-              csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            for (int b = 0; b < NB; ++b) {
+              const int p = (i0 + 32 * b) >> 3, ch = lane & 7;
+              const int hr = p >> 5, hc = p & 31;
+              const uint32_t rw[4] = {rv[b].x, rv[b].y, rv[b].z, rv[b].w}, sw[4] = {sv[b].x, sv[b].y, sv[b].z, sv[b].w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                ow[e] = pack_bf16x2(bf16lo_to_f32(rw[e]) * s8[2 * e] + bf16lo_to_f32(sw[e]),
+                                    bf16hi_to_f32(rw[e]) * s8[2 * e + 1] + bf16hi_to_f32(sw[e]));
+              const uint4 yv = okv[b] ? make_uint4(ow[0], ow[1], ow[2], ow[3]) : make_uint4(0, 0, 0, 0);
+              if (okv[b] && hr >= 1 && hr <= CV_TR && hc >= 1 && hc <= CV_TC)      // this tile owns the pixel
+                *reinterpret_cast<uint4*>(Ly.y_out + off[b]) = yv;
+              *reinterpret_cast<uint4*>(smem + CvSmem::A_OFF + warp_s * CV_ASTAGE + p * 128 + ((ch ^ (p & 7)) << 4)) = yv;
             }
           }
         }
-        // four warps hold the same 32 channels: combine them in shared memory, one global atomic per
-        // channel and CTA (148 instead of 592 reductions on each of the 64 addresses)
-        float* red = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);
-        asm volatile("bar.sync 2, 256;\n" ::: "memory");       // previous flush fully drained
-        if (q == 0) red[chalf * HC + lane] = csum[0];
-        asm volatile("bar.sync 2, 256;\n" ::: "memory");
-        if (q != 0) atomicAdd(red + chalf * HC + lane, csum[0]);
-        asm volatile("bar.sync 2, 256;\n" ::: "memory");
-        if (q == 0) atomicAdd(chan_sums + cur_n * CV_CH + chalf * HC + lane, red[chalf * HC + lane]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        mbar_arrive(bar_full + 8 * warp_s);
       }
+    } else if (warp == 4) {
+      // ===================== MMA issuer =====================
+      if (elect_one()) {
+        mbar_wait(bar_w, 0);
+        CV_TRACE(li, 3);
+        constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_CH);
+        const uint64_t b_base = umma_desc_sw128_kmajor(sB);
+        for (int tl = 0; tl < my_tiles; ++tl) {
+          const int s = tl % CV_NS, buf = tl & 1;
+          if (tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
+          mbar_wait(bar_full + 8 * s, (tl / CV_NS) & 1);
+          if (tl == 0) CV_TRACE(li, 4);
+          if (tl == 1) CV_TRACE(li, 5);
+          if (tl == my_tiles - 1) CV_TRACE(li, 6);
+          tc_fence_after();
+          const uint64_t a_base = umma_desc_sw128_kmajor(sA + s * CV_ASTAGE);
+          const uint32_t d = tmem_d + buf * CV_CH;
 #pragma unroll
-      for (int c = 0; c < HC; ++c) csum[c] = 0.f;
-    };
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      const int buf = tl & 1;
-      const int tile = first + tl * (int)gridDim.x;
-      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-      if (n != cur_n) { flush(); cur_n = n; }
-      const int oy = (rem / tiles_x) * CV_TR + q, ox = (rem % tiles_x) * CV_TC + lane;
-      const bool valid = lane < CV_TC && oy < H && ox < W;
-      mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
-      tc_fence_after();
-      uint32_t acc[HC];
-      tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH + chalf * HC, acc);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-      float f[HC];
+          for (int t = 0; t < 9; ++t) {
 #pragma unroll
-      for (int c = 0; c < HC; ++c) {
-        const float t = __uint_as_float(acc[c]) + bsm[c];
-        f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
-      }
-      if (valid) {
-        __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH + chalf * HC;
-#pragma unroll
-        for (int c = 0; c < HC; c += 16) {                   // one full 32-byte sector per store
-          uint32_t u[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[c + 2 * e], f[c + 2 * e + 1]);
-          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(op + c), "r"(u[0]), "r"(u[1]),
-                       "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
-                       : "memory");
+            for (int k = 0; k < 4; ++k) {
+              // tap view: start (r*32 + s) rows further; K step = 32 B.  The swizzle XOR is taken from the
+              // absolute shared-memory address bits, so the shifted view needs no base_offset (measured:
+              // base_offset = s gives wrong results, 0 is exact).
+              const uint64_t adesc = a_base + (uint64_t)((((t / 3) * CV_PW + (t % 3)) * 128) >> 4) + 2 * k;
+              const uint64_t bdesc = b_base + (uint64_t)((t * CV_BTILE) >> 4) + 2 * k;
+              umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+          umma_commit(bar_accf + 8 * buf);
+          if (tl == my_tiles - 1) CV_TRACE(li, 7);
         }
       }
-      if (chan_sums) {
+      __syncwarp();
+    } else if (warp < 13) {
+      // ===================== epilogue (warps 5..12 -> TMEM lane quadrants 1,2,3,0, 1,2,3,0) =====================
+      const int q = warp & 3;                       // output row of the tile handled by this warp
+      const int chalf = (warp - 5) >> 2;            // this group's 32 output channels
+      constexpr int HC = CV_CH / 2;
+      float* const chan_sums = Ly.chan_sums;
+      __nv_bfloat16* const out = Ly.out;
+      const float slope = Ly.slope;
+      float csum[HC];                               // this thread's running channel sums (its pixels)
 #pragma unroll
-        for (int c = 0; c < HC; ++c) csum[c] += f[c];
+      for (int c = 0; c < HC; ++c) csum[c] = 0.f;
+      const float* bsm = reinterpret_cast<const float*>(smem + CvSmem::BIAS_OFF) + chalf * HC;
+      int cur_n = -1;
+      auto flush = [&]() {
+        if (chan_sums && cur_n >= 0) {
+          // transpose-reduce over the 32 lanes: 31 shuffles leave lane l with the sum of channel l of this half
+          // (step k adds (16 >> k) to the channel base when lane bit (16 >> k) is set: base = lane)
+#pragma unroll
+          for (int step = 0; step < 5; ++step) {
+            const int m = 16 >> step, len = 16 >> step;
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < len) {
+                const float send = up ? csum[i] : csum[i + len];
+                const float keep = up ? csum[i + len] : csum[i];
+                csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+              }
+            }
+          }
+          // four warps hold the same 32 channels: combine them in shared memory, one global atomic per
+          // channel and CTA (148 instead of 592 reductions on each of the 64 addresses)
+          float* red = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);
+          asm volatile("bar.sync 2, 256;\n" ::: "memory");       // previous flush fully drained
+          if (q == 0) red[chalf * HC + lane] = csum[0];
+          asm volatile("bar.sync 2, 256;\n" ::: "memory");
+          if (q != 0) atomicAdd(red + chalf * HC + lane, csum[0]);
+          asm volatile("bar.sync 2, 256;\n" ::: "memory");
+          if (q == 0) atomicAdd(chan_sums + cur_n * CV_CH + chalf * HC + lane, red[chalf * HC + lane]);
+        }
+#pragma unroll
+        for (int c = 0; c < HC; ++c) csum[c] = 0.f;
+      };
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int buf = tl & 1;
+        const int tile = first + tl * (int)gridDim.x;
+        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        if (n != cur_n) { flush(); cur_n = n; }
+        const int oy = (rem / tiles_x) * CV_TR + q, ox = (rem % tiles_x) * CV_TC + lane;
+        const bool valid = lane < CV_TC && oy < H && ox < W;
+        mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
+        if (warp == 5 && lane == 0) { if (tl == 0) CV_TRACE(li, 8); if (tl == my_tiles - 1) CV_TRACE(li, 9); }
+        tc_fence_after();
+        uint32_t acc[HC];
+        tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH + chalf * HC, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+        float f[HC];
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+          const float t = __uint_as_float(acc[c]) + bsm[c];
+          f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
+        }
+        if (valid) {
+          __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH + chalf * HC;
+#pragma unroll
+          for (int c = 0; c < HC; c += 16) {                   // one full 32-byte sector per store
+            uint32_t u[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[c + 2 * e], f[c + 2 * e + 1]);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(op + c), "r"(u[0]), "r"(u[1]),
+                         "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                         : "memory");
+          }
+        }
+        if (chan_sums) {
+#pragma unroll
+          for (int c = 0; c < HC; ++c) csum[c] += f[c];
+        }
       }
+      flush();
+      if (warp == 5 && lane == 0) CV_TRACE(li, 10);
     }
-    flush();
   }
 
   tc_fence_before();
@@ -384,18 +475,33 @@ extern "C" int eavsr_conv3x3_pack_weight(const void* weight, void* packed, int c
 
 namespace eavsr {
 namespace {
-int conv3x3_launch(const void* x, const void* packed_weight, const void* bias, void* out, float* channel_sums, int n,
-                   int cin, int cout, int h, int w, float negative_slope, int dtype, unsigned flags, CaFuse ca,
-                   cudaStream_t st, const char* who) {
-  EAVSR_REQUIRE(x && packed_weight && out, "%s: null pointer", who);
+// Common launch path: one layer = an ordinary launch, several = a cooperative launch (all CTAs must be resident
+// for the grid barrier between layers).
+int conv3x3_launch_chain(ChainParams& P, int n, int h, int w, int dtype, cudaStream_t st, const char* who) {
   EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "%s: empty tensor", who);
-  if (cin != CV_CH || cout != CV_CH || dtype != EAVSR_BF16) {
-    set_error("conv3x3: only 64->64 bf16 is implemented (got %d->%d, dtype %d)", cin, cout, dtype);
+  EAVSR_REQUIRE(P.nlayers >= 1 && P.nlayers <= CV_MAXL, "%s: 1..%d layers per launch (got %d)", who, CV_MAXL, P.nlayers);
+  if (dtype != EAVSR_BF16) {
+    set_error("conv3x3: only 64->64 bf16 is implemented (dtype %d)", dtype);
     return EAVSR_ERR_UNSUPPORTED;
   }
-  EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
-                  reinterpret_cast<uintptr_t>(packed_weight)) & 15u) == 0,
-                "%s: x / out / packed weights must be 16-byte aligned dense NHWC", who);
+  bool any_fused = false;
+  for (int i = 0; i < P.nlayers; ++i) {
+    const ConvLayerDev& L = P.L[i];
+    EAVSR_REQUIRE(L.x && L.wpacked && L.out, "%s: null pointer (layer %d)", who, i);
+    EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(L.x) | reinterpret_cast<uintptr_t>(L.out) |
+                    reinterpret_cast<uintptr_t>(L.wpacked)) & 15u) == 0,
+                  "%s: x / out / packed weights must be 16-byte aligned dense NHWC (layer %d)", who, i);
+    if (L.res) {
+      any_fused = true;
+      EAVSR_REQUIRE(L.res_sums && L.w1 && L.b1 && L.w2 && L.b2 && L.y_out, "%s: null pointer (fused layer %d)", who, i);
+      EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(L.res) | reinterpret_cast<uintptr_t>(L.y_out)) & 15u) == 0,
+                    "%s: res / y_out must be 16-byte aligned dense NHWC (layer %d)", who, i);
+    }
+  }
+  if (any_fused && n > CV_MAXN) {
+    set_error("%s: at most %d images per call with a fused channel-attention input (got %d)", who, CV_MAXN, n);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
   const int tiles_x = ceil_div(w, CV_TC), tiles_y = ceil_div(h, CV_TR);
   const int tiles_per_img = tiles_x * tiles_y;
   const long long total = (long long)tiles_per_img * n;
@@ -404,16 +510,24 @@ int conv3x3_launch(const void* x, const void* packed_weight, const void* bias, v
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(total < sms ? total : sms);
-  if (channel_sums && !(flags & EAVSR_CONV_SUMS_PREZEROED)) {
-    cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
-    if (em != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
-  }
+  P.H = h; P.W = w; P.tiles_x = tiles_x; P.tiles_per_img = tiles_per_img; P.total_tiles = (int)total; P.nimg = n;
+  P.inv_hw = 1.f / ((float)h * (float)w);
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem::DYN);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
-  conv3x3_tc_kernel<<<grid, CV_THREADS, CvSmem::DYN, st>>>((const __nv_bfloat16*)x, (const uint8_t*)packed_weight,
-                                                          (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
-                                                          channel_sums, h, w, tiles_x, tiles_per_img, (int)total,
-                                                          negative_slope, ca);
+  if (P.nlayers == 1) {
+    P.sync = nullptr;
+    conv3x3_tc_kernel<<<grid, CV_THREADS, CvSmem::DYN, st>>>(P);
+    return check_launch(who);
+  }
+  EAVSR_REQUIRE(P.sync && (reinterpret_cast<uintptr_t>(P.sync) & 3u) == 0, "%s: a chain needs a 4-byte sync workspace", who);
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) { set_error("%s: device has no cooperative launch", who); return EAVSR_ERR_UNSUPPORTED; }
+  e = cudaMemsetAsync(P.sync, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  void* args[] = {&P};
+  e = cudaLaunchCooperativeKernel((const void*)conv3x3_tc_kernel, dim3(grid), dim3(CV_THREADS), args, CvSmem::DYN, st);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("%s: cooperative launch: %s", who, cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
   return check_launch(who);
 }
 }  // namespace
@@ -422,9 +536,21 @@ int conv3x3_launch(const void* x, const void* packed_weight, const void* bias, v
 extern "C" int eavsr_conv3x3_forward(const void* x, const void* packed_weight, const void* bias, void* out,
                                      float* channel_sums, int n, int cin, int cout, int h, int w,
                                      float negative_slope, int dtype, unsigned flags, void* stream) {
-  CaFuse ca{};
-  return conv3x3_launch(x, packed_weight, bias, out, channel_sums, n, cin, cout, h, w, negative_slope, dtype, flags,
-                        ca, (cudaStream_t)stream, "conv3x3_forward");
+  if (cin != CV_CH || cout != CV_CH) {
+    set_error("conv3x3: only 64->64 bf16 is implemented (got %d->%d, dtype %d)", cin, cout, dtype);
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channel_sums && !(flags & EAVSR_CONV_SUMS_PREZEROED) && n > 0) {
+    cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
+    if (em != cudaSuccess) { set_error("conv3x3_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
+  }
+  static thread_local ChainParams P;
+  P.nlayers = 1;
+  P.L[0] = ConvLayerDev{(const __nv_bfloat16*)x, (const uint8_t*)packed_weight, (const __nv_bfloat16*)bias,
+                        (__nv_bfloat16*)out, channel_sums, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                        negative_slope, 0};
+  return conv3x3_launch_chain(P, n, h, w, dtype, st, "conv3x3_forward");
 }
 
 extern "C" int eavsr_conv3x3_ca_forward(const void* skip, const void* res, const float* res_sums, const void* w1,
@@ -433,14 +559,38 @@ extern "C" int eavsr_conv3x3_ca_forward(const void* skip, const void* res, const
                                         int n, int h, int w, float negative_slope, int dtype, unsigned flags,
                                         void* stream) {
   EAVSR_REQUIRE(skip && res && res_sums && w1 && b1 && w2 && b2 && y_out, "conv3x3_ca_forward: null pointer");
-  if (n > CV_MAXN) {
-    set_error("conv3x3_ca_forward: at most %d images per call (got %d)", CV_MAXN, n);
-    return EAVSR_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channel_sums && !(flags & EAVSR_CONV_SUMS_PREZEROED) && n > 0) {
+    cudaError_t em = cudaMemsetAsync(channel_sums, 0, (size_t)n * CV_CH * sizeof(float), st);
+    if (em != cudaSuccess) { set_error("conv3x3_ca_forward: memset: %s", cudaGetErrorString(em)); return EAVSR_ERR_CUDA; }
   }
-  EAVSR_REQUIRE(((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y_out)) & 15u) == 0,
-                "conv3x3_ca_forward: res / y_out must be 16-byte aligned dense NHWC");
-  CaFuse ca{(const __nv_bfloat16*)res, res_sums, (const __nv_bfloat16*)w1, (const __nv_bfloat16*)b1,
-            (const __nv_bfloat16*)w2, (const __nv_bfloat16*)b2, (__nv_bfloat16*)y_out, 1.f / ((float)h * (float)w), n};
-  return conv3x3_launch(skip, packed_weight, bias, out, channel_sums, n, CV_CH, CV_CH, h, w, negative_slope, dtype,
-                        flags, ca, (cudaStream_t)stream, "conv3x3_ca_forward");
+  static thread_local ChainParams P;
+  P.nlayers = 1;
+  P.L[0] = ConvLayerDev{(const __nv_bfloat16*)skip, (const uint8_t*)packed_weight, (const __nv_bfloat16*)bias,
+                        (__nv_bfloat16*)out, channel_sums, (const __nv_bfloat16*)res, res_sums,
+                        (const __nv_bfloat16*)w1, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)w2,
+                        (const __nv_bfloat16*)b2, (__nv_bfloat16*)y_out, negative_slope, 0};
+  return conv3x3_launch_chain(P, n, h, w, dtype, st, "conv3x3_ca_forward");
 }
+
+extern "C" int eavsr_conv3x3_chain_forward(const EavsrConvLayer* layers, int nlayers, int n, int h, int w, int dtype,
+                                           void* sync_workspace, void* stream) {
+  EAVSR_REQUIRE(layers && nlayers >= 1 && nlayers <= CV_MAXL, "conv3x3_chain_forward: 1..%d layers (got %d)", CV_MAXL, nlayers);
+  static thread_local ChainParams P;
+  P.nlayers = nlayers;
+  P.sync = (unsigned*)sync_workspace;
+  for (int i = 0; i < nlayers; ++i) {
+    const EavsrConvLayer& a = layers[i];
+    P.L[i] = ConvLayerDev{(const __nv_bfloat16*)a.x, (const uint8_t*)a.packed_weight, (const __nv_bfloat16*)a.bias,
+                          (__nv_bfloat16*)a.out, a.channel_sums, (const __nv_bfloat16*)a.res, a.res_sums,
+                          (const __nv_bfloat16*)a.w1, (const __nv_bfloat16*)a.b1, (const __nv_bfloat16*)a.w2,
+                          (const __nv_bfloat16*)a.b2, (__nv_bfloat16*)a.y_out, a.negative_slope, 0};
+  }
+  return conv3x3_launch_chain(P, n, h, w, dtype, (cudaStream_t)stream, "conv3x3_chain_forward");
+}
+
+#ifdef EAVSR_CONV_TRACE
+extern "C" int eavsr_debug_conv_trace(unsigned long long* host, int count) {
+  return (int)cudaMemcpyFromSymbol(host, g_conv_trace, sizeof(unsigned long long) * count);
+}
+#endif

@@ -25,7 +25,8 @@ import torch.nn.functional as F
 
 from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
-                  conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, flow_warp, flow_warp2, flow_warp_nhw2, fused_inference_ok,
+                  conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, conv3x3_chain_eligible, rca_group_chain,
+                  flow_warp, flow_warp2, flow_warp_nhw2, fused_inference_ok,
                   modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
@@ -72,9 +73,14 @@ class _RCAGroup(nn.Module):
     def __init__(self, ch=64, nb=30):
         super().__init__()
         self.rg = nn.Sequential(*[_RCABlock(ch) for _ in range(nb)], nn.Conv2d(ch, ch, 3, 1, 1))
+        self.chain = True          # inference: run the group as one chained launch when eligible
 
     def forward(self, x):
         blocks = self.rg[:-1]
+        if self.chain and len(blocks) > 0 and conv3x3_chain_eligible(
+                [c for b in blocks for c in (b.res[0], b.res[2])] + [self.rg[-1]], x):
+            # the whole group -- 2 convolutions per block + the closing one -- as ONE cooperative tcgen05 launch
+            return rca_group_chain(list(blocks), self.rg[-1], x) + x
         if conv3x3_64_eligible(self.rg[-1], x) and x.shape[0] <= 8 and len(blocks) > 0:
             # tcgen05 chain with the channel attention of block i folded into the first convolution of block
             # i+1 (and of the last block into the group's closing convolution): 2 launches per block,

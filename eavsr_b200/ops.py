@@ -40,6 +40,7 @@ __all__ = [
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
+    "conv3x3_chain_eligible", "rca_group_chain",
 ]
 
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
@@ -788,6 +789,68 @@ def conv3x3_64_ca(conv: nn.Conv2d, skip, res, res_sums, w1, b1, w2, b2, negative
                 "conv3x3_ca_forward")
         del w1d, b1d, w2d, b2d
     return (out, y, sums) if want_sums else (out, y)
+
+
+def conv3x3_chain_eligible(convs, x) -> bool:
+    """True when `rca_group_chain` can run the whole residual group in one launch."""
+    return (len(convs) >= 2 and len(convs) <= 64 and x.dim() == 4 and x.shape[0] <= 8
+            and all(conv3x3_64_eligible(c, x) for c in convs))
+
+
+def rca_group_chain(blocks, tail_conv, x):
+    """``tail_conv(RCAB_k(...RCAB_1(x)))`` of an RCAGroup (models/networks.py:449-482; the caller adds the group's
+    skip) as ONE cooperative launch of the tcgen05 convolution (eavsr_conv3x3_chain_forward): 2 layers per block --
+    conv + ReLU with the previous block's channel attention folded into its input, conv + channel sums -- and the
+    closing convolution.  ``blocks``: modules with ``res[0]``, ``res[2]`` (3x3 convs) and ``ca.conv_du`` (the
+    squeeze-excite 1x1 convs); inference only (check `conv3x3_chain_eligible`)."""
+    lib = L.load()
+    n, c, h, w = x.shape
+    dev = x.device
+    with torch.cuda.device(dev):
+        xd = x.contiguous(memory_format=torch.channels_last)
+        # activations: h (conv1 output), res (conv2 output), y ping-pong (block outputs); sums one row per block
+        hbuf, rbuf, out = torch.empty_like(xd), torch.empty_like(xd), torch.empty_like(xd)
+        ybuf = [torch.empty_like(xd), torch.empty_like(xd)]
+        pool = torch.zeros((len(blocks), n, 64), dtype=torch.float32, device=dev)
+        sync = torch.empty(1, dtype=torch.int32, device=dev)
+        keep = []                      # converted parameters must outlive the launch
+
+        def par(t):
+            t = _as(t, torch.bfloat16)
+            keep.append(t)
+            return t.data_ptr()
+
+        layers = []
+        y = xd
+        for i, blk in enumerate(blocks):
+            c1, c2 = blk.res[0], blk.res[2]
+            if i == 0:
+                layers.append(dict(x=y, conv=c1, out=hbuf, slope=0.0))
+            else:
+                du = blocks[i - 1].ca.conv_du
+                ynew = ybuf[i & 1]
+                layers.append(dict(x=y, conv=c1, out=hbuf, slope=0.0, res=rbuf, res_sums=pool[i - 1], du=du, y_out=ynew))
+                y = ynew
+            layers.append(dict(x=hbuf, conv=c2, out=rbuf, slope=1.0, sums=pool[i]))
+        du = blocks[-1].ca.conv_du
+        layers.append(dict(x=y, conv=tail_conv, out=out, slope=1.0, res=rbuf, res_sums=pool[len(blocks) - 1], du=du,
+                           y_out=ybuf[len(blocks) & 1]))
+        arr = (L.ConvLayer * len(layers))()
+        for a, d in zip(arr, layers):
+            conv = d["conv"]
+            a.x, a.out = d["x"].data_ptr(), d["out"].data_ptr()
+            a.packed_weight = _packed_conv_weight(conv, dev).data_ptr()
+            a.bias = par(conv.bias) if conv.bias is not None else None
+            a.channel_sums = d["sums"].data_ptr() if "sums" in d else None
+            a.negative_slope = d["slope"]
+            if "res" in d:
+                du = d["du"]
+                a.res, a.res_sums, a.y_out = d["res"].data_ptr(), d["res_sums"].data_ptr(), d["y_out"].data_ptr()
+                a.w1, a.b1, a.w2, a.b2 = par(du[0].weight), par(du[0].bias), par(du[2].weight), par(du[2].bias)
+        L.check(lib.eavsr_conv3x3_chain_forward(arr, len(layers), n, h, w, L.BF16, sync.data_ptr(), _stream(xd)),
+                "conv3x3_chain_forward")
+        del keep
+    return out
 
 
 def ca_scale(res, skip, sums, w1, b1, w2, b2, reduction: int = 16, res_bias=None):

@@ -247,6 +247,31 @@ int eavsr_conv3x3_ca_forward(const void* skip, const void* res, const float* res
                              const void* packed_weight, const void* bias, void* out, float* channel_sums, int n,
                              int h, int w, float negative_slope, int dtype, unsigned flags, void* stream);
 
+/* A whole chain of such convolutions -- the 61 of one RCAGroup (models/networks.py:467-482) -- in ONE cooperative
+ * launch: layer i + 1 reads what layer i wrote (grid-wide barrier between layers), the launch gap, TMEM allocation
+ * and cold weight load that a launch per convolution pays are paid once, and the next layer's weights stream in
+ * while a CTA waits at the barrier.  Each layer is eavsr_conv3x3_forward (res == NULL) or eavsr_conv3x3_ca_forward
+ * (res != NULL, `x` is the skip tensor).  channel_sums buffers must be ZERO on entry (as with
+ * EAVSR_CONV_SUMS_PREZEROED).  Buffers may be recycled between layers (activations are read through L2 only).
+ * sync_workspace: 4 bytes of device memory (the call zero-fills it).  nlayers <= 64, n <= 8 when any layer is fused. */
+typedef struct EavsrConvLayer {
+  const void* x;              /* input, or the skip tensor of the fused mode */
+  const void* packed_weight;  /* eavsr_conv3x3_pack_weight image */
+  const void* bias;           /* (64) bf16 or NULL */
+  void* out;
+  float* channel_sums;        /* (n, 64) fp32, zeroed, or NULL */
+  const void* res;            /* fused channel-attention input, or NULL */
+  const float* res_sums;
+  const void* w1;
+  const void* b1;
+  const void* w2;
+  const void* b2;
+  void* y_out;
+  float negative_slope;
+} EavsrConvLayer;
+int eavsr_conv3x3_chain_forward(const EavsrConvLayer* layers, int nlayers, int n, int h, int w, int dtype,
+                                void* sync_workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

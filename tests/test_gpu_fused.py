@@ -278,3 +278,46 @@ def test_flow_warp2_equals_two_warps(cuda, pad):
     # not eligible (fp32): falls back to two calls
     o1, o2 = ops.flow_warp2(a.float(), b.float(), flow)
     assert torch.allclose(o1, ops.flow_warp(a.float(), flow)) and o2.dtype == torch.float32
+
+
+@pytest.mark.parametrize("nb,shape", [(1, (1, 24, 60)), (3, (2, 37, 53)), (5, (1, 68, 120)), (30, (1, 272, 480))])
+def test_rca_group_chain_equals_launch_per_convolution(cuda, nb, shape):
+    """Row f3: the whole RCAGroup in ONE cooperative launch (eavsr_conv3x3_chain_forward: grid barrier between
+    layers, recycled activation buffers read through L2) == the launch-per-convolution tcgen05 path, and both ==
+    the PyTorch modules in fp64 up to bf16 rounding."""
+    from eavsr_b200 import _lib
+    n, h, w = shape
+    g = torch.Generator().manual_seed(70 + nb)
+    grp = M._RCAGroup(64, nb)
+    with torch.no_grad():
+        for p in grp.parameters():
+            p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * (0.04 if p.dim() > 1 else 0.1))
+    ref_mod = grp.double() if nb <= 5 else None
+    x = torch.randn(n, 64, h, w, generator=g)
+    ref = None
+    if ref_mod is not None:
+        with torch.no_grad():
+            y = x.bfloat16().double()
+            for blk in ref_mod.rg[:-1]:
+                y = blk.ca(blk.res(y)) + y
+            ref = ref_mod.rg[-1](y) + x.bfloat16().double()
+    grp = grp.to(cuda, torch.bfloat16).to(memory_format=torch.channels_last)
+    xb = _cl(x.to(cuda, torch.bfloat16))
+    with torch.no_grad():
+        grp.chain = False
+        grp(xb)                              # first call packs the weights (one extra launch per convolution)
+        n0 = _lib.launch_count()
+        per_conv = grp(xb)
+        n1 = _lib.launch_count()
+        grp.chain = True
+        chained = grp(xb)
+        n2 = _lib.launch_count()
+        again = grp(xb)                      # recycled buffers / re-armed grid barrier: a second call is the same
+    assert n1 - n0 == 2 * nb + 1 and n2 - n1 == 1
+    rms = per_conv.float().pow(2).mean().sqrt().item()
+    # the channel sums are accumulated with atomics in a different order: equal up to that rounding
+    assert (chained.float() - per_conv.float()).abs().max().item() <= 2e-2 * rms
+    assert (chained.float() - per_conv.float()).pow(2).mean().sqrt().item() <= 2e-3 * rms
+    assert (again.float() - chained.float()).abs().max().item() <= 2e-2 * rms
+    if ref is not None:
+        assert (chained.double().cpu() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
