@@ -24,6 +24,7 @@ DCN_WS_PACKED = 16
 DCN_BWD_GENERIC_DATA = 32
 DCN_BWD_GENERIC_WEIGHT = 64
 CONV_SUMS_PREZEROED = 1
+CORR_TF32 = 2
 
 Strides = c_int64 * 4
 _P64 = POINTER(c_int64)
@@ -66,6 +67,8 @@ _SIGNATURES = {
                                  [c_int] * 5 + [c_void_p, c_size_t, c_uint, c_void_p]),
     "eavsr_correlation_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),
+    "eavsr_correlation_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint,
+                                             c_void_p]),
     "eavsr_correlation_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_int, c_int, c_void_p]),
     "eavsr_adapt_mix_forward": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_float, c_int, c_void_p]),

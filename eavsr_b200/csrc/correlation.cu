@@ -422,14 +422,298 @@ bool make_corr_map(CUtensorMap* tm, const void* base, int n, int c, int h, int w
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+// ---- fp32 cost volume on tcgen05 (kind::tf32), straight from the reference's NCHW layout ------------------
+// The SIMT kernels above sit at the shared-memory pipe (10 LDS.128 per 108 FMAs and thread, profiles/
+// r1_corr_fwd_tma_ncu.txt): the 70 %-of-HBM target needs the multiply-adds on the tensor cores.  Banded GEMM:
+// for a 4-row x 32-column block of pixels (M = 128) and the 12 x 32 halo box of `second` that starts 4 pixels up
+// and to the left (N = 384),
+//     D[pixel m, halo j] = sum_c first[c, m] * second[c, j]                    (K = C, 8 channels per MMA)
+// and the 81 outputs of pixel (r, cx) are the entries j = (r + a) * 32 + cx + b, a, b = 0..8.  A 32-wide halo row
+// serves pixel columns cx <= 23, so tiles advance by 24 pixels in x (the last 8 MMA rows of every pixel row are
+// recomputed by the next tile): ~20 % of D is used, but the tensor pipe has several times the throughput to spare.
+//   * Operands are consumed MN-MAJOR, i.e. exactly as NCHW stores them (x contiguous, channel = the K row): one
+//     elected thread issues two cp.async.bulk.tensor per 8-channel chunk with tensor maps over (x, c, y, n) --
+//     that dimension order makes the TMA unit write [row][channel][32 px] = the canonical MN-major atoms -- zero-
+//     filling the image border and the channel tail.  No rearrange / pad pass (the reference runs two,
+//     correlation.py:8-33), no transposes.  32-bit MN-major operands exist in ONE swizzle mode only: 128-byte
+//     swizzle with 32-byte atomicity (UMMA layout type SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+//     atoms of 4 K-rows x 128 B, SBO = 512 B between K atoms, LBO = 1 KB between MN atoms); a first version with
+//     SWIZZLE_64B / SWIZZLE_128B operands computed nothing at all (the accumulator stayed zero).
+//   * fp32 accumulators: 384 TMEM columns.  8 epilogue warps (two per TMEM lane quadrant = pixel row) read a halo
+//     row (32 columns) per lane with tcgen05.ld, pick the 9 that belong to their pixel with a 5-level select
+//     network on cx (a per-lane register array cannot be indexed dynamically), scale by 1 / C and store -- 24
+//     consecutive lanes write 96 contiguous bytes of one (displacement, row).
+//   * The band goes through a [81][4][24] shared-memory staging buffer and ONE bulk tensor store per tile (clipped
+//     at the image border by the TMA unit), so TMEM is released before the stores drain.
+//   * OPT-IN (flag EAVSR_CORR_TF32), not the default, for two measured reasons (30x32x80x128, 178 MB):
+//       - kind::tf32 TRUNCATES the inputs to 10 mantissa bits: max-abs error 0.8e-3 (C = 32) ... 2.5e-3 (C = 5) on
+//         unit-variance features, i.e. at / over the 1e-3 fp32 bound of BASELINE.json, where the SIMT kernels are exact;
+//       - 52 us = the SIMT kernel's time (0.52 of the HBM roofline), not the ~30 us the MMA count promised: loads +
+//         MMAs alone take 26 us (the 12 x 32 halo box per 4 x 24 pixels is a 4x amplification of `second`: 230 MB
+//         through L2 -> TMA at ~128-byte rows), the band extraction another ~25 us (47-63 selects + 9 stores per
+//         halo row and lane), and with 384 of 512 TMEM columns taken by one accumulator the two cannot overlap.
+//     What would fix it -- 8-row pixel tiles sharing one halo stage, a second accumulator -- does not fit TMEM.
+namespace tc {
+constexpr int PT_H = 4, PT_W = 32, PT_STEP = 24;   // MMA rows per tile: 4 x 32 pixels, of which 4 x 24 are stored
+constexpr int HB_H = PT_H + 2 * D, HB_W = 32;       // halo box (12 x 32)
+constexpr int KC = 8;                              // channels per stage = one kind::tf32 K step
+constexpr int A_BYTES = PT_H * KC * PT_W * 4;      // 4 KB   [y][c][32 px]
+constexpr int B_BYTES = HB_H * KC * HB_W * 4;      // 12 KB  [hy][c][32 px]
+constexpr int STAGE = A_BYTES + B_BYTES;           // 16 KB
+constexpr int NST = 8;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;      // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue
+constexpr int NCOLS = HB_H * HB_W;                 // 384 accumulator columns
+constexpr int OUT_BYTES = ND * ND * PT_H * PT_STEP * 4;   // 31 104 B: [81][4 rows][24 px] of one tile, TMA-stored
+constexpr int OUT_OFF = NST * STAGE;               // two output staging buffers (128-byte aligned)
+constexpr int OUT_PITCH = (OUT_BYTES + 127) / 128 * 128;
+constexpr int BAR_OFF = OUT_OFF + 2 * OUT_PITCH;
+constexpr int BAR_BYTES = (2 * NST + 2) * 8 + 16;
+constexpr int DYN = BAR_OFF + BAR_BYTES + 1024;
+static_assert(DYN <= 232448, "shared memory budget");
+
+// 32-bit MN-major operand, SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 B (32 elements along MN);
+// LBO = byte stride between atoms along MN, SBO = byte stride between atoms along K
+__device__ __forceinline__ uint64_t desc_mn32(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                          // LayoutType::SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+#ifdef EAVSR_CORR_DEBUG     // development only: stage 0 as the TMA unit wrote it + the accumulator of CTA 0's first tile
+__device__ float g_corr_dbg[STAGE / 4 + 128 * NCOLS];
+#endif
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int x, int y, int d, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(x), "r"(y), "r"(d), "r"(n)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, int C, int H, int W, int tiles_x, int tiles_y, int total_tiles) {
+  extern __shared__ uint8_t tc_smem[];
+  const uint32_t sbase = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  uint8_t* sgen = tc_smem + (sbase - smem_u32(tc_smem));
+  const uint32_t bars = sbase + BAR_OFF;
+  const uint32_t bar_full = bars, bar_empty = bars + NST * 8, bar_accf = bars + 2 * NST * 8, bar_acce = bar_accf + 8;
+  const uint32_t tmem_slot_addr = bar_acce + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + BAR_OFF + (2 * NST + 2) * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot_addr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const int nchunks = (C + KC - 1) / KC;
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+#define TILE_OF(tl) ((int)blockIdx.x + (tl) * (int)gridDim.x)
+  const int tiles_per_img = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int cnt = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int tile = TILE_OF(tl);
+        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        const int y0 = (rem / tiles_x) * PT_H, x0 = (rem % tiles_x) * PT_STEP;
+        for (int k = 0; k < nchunks; ++k, ++cnt) {
+          const int s = cnt % NST;
+          if (cnt >= NST) mbar_wait(bar_empty + 8 * s, ((cnt / NST) - 1) & 1);
+          const uint32_t full = bar_full + 8 * s, dst = sbase + s * STAGE;
+          mbar_arrive_expect_tx(full, STAGE);
+          // tensor-map dimensions are (x, c, y, n)
+          tma_load_4d(dst, &tmB, x0 - D, k * KC, y0 - D, n, full);
+          tma_load_4d(dst + B_BYTES, &tmA, x0, k * KC, y0, n, full);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t IDESC_256 = idesc_tf32_mn(128, 256), IDESC_128 = idesc_tf32_mn(128, 128);
+      int cnt = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        if (tl >= 1) mbar_wait(bar_acce, (tl - 1) & 1);        // the epilogue has read tile tl-1 out of TMEM
+        tc_fence_after();
+        for (int k = 0; k < nchunks; ++k, ++cnt) {
+          const int s = cnt % NST;
+          mbar_wait(bar_full + 8 * s, (cnt / NST) & 1);
+          tc_fence_after();
+          const uint32_t sb = sbase + s * STAGE, sa = sb + B_BYTES;
+          const uint64_t adesc = desc_mn32(sa, 1024, 512);
+          const uint64_t bdesc = desc_mn32(sb, 1024, 512);
+          umma_tf32(tmem_d, adesc, bdesc, IDESC_256, k != 0);                                    // halo rows 0-7
+          umma_tf32(tmem_d + 256, adesc, bdesc + (uint64_t)((8 * 1024) >> 4), IDESC_128, k != 0);   // halo rows 8-11
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_accf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: band extraction -> shared memory -> TMA store =====================
+    // Stores straight from registers (81 planes x 96-byte pieces per tile) cost more than everything else together
+    // (ablation: 72 us with them, 29 us without), and with a single 384-column accumulator they also held up the
+    // next tile's MMAs.  The band goes to a [81][4][24] staging buffer instead, TMEM is released, and ONE bulk
+    // tensor store per tile (clipped at the image border by the TMA unit) drains it while the next tile runs.
+    const int q = warp & 3;                         // TMEM lane quadrant = pixel row of the tile
+    const int half = (warp - 2) >> 2;               // halo rows q .. q+4 (half 0) / q+5 .. q+8 (half 1)
+    const int cx = lane;                            // pixel column (kept when < PT_STEP)
+    const float inv = 1.f / (float)C;
+    const bool b4 = cx & 16, b3 = cx & 8, b2 = cx & 4, b1 = cx & 2, b0 = cx & 1;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = TILE_OF(tl);
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int y0 = (rem / tiles_x) * PT_H, x0 = (rem % tiles_x) * PT_STEP;
+      float* so = reinterpret_cast<float*>(sgen + OUT_OFF + (tl & 1) * OUT_PITCH) + q * PT_STEP + cx;
+      mbar_wait(bar_accf, tl & 1);
+      tc_fence_after();
+#ifdef EAVSR_CORR_DEBUG
+      if (blockIdx.x == 0 && tl == 0) {
+        if (half == 0) {
+          for (int col = 0; col < NCOLS; col += 32) {
+            uint32_t t32[32];
+            tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + col, t32);
+            tmem_ld_wait();
+            for (int e = 0; e < 32; ++e) g_corr_dbg[STAGE / 4 + (q * 32 + lane) * NCOLS + col + e] = __uint_as_float(t32[e]);
+          }
+        }
+        if (warp == 2)
+          for (int e = lane; e < STAGE / 4; e += 32) g_corr_dbg[e] = reinterpret_cast<const float*>(sgen)[e];
+      }
+#endif
+      const int a_lo = half * 5, a_hi = half ? ND : 5;
+#pragma unroll 1
+      for (int a = a_lo; a < a_hi; ++a) {           // displacement row a <-> halo row q + a (warp-uniform)
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + (q + a) * HB_W, v);
+        tmem_ld_wait();
+        // w0[b] = v[cx + b], cx = 0..23: shift by 16 (only cx >= 16, i.e. then by < 8 more), 8, 4, 2, 1
+        uint32_t w4[24], w3[16], w2[12], w1[10], w0[9];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w4[j] = b4 ? v[j + 16] : v[j];
+#pragma unroll
+        for (int j = 16; j < 24; ++j) w4[j] = v[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w3[j] = b3 ? w4[j + 8] : w4[j];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) w2[j] = b2 ? w3[j + 4] : w3[j];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) w1[j] = b1 ? w2[j + 2] : w2[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) w0[j] = b0 ? w1[j + 1] : w1[j];
+        if (cx < PT_STEP) {
+#pragma unroll
+          for (int b = 0; b < ND; ++b) so[(a * ND + b) * (PT_H * PT_STEP)] = __uint_as_float(w0[b]) * inv;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce);          // TMEM is free: the next tile's MMAs may start
+      fence_proxy_async_smem();                      // staging writes -> visible to the TMA store
+      if (warp == 2 && lane == 0)                    // the store of tile tl-1 has read its buffer: tile tl+1 may fill it
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");
+      if (warp == 2 && lane == 0) {
+        tma_store_4d(&tmO, sbase + OUT_OFF + (tl & 1) * OUT_PITCH, x0, y0, 0, n);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
+    }
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_d);
+}
+
+// (x, c, y, n) view of an NCHW fp32 tensor with a [32 x KC x box_h x 1] box: the TMA unit then writes
+// [row][channel][32 px], the MN-major operand layout; zero fill outside (image border, channel tail)
+bool make_map(CUtensorMap* tm, const void* base, int n, int c, int h, int w, int box_h) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)c, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)w * h * 4, (cuuint64_t)w * 4, (cuuint64_t)w * h * c * 4};
+  const cuuint32_t box[4] = {32, (cuuint32_t)KC, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns -1 when this shape is not eligible (caller falls back to the SIMT kernels)
+int launch(const void* f1, const void* f2, void* out, int n, int c, int h, int w, cudaStream_t st) {
+  const bool ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15u) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(f2) & 15u) == 0) && (long long)w * h * c * 4 < (1ll << 40) &&
+                  (long long)h * w > 256 && (long long)n * 81 * h * w < (1ll << 40);
+  if (!ok) return -1;
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return -1;
+  CUtensorMap tmA, tmB, tmO;
+  if (!make_map(&tmA, f1, n, c, h, w, PT_H) || !make_map(&tmB, f2, n, c, h, w, HB_H)) return -1;
+  {  // (x, y, displacement, n) view of the output with a [24 x 4 x 81 x 1] box, no swizzle
+    EncodeTiledFn enc = encode_tiled_fn();
+    const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(ND * ND), (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4, (cuuint64_t)w * h * ND * ND * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)PT_STEP, (cuuint32_t)PT_H, (cuuint32_t)(ND * ND), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!enc || enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+                    CUDA_SUCCESS)
+      return -1;
+  }
+  cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN);
+  if (e != cudaSuccess) { set_error("correlation_forward(tc): smem attr: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_x = ceil_div(w, PT_STEP), tiles_y = ceil_div(h, PT_H);
+  const long long total = (long long)tiles_x * tiles_y * n;
+  if (total >= (1ll << 31)) return -1;
+  const int ctas = (int)(total < sms ? total : sms);
+  corr_fwd_tc<<<ctas, THREADS, DYN, st>>>(tmA, tmB, tmO, c, h, w, tiles_x, tiles_y, (int)total);
+  return check_launch("correlation_forward(tcgen05)");
+}
+}  // namespace tc
+
 template <typename T>
-int corr_forward_t(const void* f1, const void* f2, void* out, int n, int c, int h, int w, cudaStream_t st) {
+int corr_forward_t(const void* f1, const void* f2, void* out, int n, int c, int h, int w, cudaStream_t st, unsigned flags = 0) {
   if (h * w <= 256) {                       // PWC pyramid of 64x64 training crops: 1x1 ... 16x16
     const long long total = (long long)n * ND * ND * h * w;
     corr_fwd_small<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)f1, (const T*)f2, (T*)out, n, c, h, w);
     return check_launch("correlation_forward(small)");
   }
   dim3 grid(ceil_div(w, TW), ceil_div(h, TH), n);
+  if (sizeof(T) == 4 && (flags & EAVSR_CORR_TF32)) {       // opt-in: tcgen05 / tf32 (see the kernel's header comment)
+    const int rc = tc::launch(f1, f2, out, n, c, h, w, st);
+    if (rc >= 0) return rc;
+  }
   if (sizeof(T) == 4) {
     const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(f2) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
@@ -593,15 +877,20 @@ int corr_backward_t(const void* f1, const void* f2, const void* gout, void* g1, 
 
 using namespace eavsr;
 
-extern "C" int eavsr_correlation_forward(const void* first, const void* second, void* out, int n, int c, int h,
-                                         int w, int dtype, void* stream) {
+extern "C" int eavsr_correlation_forward_ex(const void* first, const void* second, void* out, int n, int c, int h,
+                                            int w, int dtype, unsigned flags, void* stream) {
   EAVSR_REQUIRE(first && second && out, "correlation_forward: null pointer");
   EAVSR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "correlation_forward: empty tensor");
   EAVSR_REQUIRE(n <= 65535 && ceil_div(h, TH) <= 65535, "correlation_forward: batch/height too large");
-  if (dtype == EAVSR_F32) return corr_forward_t<float>(first, second, out, n, c, h, w, (cudaStream_t)stream);
-  if (dtype == EAVSR_BF16) return corr_forward_t<__nv_bfloat16>(first, second, out, n, c, h, w, (cudaStream_t)stream);
+  if (dtype == EAVSR_F32) return corr_forward_t<float>(first, second, out, n, c, h, w, (cudaStream_t)stream, flags);
+  if (dtype == EAVSR_BF16) return corr_forward_t<__nv_bfloat16>(first, second, out, n, c, h, w, (cudaStream_t)stream, flags);
   set_error("correlation_forward: bad dtype %d", dtype);
   return EAVSR_ERR_INVALID;
+}
+
+extern "C" int eavsr_correlation_forward(const void* first, const void* second, void* out, int n, int c, int h,
+                                         int w, int dtype, void* stream) {
+  return eavsr_correlation_forward_ex(first, second, out, n, c, h, w, dtype, 0u, stream);
 }
 
 extern "C" int eavsr_correlation_backward(const void* first, const void* second, const void* gout, void* gfirst,
@@ -613,3 +902,9 @@ extern "C" int eavsr_correlation_backward(const void* first, const void* second,
   set_error("correlation_backward: bad dtype %d", dtype);
   return EAVSR_ERR_INVALID;
 }
+
+#ifdef EAVSR_CORR_DEBUG
+extern "C" int eavsr_debug_corr(float* host, int count) {
+  return (int)cudaMemcpyFromSymbol(host, eavsr::tc::g_corr_dbg, sizeof(float) * count);
+}
+#endif

@@ -481,6 +481,12 @@ class ModulatedDeformConv2d(nn.Module):
 # ------------------------------------------------------------------------------------------
 # correlation
 # ------------------------------------------------------------------------------------------
+# Opt-in: fp32 cost volumes larger than 16x16 (w % 4 == 0) as a banded GEMM on tcgen05 in tf32.  tf32 truncates the
+# inputs to 10 mantissa bits (max-abs error 0.8e-3 .. 2.5e-3 on unit-variance features, the fp32 bound is 1e-3) and
+# the kernel is no faster than the exact fp32 path yet (csrc/correlation.cu), so the default stays exact.
+CORRELATION_TF32 = False
+
+
 class _FunctionCorrelation(Function):
     @staticmethod
     def forward(ctx, first, second):
@@ -496,8 +502,9 @@ class _FunctionCorrelation(Function):
             code = _dtype_code("FunctionCorrelation", first)
             second = second.to(first.dtype)
             out = first.new_empty((n, 81, h, w))
-            L.check(lib.eavsr_correlation_forward(first.data_ptr(), second.data_ptr(), out.data_ptr(), n, c, h, w,
-                                                  code, _stream(first)), "correlation_forward")
+            L.check(lib.eavsr_correlation_forward_ex(first.data_ptr(), second.data_ptr(), out.data_ptr(), n, c, h, w,
+                                                     code, L.CORR_TF32 if CORRELATION_TF32 else 0,
+                                                     _stream(first)), "correlation_forward")
         ctx.save_for_backward(first, second)
         return out
 

@@ -169,6 +169,13 @@ int eavsr_dcn_backward(const void* gout, const int64_t gout_strides[4], const vo
  * out[n,(dy+4)*9+(dx+4),y,x] = 1/c * sum_ch first[n,ch,y,x]*second[n,ch,y+dy,x+dx]. */
 int eavsr_correlation_forward(const void* first, const void* second, void* out, int n, int c, int h, int w,
                               int dtype, void* stream);
+/* Same with flags.  EAVSR_CORR_TF32 (opt-in): fp32 maps larger than 16x16 with w % 4 == 0 run as a banded GEMM on
+ * tcgen05 (kind::tf32, operands MN-major straight from NCHW through TMA).  tf32 truncates the inputs to 10 mantissa
+ * bits: max-abs error 0.8e-3 .. 2.5e-3 on unit-variance features (the fp32 bound of BASELINE.json is 1e-3), which is
+ * why the exact fp32 SIMT kernels stay the default. */
+#define EAVSR_CORR_TF32 2u
+int eavsr_correlation_forward_ex(const void* first, const void* second, void* out, int n, int c, int h, int w,
+                                 int dtype, unsigned flags, void* stream);
 /* gfirst/gsecond: (n,c,h,w) same dtype, either may be NULL. */
 int eavsr_correlation_backward(const void* first, const void* second, const void* gout, void* gfirst,
                                void* gsecond, int n, int c, int h, int w, int dtype, void* stream);

@@ -162,6 +162,7 @@ def bench_dcn_affine():
 
 
 def bench_corr():
+    fwd_only = os.environ.get("CORR_FWD_ONLY") == "1"
     for n, c, h, w in ((30, 32, 80, 128), (30, 64, 40, 64), (30, 96, 20, 32), (30, 128, 10, 16), (30, 196, 5, 8),
                        (8, 32, 16, 16), (8, 196, 1, 1)):
         each = 2 * n * c * h * w * 4
@@ -170,10 +171,12 @@ def bench_corr():
         b = [torch.randn(n, c, h, w, device=dev) for _ in range(k)]
         sec = timeit(lambda i: E.FunctionCorrelation(tenFirst=a[i % k], tenSecond=b[i % k]), 50)
         rec(f"correlation fwd f32 {n}x{c}x{h}x{w}", sec, n * h * w * (2 * c + 81) * 4, 2.0 * 81 * c * n * h * w)
+        if fwd_only:
+            continue
         ag, bg = a[0].clone().requires_grad_(), b[0].clone().requires_grad_()
         out = E.FunctionCorrelation(tenFirst=ag, tenSecond=bg)
         go = torch.randn_like(out)
-        sec = timeit(lambda i: torch.autograd.grad(out, [ag, bg], go, retain_graph=True), 10)
+        sec = timeit(lambda i: torch.autograd.grad(out, [ag, bg], go, retain_graph=True), 10, graph=False)
         rec(f"correlation bwd f32 {n}x{c}x{h}x{w}", sec, n * h * w * (4 * c + 81) * 4, 4.0 * 81 * c * n * h * w)
 
 
