@@ -35,6 +35,11 @@ class EavsrError(RuntimeError):
     pass
 
 
+class FlowTerm(ctypes.Structure):
+    """EavsrFlowTerm of include/eavsr_b200.h (one term of a pyramid flow)."""
+    _fields_ = [("flow", c_void_p), ("scaled_out", c_void_p), ("h", c_int), ("w", c_int), ("scale", c_float)]
+
+
 class ConvLayer(ctypes.Structure):
     """EavsrConvLayer of include/eavsr_b200.h (one convolution of eavsr_conv3x3_chain_forward)."""
     _fields_ = [("x", c_void_p), ("packed_weight", c_void_p), ("bias", c_void_p), ("out", c_void_p),
@@ -53,6 +58,9 @@ _SIGNATURES = {
                                          c_int, c_int, c_int, c_int, c_void_p]),
     "eavsr_flow_warp2_forward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, c_int, c_void_p, _P64, c_void_p, _P64] +
                                  [c_int] * 6 + [c_void_p]),
+    "eavsr_flow_warp_pyramid_forward": (c_int, [c_void_p, _P64, c_void_p, _P64, POINTER(FlowTerm), c_int, c_void_p, _P64,
+                                                c_void_p, _P64, _PF] + [c_int] * 6 + [c_void_p]),
+    "eavsr_spynet_level_input_forward": (c_int, [_PF, _PF, _PF, _PF] + [c_int] * 5 + [c_void_p]),
     "eavsr_backwarp_forward": (c_int, [c_void_p, _P64, _PF, c_void_p, _P64, c_void_p] + [c_int] * 5 + [c_void_p]),
     "eavsr_backwarp_backward": (c_int, [c_void_p, _P64, c_void_p, _P64, _PF, _PF, _P64, _PF] + [c_int] * 5 +
                                 [c_void_p]),

@@ -9,6 +9,8 @@
 // 8x16-pixel CTA tiles so that the 4 bilinear corners of neighbouring outputs hit L1, all four
 // 16-byte corner loads of a thread in flight together.  Algorithmic bytes per pixel:
 // 2*C*sizeof(T) + 8 (read x once, read flow, write out) -- see DESIGN.md.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace eavsr {
@@ -94,14 +96,78 @@ __device__ __forceinline__ void load_flow(const float* __restrict__ flow, int la
 // ------------------------------------------------------------------------------------------
 constexpr int LEAN_THREADS = 128;
 
+// Pyramid flows: MultiAdSTN.forward (models/networks.py:600-615) warps with flows that are
+// sums of bilinearly resized (align_corners=True), rescaled coarser / finer flow fields --
+//   level 3:  interp(offset, 1/4) / 4;   level 2:  interp(offset, 1/2) / 2 + interp(p1, 2) * 2;
+//   level 1:  offset + interp(p2 + p1_up, 2) * 2;    final:  p3 + p2_up + offset
+// -- each materialised by F.interpolate + an elementwise launch or two in the reference.  Here the lane <-> pixel
+// phase of the warp evaluates  flow(y, x) = sum_i scale_i * resize(flow_i)(y, x)  itself, with ATen's
+// upsample_bilinear2d arithmetic (source index = dst * (in - 1) / (out - 1), lambda = fraction); a term can also be
+// written out (`scaled_out`: level 2 keeps p1_up for level 1), and so can the sum (`flow_out`).
+constexpr int PYR_MAX = 4;
+struct PyrTerm {
+  const float* flow;   // (n, 2, h, w) fp32 contiguous
+  float* scaled_out;   // optional (n, 2, H, W): scale * resize(flow)
+  int h, w;
+  float scale, ry, rx; // ry = (h - 1) / (H - 1) (0 when H == 1)
+};
+struct PyrParams {
+  int nterms;
+  float* flow_out;     // optional (n, 2, H, W): the sum
+  PyrTerm t[PYR_MAX];
+};
+
+__device__ __forceinline__ void pyr_eval(const PyrParams& P, int n, int y, int x, int H, int W, float& fx, float& fy) {
+  fx = 0.f;
+  fy = 0.f;
+  const size_t opix = (size_t)y * W + x, oplane = (size_t)H * W;
+#pragma unroll
+  for (int i = 0; i < PYR_MAX; ++i) {
+    if (i < P.nterms) {
+      const PyrTerm& t = P.t[i];
+      float vx, vy;
+      const float* f0 = t.flow + (size_t)n * 2 * t.h * t.w;
+      const size_t pl = (size_t)t.h * t.w;
+      if (t.h == H && t.w == W) {
+        vx = __ldg(f0 + opix);
+        vy = __ldg(f0 + pl + opix);
+      } else {
+        const float sy = t.ry * (float)y, sx = t.rx * (float)x;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = (y0 < t.h - 1) ? t.w : 0, xp = (x0 < t.w - 1) ? 1 : 0;
+        const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+        const float* p = f0 + (size_t)y0 * t.w + x0;
+        vx = hy * (hx * __ldg(p) + lx * __ldg(p + xp)) + ly * (hx * __ldg(p + yp) + lx * __ldg(p + yp + xp));
+        p += pl;
+        vy = hy * (hx * __ldg(p) + lx * __ldg(p + xp)) + ly * (hx * __ldg(p + yp) + lx * __ldg(p + yp + xp));
+      }
+      vx *= t.scale;
+      vy *= t.scale;
+      if (t.scaled_out) {
+        t.scaled_out[(size_t)n * 2 * oplane + opix] = vx;
+        t.scaled_out[(size_t)n * 2 * oplane + oplane + opix] = vy;
+      }
+      fx += vx;
+      fy += vy;
+    }
+  }
+  if (P.flow_out) {
+    P.flow_out[(size_t)n * 2 * oplane + opix] = fx;
+    P.flow_out[(size_t)n * 2 * oplane + oplane + opix] = fy;
+  }
+  if (W == 1) fx = 0.f;
+  if (H == 1) fy = 0.f;
+}
+
 // DUAL: two feature maps warped with the same flow in one launch (nbr and feat_prop
 // in MultiAdSTN.forward, models/networks.py:621-623) -- the flow read and phase 1 are shared.
-template <typename T, int CPP, int PAD, bool DUAL = false>
+struct NoPyr {};
+template <typename T, int CPP, int PAD, bool DUAL = false, bool PYR = false>
 __global__ void __launch_bounds__(LEAN_THREADS)
 flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* __restrict__ out, int H, int W,
                    int layout, int tiles_x, int tiles_y, long long xs_n, long long os_n,
                    const T* __restrict__ x2 = nullptr, T* __restrict__ out2 = nullptr, long long xs2_n = 0,
-                   long long os2_n = 0) {
+                   long long os2_n = 0, const __grid_constant__ typename std::conditional<PYR, PyrParams, NoPyr>::type pyr = {}) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int C = CPP * VEC;
   constexpr int PPI = 32 / CPP;          // pixels per phase-2 iteration
@@ -122,7 +188,8 @@ flow_warp_fwd_lean(const T* __restrict__ x, const float* __restrict__ flow, T* _
   float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
   if (live) {
     float fx, fy;
-    load_flow(flow, layout, n, y, xq, H, W, fx, fy);
+    if constexpr (PYR) pyr_eval(pyr, n, y, xq, H, W, fx, fy);
+    else load_flow(flow, layout, n, y, xq, H, W, fx, fy);
     float sx = (float)xq + fx, sy = (float)y + fy;
     if (PAD == EAVSR_PAD_BORDER) {
       sx = fminf(fmaxf(sx, 0.f), (float)(W - 1));
@@ -479,6 +546,49 @@ backwarp_bwd_kernel(const T* __restrict__ gout, Strides4 gs, const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// SPyNet level input (SPyNet.compute_flow, models/eavsrp_model.py:468-486): per pyramid level
+// the reference runs F.interpolate(flow, 2) * 2, a permute, flow_warp(supp, ., 'border') and torch.cat([ref, warped,
+// flow_up]) -- five launches around three 3-channel images.  One kernel writes the 8-channel input of the level's
+// first 7x7 convolution: channels 0-2 ref, 3-5 supp warped (border padding) by up = 2 * resize_x2(flow_prev), 6-7 up.
+// NCHW fp32 (flows are coordinates: SPyNet stays fp32), one thread per pixel; flow_prev == NULL: up = 0 (level 0).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spynet_level_input_kernel(const float* __restrict__ ref, const float* __restrict__ supp,
+                          const float* __restrict__ flow_prev, float* __restrict__ out, int N, int H, int W, int hp,
+                          int wp, float ry, float rx) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  const size_t plane = (size_t)H * W, o = (size_t)y * W + x;
+  float ux = 0.f, uy = 0.f;
+  if (flow_prev) {
+    const float sy = ry * (float)y, sx = rx * (float)x;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int yp = (y0 < hp - 1) ? wp : 0, xp = (x0 < wp - 1) ? 1 : 0;
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = flow_prev + (size_t)n * 2 * hp * wp + (size_t)y0 * wp + x0;
+    ux = (hy * (hx * __ldg(p) + lx * __ldg(p + xp)) + ly * (hx * __ldg(p + yp) + lx * __ldg(p + yp + xp))) * 2.f;
+    p += (size_t)hp * wp;
+    uy = (hy * (hx * __ldg(p) + lx * __ldg(p + xp)) + ly * (hx * __ldg(p + yp) + lx * __ldg(p + yp + xp))) * 2.f;
+  }
+  const Corner c = make_corner<EAVSR_PAD_BORDER>((float)y + (H == 1 ? 0.f : uy), (float)x + (W == 1 ? 0.f : ux), H, W);
+  float* on = out + (size_t)n * 8 * plane + o;
+  const float* rn = ref + (size_t)n * 3 * plane + o;
+  const float* sn = supp + (size_t)n * 3 * plane;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    on[ch * plane] = __ldg(rn + ch * plane);
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c.ok[k]) r += c.wgt[k] * __ldg(sn + ch * plane + c.off[k]);
+    on[(3 + ch) * plane] = r;
+  }
+  on[6 * plane] = ux;
+  on[7 * plane] = uy;
+}
+
 bool is_nhwc_dense(const int64_t s[4], int c, int h, int w) {
   return s[1] == 1 && s[3] == c && s[2] == (int64_t)w * c && s[0] >= (int64_t)h * w * c;
 }
@@ -700,4 +810,69 @@ extern "C" int eavsr_backwarp_backward(const void* gout, const int64_t gout_stri
         (const __nv_bfloat16*)gout, a, (const __nv_bfloat16*)x, b, flow, gx32, g, gflow, n, c, h, w, ky, kx);
   else { set_error("backwarp_backward: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
   return check_launch("backwarp_backward");
+}
+
+extern "C" int eavsr_flow_warp_pyramid_forward(const void* x, const int64_t x_strides[4], const void* x2,
+                                               const int64_t x2_strides[4], const EavsrFlowTerm* terms, int nterms,
+                                               void* out, const int64_t out_strides[4], void* out2,
+                                               const int64_t out2_strides[4], float* flow_out, int n, int c, int h,
+                                               int w, int dtype, int padding_mode, void* stream) {
+  EAVSR_REQUIRE(x && terms && out && x_strides && out_strides, "flow_warp_pyramid_forward: null pointer");
+  EAVSR_REQUIRE(!x2 || (out2 && x2_strides && out2_strides), "flow_warp_pyramid_forward: x2 without out2");
+  EAVSR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "flow_warp_pyramid_forward: empty tensor");
+  EAVSR_REQUIRE(nterms >= 1 && nterms <= PYR_MAX, "flow_warp_pyramid_forward: 1..%d flow terms (got %d)", PYR_MAX, nterms);
+  EAVSR_REQUIRE(padding_mode == EAVSR_PAD_ZEROS, "flow_warp_pyramid_forward: zeros padding only");
+  PyrParams P{};
+  P.nterms = nterms;
+  P.flow_out = flow_out;
+  for (int i = 0; i < nterms; ++i) {
+    EAVSR_REQUIRE(terms[i].flow && terms[i].h > 0 && terms[i].w > 0, "flow_warp_pyramid_forward: bad term %d", i);
+    P.t[i] = PyrTerm{terms[i].flow, terms[i].scaled_out, terms[i].h, terms[i].w, terms[i].scale,
+                     h > 1 ? (float)(terms[i].h - 1) / (float)(h - 1) : 0.f, w > 1 ? (float)(terms[i].w - 1) / (float)(w - 1) : 0.f};
+  }
+  auto dense = [&](const void* p, const int64_t* s, size_t es) {
+    return is_nhwc_dense(s, c, h, w) && aligned16(p) && (s[0] * es) % 16 == 0;
+  };
+  const size_t es = dtype == EAVSR_BF16 ? 2 : 4;
+  const bool ok = (dtype == EAVSR_BF16 || dtype == EAVSR_F32) && c == 64 && (long long)h * w * c < (1ll << 31) &&
+                  dense(x, x_strides, es) && dense(out, out_strides, es) &&
+                  (!x2 || (dtype == EAVSR_BF16 && dense(x2, x2_strides, es) && dense(out2, out2_strides, es)));
+  if (!ok) {
+    set_error("flow_warp_pyramid_forward: dense NHWC 64-channel bf16 / fp32 maps only (dual: bf16); compose "
+              "F.interpolate + flow_warp_forward otherwise");
+    return EAVSR_ERR_UNSUPPORTED;
+  }
+  const int tx = ceil_div(w, TILE_W), ty = ceil_div(h, TILE_H);
+  const unsigned blocks = (unsigned)((long long)n * tx * ty);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == EAVSR_BF16) {
+    using T = __nv_bfloat16;
+    if (x2)
+      flow_warp_fwd_lean<T, 8, EAVSR_PAD_ZEROS, true, true><<<blocks, LEAN_THREADS, 0, st>>>(
+          (const T*)x, nullptr, (T*)out, h, w, EAVSR_FLOW_N2HW, tx, ty, x_strides[0], out_strides[0], (const T*)x2,
+          (T*)out2, x2_strides[0], out2_strides[0], P);
+    else
+      flow_warp_fwd_lean<T, 8, EAVSR_PAD_ZEROS, false, true><<<blocks, LEAN_THREADS, 0, st>>>(
+          (const T*)x, nullptr, (T*)out, h, w, EAVSR_FLOW_N2HW, tx, ty, x_strides[0], out_strides[0], nullptr, nullptr,
+          0, 0, P);
+  } else {
+    flow_warp_fwd_lean<float, 16, EAVSR_PAD_ZEROS, false, true><<<blocks, LEAN_THREADS, 0, st>>>(
+        (const float*)x, nullptr, (float*)out, h, w, EAVSR_FLOW_N2HW, tx, ty, x_strides[0], out_strides[0], nullptr,
+        nullptr, 0, 0, P);
+  }
+  return check_launch("flow_warp_pyramid_forward");
+}
+
+extern "C" int eavsr_spynet_level_input_forward(const float* ref, const float* supp, const float* flow_prev, float* out,
+                                                int n, int h, int w, int prev_h, int prev_w, void* stream) {
+  EAVSR_REQUIRE(ref && supp && out, "spynet_level_input_forward: null pointer");
+  EAVSR_REQUIRE(n > 0 && h > 0 && w > 0, "spynet_level_input_forward: empty tensor");
+  EAVSR_REQUIRE(!flow_prev || (prev_h > 0 && prev_w > 0), "spynet_level_input_forward: bad previous flow size");
+  EAVSR_REQUIRE((long long)h * w < (1ll << 31), "spynet_level_input_forward: image too large");
+  const long long total = (long long)n * h * w;
+  const float ry = (flow_prev && h > 1) ? (float)(prev_h - 1) / (float)(h - 1) : 0.f;
+  const float rx = (flow_prev && w > 1) ? (float)(prev_w - 1) / (float)(w - 1) : 0.f;
+  spynet_level_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      ref, supp, flow_prev, out, n, h, w, prev_h, prev_w, ry, rx);
+  return check_launch("spynet_level_input_forward");
 }

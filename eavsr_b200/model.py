@@ -26,7 +26,8 @@ import torch.nn.functional as F
 from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
                   conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, conv3x3_chain_eligible, rca_group_chain,
-                  flow_warp, flow_warp2, flow_warp_nhw2, fused_inference_ok,
+                  flow_warp, flow_warp2, flow_warp_nhw2, flow_warp_pyramid, flow_warp_pyramid_eligible, fused_inference_ok,
+                  spynet_level_input,
                   modulated_deform_conv2d)
 
 __all__ = ["EAVSRP", "MultiAdSTN", "SPyNet"]
@@ -259,6 +260,7 @@ class MultiAdSTN(ModulatedDeformConv2d):
             setattr(self, f"flow_l{i}", _AdaptBlock2_3x3(ch))
         self.adastn = _AdaptBlockOffset(ch, deformable_groups)
         self.fuse_offsets = True     # inference: expand offsets / masks inside the DCN kernel (dcn_affine)
+        self.fold_pyramid = True     # inference: evaluate the pyramid flows inside the warp kernels (row f2)
         for i in (3, 2, 1):
             setattr(self, f"trans_l{i}", _TransOffset())
 
@@ -270,6 +272,17 @@ class MultiAdSTN(ModulatedDeformConv2d):
         """`out`: optional 64-channel slice of a wider channels_last buffer that receives the result when the
         fused-offset DCN runs (saves the torch.cat copy of the caller); the returned tensor is what to use."""
         flow = flow.float()
+        if self.fold_pyramid and flow_warp_pyramid_eligible(nbr[0], feat_prop) and flow_warp_pyramid_eligible(nbr[1]) \
+                and flow_warp_pyramid_eligible(nbr[2]) and nbr[0].dtype == torch.bfloat16:
+            # row f2: the resized / rescaled / summed flows of the three pyramid levels are evaluated inside the warps
+            w3 = flow_warp_pyramid(nbr[2], [(flow, 0.25)])
+            p1 = self._residual(3, w3, ref[2])
+            w2, p1_up = flow_warp_pyramid(nbr[1], [(flow, 0.5), (p1, 2.0)], keep=(1,))
+            p2 = self._residual(2, w2, ref[1])
+            w1, flow_p2 = flow_warp_pyramid(nbr[0], [(flow, 1.0), (p2, 2.0), (p1_up, 2.0)], want_flow=True)
+            p3 = self._residual(1, w1, ref[0])
+            nbr_w, feat = flow_warp_pyramid(nbr[0], [(flow_p2, 1.0), (p3, 1.0)], x2=feat_prop)
+            return self._deform(nbr_w, feat, ref, out)
         f4 = _resize_flow(flow, 0.25)
         f2 = _resize_flow(flow, 0.5)
         p1 = self._residual(3, flow_warp(nbr[2], f4), ref[2])
@@ -283,6 +296,10 @@ class MultiAdSTN(ModulatedDeformConv2d):
         else:
             nbr_w = flow_warp(nbr[0], flow)
             feat = flow_warp(feat_prop, flow)
+        return self._deform(nbr_w, feat, ref, out)
+
+    def _deform(self, nbr_w, feat, ref, out=None):
+        """offsets / masks from the warped neighbour and the reference, then DCNv2 (models/networks.py:625-630)."""
         if (self.fuse_offsets and fused_inference_ok(nbr_w, self.adastn.mask_conv.weight)
                 and nbr_w.dtype == torch.bfloat16 and tuple(self.weight.shape) == (64, 64, 3, 3)):
             y, yb = self.adastn.raw(nbr_w, ref[0])
@@ -325,6 +342,7 @@ class SPyNet(nn.Module):
     def __init__(self):
         super().__init__()
         self.basic_module = nn.ModuleList([_SPyNetLevel() for _ in range(6)])
+        self.fuse_level_input = True    # inference: warp + upsampled flow + concat of a level in one launch (row f4)
         self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
         self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
 
@@ -336,6 +354,12 @@ class SPyNet(nn.Module):
             ref.append(F.avg_pool2d(ref[-1], 2, 2, count_include_pad=False))
             supp.append(F.avg_pool2d(supp[-1], 2, 2, count_include_pad=False))
         ref, supp = ref[::-1], supp[::-1]
+        if self.fuse_level_input and fused_inference_ok(ref[0], supp[0]) and ref[0].dtype == torch.float32:
+            flow = None                                   # row f4: one launch builds each level's 8-channel input
+            for lvl in range(6):
+                x8 = spynet_level_input(ref[lvl], supp[lvl], flow)
+                flow = x8[:, 6:] + self.basic_module[lvl](x8)
+            return flow
         flow = ref[0].new_zeros(n, 2, h // 32, w // 32)
         for lvl in range(6):
             up = flow if lvl == 0 else _resize_flow(flow, 2)

@@ -36,7 +36,8 @@ from . import _lib as L
 
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
-    "backwarp", "get_backwarp", "invalidate_caches",
+    "backwarp", "get_backwarp", "invalidate_caches", "flow_warp_pyramid", "flow_warp_pyramid_eligible",
+    "spynet_level_input",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
@@ -196,6 +197,73 @@ def flow_warp2(x1, x2, flow, padding_mode='zeros'):
                                              n, c, h, w, L.BF16, L.PAD_ZEROS if padding_mode == 'zeros' else L.PAD_BORDER,
                                              _stream(x1)), "flow_warp2_forward")
     return o1, o2
+
+
+def flow_warp_pyramid_eligible(x, x2=None) -> bool:
+    """True when `flow_warp_pyramid` can run: inference, dense channels_last 64-channel bf16 / fp32 maps."""
+    ok = (fused_inference_ok(x, x2) and x.dim() == 4 and x.shape[1] == 64
+          and x.is_contiguous(memory_format=torch.channels_last) and x.shape[2] * x.shape[3] * 64 < (1 << 31))
+    if ok and x2 is not None:
+        ok = (x2.shape == x.shape and x2.dtype == x.dtype == torch.bfloat16
+              and x2.is_contiguous(memory_format=torch.channels_last))
+    return ok
+
+
+def flow_warp_pyramid(x, terms, x2=None, want_flow=False, keep=()):
+    """``flow_warp(x, sum_i scale_i * F.interpolate(flow_i, size=x.shape[2:], mode='bilinear', align_corners=True))``
+    with the resizes, scalings and the sum evaluated inside the warp kernel (the
+    interpolate -> scale -> add -> warp chains of MultiAdSTN.forward, models/networks.py:600-615,619).
+    ``terms``: [(flow (n,2,hi,wi), scale), ...] (<= 4); ``x2``: a second map warped with the same flow (:621-623);
+    ``want_flow``: also return the summed flow; ``keep``: indices of terms whose ``scale * resize(flow)`` is returned
+    too.  Returns (out, [out2], [flow], [kept terms...]).  Inference only: check `flow_warp_pyramid_eligible`."""
+    lib = L.load()
+    n, c, h, w = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty_like(x)
+        out2 = torch.empty_like(x2) if x2 is not None else None
+        fl = torch.empty((n, 2, h, w), dtype=torch.float32, device=x.device) if want_flow else None
+        arr = (L.FlowTerm * len(terms))()
+        hold, kept = [], []
+        for i, (a, (f, sc)) in enumerate(zip(arr, terms)):
+            f32 = f.detach().to(torch.float32).contiguous()
+            hold.append(f32)
+            a.flow, a.h, a.w, a.scale = f32.data_ptr(), f32.shape[2], f32.shape[3], float(sc)
+            if i in keep:
+                t = torch.empty((n, 2, h, w), dtype=torch.float32, device=x.device)
+                kept.append(t)
+                a.scaled_out = t.data_ptr()
+        L.check(lib.eavsr_flow_warp_pyramid_forward(
+            x.data_ptr(), _strides(x), _ptr(x2), _strides(x2) if x2 is not None else None, arr, len(terms),
+            out.data_ptr(), _strides(out), _ptr(out2), _strides(out2) if out2 is not None else None, _ptr(fl),
+            n, c, h, w, _dtype_code("flow_warp_pyramid", x), L.PAD_ZEROS, _stream(x)), "flow_warp_pyramid_forward")
+        del hold
+    res = [out]
+    if out2 is not None:
+        res.append(out2)
+    if fl is not None:
+        res.append(fl)
+    return tuple(res + kept) if len(res) + len(kept) > 1 else out
+
+
+def spynet_level_input(ref, supp, flow_prev=None):
+    """``torch.cat([ref, flow_warp(supp, up.permute(0,2,3,1), padding_mode='border'), up], 1)`` with
+    ``up = F.interpolate(flow_prev, scale_factor=2, mode='bilinear', align_corners=True) * 2`` (zero at the coarsest
+    level, ``flow_prev=None``): the input of one SPyNet level (models/eavsrp_model.py:468-486) in one launch
+    (SURVEY.md section 8 row f4).  NCHW fp32, inference only.  Returns (n, 8, h, w); channels 6:8 are ``up``."""
+    _require_cuda("spynet_level_input", ref, supp, flow_prev)
+    lib = L.load()
+    n, c, h, w = ref.shape
+    if c != 3 or supp.shape != ref.shape or ref.dtype != torch.float32 or supp.dtype != torch.float32:
+        raise ValueError(f"spynet_level_input: expected two (n,3,h,w) fp32 images, got {tuple(ref.shape)} / {tuple(supp.shape)}")
+    with torch.cuda.device(ref.device):
+        r, s_ = ref.contiguous(), supp.contiguous()
+        fp = flow_prev.detach().to(torch.float32).contiguous() if flow_prev is not None else None
+        out = torch.empty((n, 8, h, w), dtype=torch.float32, device=ref.device)
+        L.check(lib.eavsr_spynet_level_input_forward(r.data_ptr(), s_.data_ptr(), _ptr(fp), out.data_ptr(), n, h, w,
+                                                     fp.shape[2] if fp is not None else 0,
+                                                     fp.shape[3] if fp is not None else 0, _stream(ref)),
+                "spynet_level_input_forward")
+    return out
 
 
 # ------------------------------------------------------------------------------------------

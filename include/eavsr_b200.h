@@ -78,7 +78,33 @@ int eavsr_flow_warp2_forward(const void* x1, const int64_t x1_strides[4], const 
                              const int64_t out1_strides[4], void* out2, const int64_t out2_strides[4], int n, int c,
                              int h, int w, int dtype, int padding_mode, void* stream);
 
-/* Gradients of the above.  gx32 is an fp32 accumulation buffer with strides gx_strides that
+/* Warp with a PYRAMID flow: flow(y, x) = sum_i scale_i * resize(flow_i)(y, x), resize =
+ * bilinear with align_corners=True to (h, w) -- the F.interpolate(offset, s) * s / ... + ... chains of
+ * MultiAdSTN.forward (models/networks.py:600-615, :619) evaluated inside the warp's coordinate phase instead of
+ * being materialised by F.interpolate + elementwise launches.  terms[i].flow: (n, 2, terms[i].h, terms[i].w) fp32
+ * contiguous; terms[i].scaled_out (optional, (n,2,h,w) fp32) receives scale_i * resize(flow_i); flow_out (optional,
+ * (n,2,h,w) fp32) the sum.  x2 / out2 (optional): a second map warped with the same flow (models/networks.py:
+ * 621-623).  Dense NHWC 64-channel bf16 / fp32 maps, zeros padding (x2: bf16); anything else returns
+ * EAVSR_ERR_UNSUPPORTED and the caller composes the reference's operations. */
+typedef struct EavsrFlowTerm {
+  const float* flow;
+  float* scaled_out;
+  int h, w;
+  float scale;
+} EavsrFlowTerm;
+int eavsr_flow_warp_pyramid_forward(const void* x, const int64_t x_strides[4], const void* x2,
+                                    const int64_t x2_strides[4], const EavsrFlowTerm* terms, int nterms, void* out,
+                                    const int64_t out_strides[4], void* out2, const int64_t out2_strides[4],
+                                    float* flow_out, int n, int c, int h, int w, int dtype, int padding_mode,
+                                    void* stream);
+
+/* SPyNet level input (SPyNet.compute_flow, models/eavsrp_model.py:468-486):
+ * out (n,8,h,w) = cat[ref, flow_warp(supp, up, 'border'), up] with up = 2 * resize_x2(flow_prev) (bilinear,
+ * align_corners=True; flow_prev (n,2,prev_h,prev_w) or NULL = zero flow at the coarsest level).  NCHW fp32. */
+int eavsr_spynet_level_input_forward(const float* ref, const float* supp, const float* flow_prev, float* out, int n,
+                                     int h, int w, int prev_h, int prev_w, void* stream);
+
+/* Gradients of eavsr_flow_warp_forward.  gx32 is an fp32 accumulation buffer with strides gx_strides that
  * the call zero-fills and scatter-adds into (for dtype F32 it is the final gradient);
  * gflow (fp32, same layout as flow) may be NULL when the flow needs no gradient.
  * gx32 may be NULL when x needs no gradient. */

@@ -321,3 +321,75 @@ def test_rca_group_chain_equals_launch_per_convolution(cuda, nb, shape):
     assert (again.float() - chained.float()).abs().max().item() <= 2e-2 * rms
     if ref is not None:
         assert (chained.double().cpu() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("hw", [(68, 120), (34, 60), (16, 24), (272, 480)])
+def test_flow_warp_pyramid_equals_interpolate_add_warp(cuda, dtype, hw):
+    """Row f2: the interpolate -> scale -> add -> warp chains of MultiAdSTN.forward (models/networks.py:600-615,619)
+    evaluated inside the warp kernel == F.interpolate(align_corners=True) + elementwise + flow_warp."""
+    h, w = hw
+    g = torch.Generator().manual_seed(90)
+    up = lambda t, size: F.interpolate(t, size=size, mode="bilinear", align_corners=True)     # noqa: E731
+    x = _cl(torch.randn(2, 64, h, w, generator=g).to(cuda, dtype))
+    x2 = _cl(torch.randn(2, 64, h, w, generator=g).to(cuda, dtype))
+    full = (torch.randn(2, 2, 4 * h, 4 * w, generator=g) * 6).to(cuda)           # a flow 4x finer (level 3 of the pyramid)
+    same = (torch.randn(2, 2, h, w, generator=g) * 2).to(cuda)
+    half = (torch.randn(2, 2, h // 2, w // 2, generator=g) * 1.5).to(cuda)        # coarser fields (levels 2 / 1)
+    half2 = (torch.randn(2, 2, h // 2, w // 2, generator=g) * 1.5).to(cuda)
+    with torch.no_grad():
+        assert ops.flow_warp_pyramid_eligible(x)
+        # level 3: one 4x finer flow, scaled by 1/4
+        ref_flow = up(full, (h, w)) / 4.
+        out = ops.flow_warp_pyramid(x, [(full, 0.25)])
+        assert torch.equal(out, E.flow_warp(x, ref_flow)) or (out.float() - E.flow_warp(x, ref_flow).float()).abs().max() < 2e-2
+        # level 2 / 1: several terms, one kept, the sum returned
+        t1, t2 = up(half, (h, w)) * 2, up(half2, (h, w)) * 2
+        ref_flow = same + t1 + t2
+        out, fl, kept = ops.flow_warp_pyramid(x, [(same, 1.0), (half, 2.0), (half2, 2.0)], want_flow=True, keep=(2,))
+        assert (fl - ref_flow).abs().max().item() < 1e-4 and (kept - t2).abs().max().item() < 1e-5
+        ref = E.flow_warp(x, fl)                       # same flow tensor -> the warp itself must agree exactly
+        assert torch.equal(out, ref)
+        if dtype == torch.bfloat16:                    # dual warp with a 2-term flow (the final warp of MultiAdSTN)
+            o1, o2 = ops.flow_warp_pyramid(x, [(fl, 1.0), (same, 1.0)], x2=x2)
+            r1, r2 = ops.flow_warp2(x, x2, fl + same)
+            assert torch.equal(o1, r1) and torch.equal(o2, r2)
+
+
+def test_spynet_level_input_equals_interpolate_warp_cat(cuda):
+    """Row f4: one launch builds cat[ref, flow_warp(supp, up, 'border'), up] with up = 2 * resize_x2(flow_prev)
+    (SPyNet.compute_flow, models/eavsrp_model.py:468-486)."""
+    g = torch.Generator().manual_seed(91)
+    for (n, h, w) in ((3, 18, 30), (2, 9, 15), (29, 72, 120)):
+        ref = torch.rand(n, 3, h, w, generator=g).to(cuda)
+        supp = torch.rand(n, 3, h, w, generator=g).to(cuda)
+        with torch.no_grad():
+            x0 = ops.spynet_level_input(ref, supp, None)
+            want0 = torch.cat([ref, supp, torch.zeros(n, 2, h, w, device=cuda)], 1)
+            assert torch.equal(x0, want0)                                  # zero flow: the border warp is the identity
+            if h % 2 == 0:
+                prev = (torch.randn(n, 2, h // 2, w // 2, generator=g) * 2).to(cuda)
+                up = F.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+                want = torch.cat([ref, E.flow_warp_nhw2(supp, up.permute(0, 2, 3, 1), padding_mode="border"), up], 1)
+                got = ops.spynet_level_input(ref, supp, prev)
+                assert (got[:, 6:] - up).abs().max().item() < 1e-5
+                assert (got - want).abs().max().item() < 1e-4
+
+
+def test_multi_adstn_pyramid_folding_matches_unfolded_path(cuda):
+    g = torch.Generator().manual_seed(92)
+    m = M.MultiAdSTN(64, 8)
+    from eavsr_b200.synthetic import seeded_parameters
+    seeded_parameters(m)
+    m = m.to(cuda, torch.bfloat16).to(memory_format=torch.channels_last)
+    h, w = 48, 80
+    feats = lambda: [_cl(torch.randn(1, 64, h >> i, w >> i, generator=g).to(cuda, torch.bfloat16)) for i in range(3)]   # noqa: E731
+    nbr, ref, prop = feats(), feats(), feats()[0]
+    flow = (torch.randn(1, 2, h, w, generator=g) * 2).to(cuda)
+    with torch.no_grad():
+        m.fold_pyramid = True
+        a = m(nbr, ref, prop, flow).float()
+        m.fold_pyramid = False
+        b = m(nbr, ref, prop, flow).float()
+    rms = b.pow(2).mean().sqrt().item()
+    assert (a - b).pow(2).mean().sqrt().item() < 1e-2 * rms        # same arithmetic up to fp32 summation order of the flows
