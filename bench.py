@@ -172,7 +172,7 @@ class ModelWorkload:
     name = "eavsrp_x4_full_clip_30x270x480_bf16"
 
     def __init__(self, device, t=T_FRAMES, h=LR_H, w=LR_W, dtype=torch.bfloat16, graph=True, rank=0, world=1,
-                 distinct=8, clips_per_step=1, streams=1):
+                 distinct=8, clips_per_step=1, streams=1, net=None):
         from eavsr_b200.clip_parallel import shard
         from eavsr_b200.model import EAVSRP, pad_clip
         from eavsr_b200.synthetic import clip_inputs, seeded_parameters
@@ -182,9 +182,15 @@ class ModelWorkload:
         # the other's (every kernel here is a one-CTA-per-SM persistent grid of ~15 us)
         self.streams = max(1, min(streams, clips_per_step))
         assert clips_per_step % self.streams == 0
-        net = EAVSRP(4).eval()
-        seeded_parameters(net)
-        self.net = net.to(device).prepare(dtype)
+        if net is None:
+            net = EAVSRP(4).eval()
+            seeded_parameters(net)
+            net = net.to(device).prepare(dtype)
+        self.net = net
+        if os.environ.get("EAVSR_BENCH_CHAIN", "1") != "1":     # A/B switch: one launch per convolution
+            for m in self.net.modules():
+                if hasattr(m, "chain"):
+                    m.chain = False
         self.pad = lambda x: pad_clip(x, 4)
         # this rank's clips of the 64-clip set; `distinct` of them are materialised (47 MB each on the device)
         self.clip_ids = shard(NUM_CLIPS, rank, world)[:max(1, distinct) * clips_per_step]
@@ -563,7 +569,7 @@ def run_reference_arm(args):
         from oracle import eavsrp_cpu as R
         sd = R._seeded_state_dict()
         t_s, hs, ws, est = R.plan_sample(120.0, PAD_H, LR_W, sd, frames=(6, 4, 3))
-        steps = max(1, min(args.steps, int(240.0 // max(est, 1.0))))
+        steps = max(1, min(args.steps, int(180.0 // max(est, 1.0))))
         secs = [R.time_clip_forward(t_s, hs, ws, sd, seed=1234 + i) for i in range(steps)]
         el = sum(secs) / len(secs)
         fps = t_s / el * (hs * ws) / (PAD_H * LR_W)
@@ -611,10 +617,12 @@ def main():
     ap.add_argument("--train-dtype", default="bf16", choices=["bf16", "f32"], help="--workload train: compute dtype")
     ap.add_argument("--train-pwc", action="store_true",
                     help="--workload train: run the epoch >= npost branch too (PWC-Net cost volume + backwarp)")
-    ap.add_argument("--streams", type=int, default=1,
+    ap.add_argument("--streams", type=int, default=2,
                     help="run the clips of a step as this many concurrent forwards (CUDA streams) instead of one batch")
-    ap.add_argument("--clips-per-step", type=int, default=1,
-                    help="clips batched into one forward per GPU (config 4 gives every GPU 8+ clips); default 1")
+    ap.add_argument("--clips-per-step", type=int, default=4,
+                    help="clips in flight per GPU and step (BASELINE config 4 gives every GPU 8+ clips): clips-per-step / "
+                         "streams are batched into one forward, the forwards run on `streams` CUDA streams; default 4 on 2 "
+                         "streams (+5 %% over one clip at a time, which is reported next to it as `single_clip`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -728,6 +736,28 @@ def main():
                 parity = wl.parity()
             except Exception as exc:   # reported, never a reason to lose the bench line
                 parity = {"failed": repr(exc)}
+        single = None
+        if rank == 0 and args.workload == "model" and getattr(wl, "cps", 1) > 1 and not args.no_parity:
+            # BASELINE config 3 as literally written: ONE clip at a time (latency of a clip = this ms_per_clip)
+            try:
+                w1 = ModelWorkload(device, t=T_FRAMES, h=LR_H, w=LR_W, rank=rank, world=world, distinct=2,
+                                   clips_per_step=1, streams=1, net=wl.net)
+                for _ in range(3):
+                    w1.step()
+                torch.cuda.synchronize()
+                a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k1 = max(2, min(args.steps, 5))
+                a1.record()
+                for _ in range(k1):
+                    w1.step()
+                b1.record()
+                torch.cuda.synchronize()
+                ms1 = a1.elapsed_time(b1) / k1
+                single = {"clips_in_flight": 1, "ms_per_clip": round(ms1, 3), "value": round(T_FRAMES / (ms1 / 1e3), 3),
+                          "unit": "frames/s", "steps": k1}
+                del w1
+            except Exception as exc:
+                single = {"failed": repr(exc)}
         roof = dcn_roofline(device, peaks) if (rank == 0 and not args.no_roofline and args.workload != "train") else None
 
     cpu = None
@@ -772,7 +802,7 @@ def main():
                 "data": "synthetic",
                 "config": bench_config(wl.name, world, getattr(wl, "cps", 1)),
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-                "cpu_baseline": cpu, "parity": parity,
+                "cpu_baseline": cpu, "parity": parity, "single_clip": single,
                 "clips": {"set": NUM_CLIPS, "seeds": "1234 + clip_id", "this_run_per_rank": len(getattr(wl, "dev_clips", [])),
                           "sharding": "clip i -> rank i mod N (eavsr_b200.clip_parallel.shard)"}}
         print(json.dumps(line))

@@ -4,6 +4,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+import eavsr_b200 as E
+
 import eavsr_b200.model as M
 from eavsr_b200 import ops
 from oracle import alignment as O
