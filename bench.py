@@ -318,7 +318,8 @@ class TrainWorkload:
     all-reduce (12.28 M fp32 = 49.1 MB) is the collective.  bf16 = autocast with fp32 master weights."""
     name = "eavsrp_x4_train_step_8x15x64x64_bf16"
 
-    def __init__(self, device, rank=0, world=1, batch=8, t=15, size=64, dtype=torch.bfloat16, distinct=4, pwc=False):
+    def __init__(self, device, rank=0, world=1, batch=8, t=15, size=64, dtype=torch.bfloat16, distinct=4, pwc=False,
+                 graph=False):
         import torch.nn.functional as F
         from eavsr_b200.model import EAVSRP
         from eavsr_b200.synthetic import clip_inputs, seeded_parameters
@@ -333,8 +334,9 @@ class TrainWorkload:
             pwcnet = PWCNET()
             seeded_parameters(pwcnet)
             pwcnet = pwcnet.to(device)
+        self.graph = graph
         self.trainer = Trainer(net, lr=1e-4, dtype=dtype, ddp=world > 1, device_ids=[device.index], pwcnet=pwcnet,
-                               npost=0 if pwc else 350)
+                               npost=0 if pwc else 350, capturable=graph)
         self.grad_bytes = trainable_bytes(net)
         self.host, self.dev = [], []
         for k in range(distinct):
@@ -351,19 +353,24 @@ class TrainWorkload:
         self.loss = None
         self.epoch = 0
 
+    def _do(self, lr, hr, sync=True):
+        with torch.enable_grad():
+            if self.graph and sync:
+                if self.trainer._graph is None:
+                    self.trainer.capture(lr, hr, epoch=self.epoch)
+                return self.trainer.step_graphed(lr, hr)
+            return self.trainer.step(lr, hr, epoch=self.epoch, sync=sync)
+
     def step(self, sync=True):
         lr, hr = self.dev[self.cursor % len(self.dev)]
         self.cursor += 1
-        with torch.enable_grad():
-            self.loss = self.trainer.step(lr, hr, epoch=self.epoch, sync=sync)
+        self.loss = self._do(lr, hr, sync)
         return self.loss
 
     def e2e_step(self):
         lr, hr = self.host[self.cursor % len(self.host)]
         self.cursor += 1
-        with torch.enable_grad():
-            loss = self.trainer.step(lr.to(self.device, non_blocking=True), hr.to(self.device, non_blocking=True),
-                                     epoch=self.epoch)
+        loss = self._do(lr.to(self.device, non_blocking=True), hr.to(self.device, non_blocking=True))
         return loss.item()                      # D2H read of the step's result
 
     def collective(self, steps, time_steps):
@@ -372,6 +379,13 @@ class TrainWorkload:
         import torch.distributed as dist
         if self.world == 1:
             return {"op": "none (1 GPU)", "bytes_per_step": self.grad_bytes}
+        if self.graph:      # the all-reduce is inside the captured graph: only its stand-alone cost can be reported
+            flat = torch.zeros(self.grad_bytes // 4, device=self.device)
+            buckets = list(flat.split(25 * 1024 * 1024 // 4))
+            t_alone = time_steps(lambda: [dist.all_reduce(b) for b in buckets], max(steps, 5))
+            return {"op": "all_reduce (NCCL, DistributedDataParallel buckets of 25 MB, captured in the step's CUDA graph)",
+                    "bytes_per_step": self.grad_bytes, "alone_ms": round(t_alone, 3),
+                    "busbw_GBps_alone": round(2 * (self.world - 1) / self.world * self.grad_bytes / (t_alone / 1e3) / 1e9, 1)}
         t_sync = time_steps(lambda: self.step(True), steps)
         t_nosync = time_steps(lambda: self.step(False), steps)
         flat = torch.zeros(self.grad_bytes // 4, device=self.device)
@@ -388,7 +402,7 @@ class TrainWorkload:
 def make_workload(name, device, rank=0, world=1, args=None):
     if name == "train":
         return TrainWorkload(device, rank, world, dtype=torch.float32 if (args and args.train_dtype == "f32") else torch.bfloat16,
-                             pwc=bool(args and args.train_pwc))
+                             pwc=bool(args and args.train_pwc), graph=bool(args and args.train_graph))
     if name == "hotpath":
         return HotpathWorkload(device, t=T_FRAMES)
     if name == "model":
@@ -615,6 +629,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--train-dtype", default="bf16", choices=["bf16", "f32"], help="--workload train: compute dtype")
+    ap.add_argument("--train-graph", action="store_true",
+                    help="--workload train: capture the whole step (forward, backward, Adam) into one CUDA graph")
     ap.add_argument("--train-pwc", action="store_true",
                     help="--workload train: run the epoch >= npost branch too (PWC-Net cost volume + backwarp)")
     ap.add_argument("--streams", type=int, default=2,
@@ -788,7 +804,7 @@ def main():
                 "config": {"workload": wl.name if args.train_dtype == "bf16" else wl.name.replace("bf16", "f32"),
                            "crops_per_gpu": wl.batch, "global_batch": wl.batch * world, "frames": wl.t,
                            "optimizer": "Adam, 2 groups (deform_align lr 1e-5)", "loss": "L1",
-                           "npost_branch": bool(args.train_pwc),
+                           "npost_branch": bool(args.train_pwc), "cuda_graph": bool(args.train_graph),
                            "parallelism": f"ddp x{world} (NCCL all-reduce of {wl.grad_bytes / 1e6:.1f} MB gradients)",
                            "l2": "activations per step >> 126 MB L2"},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "collective": collective,

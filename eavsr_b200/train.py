@@ -45,8 +45,9 @@ def param_groups(net: nn.Module, lr: float, align_lr: float = 1e-5) -> List[dict
 
 
 def build_optimizer(net: nn.Module, lr: float = 1e-4, betas: Tuple[float, float] = (0.9, 0.999),
-                    weight_decay: float = 0.0, align_lr: float = 1e-5) -> torch.optim.Adam:
-    return torch.optim.Adam(param_groups(net, lr, align_lr), lr=lr, betas=betas, weight_decay=weight_decay)
+                    weight_decay: float = 0.0, align_lr: float = 1e-5, capturable: bool = False) -> torch.optim.Adam:
+    return torch.optim.Adam(param_groups(net, lr, align_lr), lr=lr, betas=betas, weight_decay=weight_decay,
+                            capturable=capturable)
 
 
 def trainable_bytes(net: nn.Module) -> int:
@@ -67,10 +68,11 @@ class Trainer:
     def __init__(self, net: nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 0.0,
                  align_lr: float = 1e-5, dtype: torch.dtype = torch.float32, ddp: bool = False, scale: int = 4,
                  pwcnet: Optional[nn.Module] = None, npost: int = 350, bucket_cap_mb: int = 25,
-                 device_ids: Optional[list] = None):
+                 device_ids: Optional[list] = None, capturable: bool = False):
         self.net = net
         self.dtype, self.scale, self.npost = dtype, scale, npost
-        self.optimizer = build_optimizer(net, lr, betas, weight_decay, align_lr)
+        self.optimizer = build_optimizer(net, lr, betas, weight_decay, align_lr, capturable)
+        self._graph = None
         self.pwcnet = pwcnet
         if pwcnet is not None:
             for p in pwcnet.parameters():
@@ -119,6 +121,41 @@ class Trainer:
             self.loss = self.compute_loss(sr, hr_seq)
             self.loss.backward()
         self.optimizer.step()
+        return self.loss.detach()
+
+    # -- the whole step as one CUDA graph ------------------------------------------------------------------------
+    def capture(self, lr_seq: torch.Tensor, hr_seq: torch.Tensor, epoch: int = 0, warmup: int = 3) -> "Trainer":
+        """Capture forward + loss + backward + Adam of `step` into ONE CUDA graph (the eager step issues ~45 k launches
+        from one Python thread and is bound by the host, not the GPU).  Needs ``Trainer(capturable=True)``; runs
+        `warmup` REAL steps on a side stream first (lazy initialisation, cuDNN algorithm selection, DDP bucket
+        set-up), then records one step on static copies of the inputs.  `step_graphed` replays it."""
+        if not any(g.get("capturable") for g in self.optimizer.param_groups):
+            raise RuntimeError("Trainer.capture needs Trainer(..., capturable=True) (Adam state on the device)")
+        self._static = (lr_seq.clone(), hr_seq.clone())
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.step(self._static[0], self._static[1], epoch)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.optimizer.zero_grad(set_to_none=True)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            sr = self.forward(self._static[0], self._static[1], epoch)
+            self.loss = self.compute_loss(sr, self._static[1])
+            self.loss.backward()
+            self.optimizer.step()
+        return self
+
+    def step_graphed(self, lr_seq: torch.Tensor, hr_seq: torch.Tensor) -> torch.Tensor:
+        """One training step by graph replay (same shapes as at `capture`)."""
+        if self._graph is None:
+            raise RuntimeError("call Trainer.capture first")
+        self._static[0].copy_(lr_seq, non_blocking=True)
+        self._static[1].copy_(hr_seq, non_blocking=True)
+        self._graph.replay()
         return self.loss.detach()
 
     def gradients(self) -> Dict[str, torch.Tensor]:

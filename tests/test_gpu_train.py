@@ -157,3 +157,25 @@ def test_two_gpu_ddp_gradients_equal_single_process(cuda):
             assert (grads[n] - g).abs().max().item() <= 1e-5 * max(g.abs().max().item(), 1e-3) + 1e-7, n
     for n in single:
         assert torch.equal(ret[0][0][n], ret[1][0][n]), n           # both ranks hold the same reduced gradient
+
+
+def test_graph_captured_step_equals_eager_step(cuda):
+    """Trainer.capture: forward + L1 + backward + Adam as ONE CUDA graph; a replayed step changes the parameters
+    exactly as an eager step from the same state does (up to the atomics' summation order)."""
+    import copy
+    lr, hr = _crops(2, 3, 64, seed=80)
+    lr, hr = lr.to(cuda), hr.to(cuda)
+    net_g = _net(1, cuda)
+    tg = T.Trainer(net_g, dtype=torch.bfloat16, capturable=True)
+    tg.capture(lr, hr, warmup=2)                       # two real steps, then the recording (which does not execute)
+    net_e = copy.deepcopy(net_g)
+    te = T.Trainer(net_e, dtype=torch.bfloat16, capturable=True)
+    te.optimizer.load_state_dict(copy.deepcopy(tg.optimizer.state_dict()))
+    lr2, hr2 = _crops(2, 3, 64, seed=81)
+    lg = tg.step_graphed(lr2.to(cuda), hr2.to(cuda))
+    le = te.step(lr2.to(cuda), hr2.to(cuda))
+    assert torch.isfinite(lg) and abs(lg.item() - le.item()) < 1e-5
+    worst = 0.0
+    for (n, a), (_, b) in zip(net_g.named_parameters(), net_e.named_parameters()):
+        worst = max(worst, (a - b).abs().max().item())
+    assert worst < 5e-5, worst                         # one Adam step moves a weight by <= lr = 1e-4

@@ -29,6 +29,12 @@ if "warp" in which:
     a, b = (cl(torch.randn(1, 64, 21, 33, device=dev).bfloat16()) for _ in range(2))
     with torch.no_grad():
         ops.flow_warp2(a, b, torch.randn(1, 2, 21, 33, device=dev))
+        c, d = (cl(torch.randn(1, 64, 20, 32, device=dev).bfloat16()) for _ in range(2))
+        ops.flow_warp_pyramid(c, [(torch.randn(1, 2, 80, 128, device=dev), 0.25)])
+        ops.flow_warp_pyramid(c, [(torch.randn(1, 2, 20, 32, device=dev), 1.0), (torch.randn(1, 2, 10, 16, device=dev), 2.0)],
+                              x2=d, want_flow=True, keep=(1,))
+        ops.spynet_level_input(torch.rand(2, 3, 18, 30, device=dev), torch.rand(2, 3, 18, 30, device=dev),
+                               torch.randn(2, 2, 9, 15, device=dev))
 if "dcn" in which:
     for dg, dtype in ((8, torch.bfloat16), (8, torch.float32), (16, torch.bfloat16), (4, torch.bfloat16)):
         x, off, mask, w, b = dcn_inputs(1, 64, 21, 35, 64, dg, seed=3)
@@ -43,6 +49,10 @@ if "corr" in which:
         f1 = torch.randn(shape, device=dev, requires_grad=True)
         f2 = torch.randn(shape, device=dev, requires_grad=True)
         E.FunctionCorrelation(tenFirst=f1, tenSecond=f2).square().mean().backward()
+    ops.CORRELATION_TF32 = True                  # the opt-in tcgen05 / tf32 banded GEMM
+    for shape in ((1, 32, 24, 32), (2, 20, 24, 72), (1, 5, 18, 16)):
+        E.FunctionCorrelation(tenFirst=torch.randn(shape, device=dev), tenSecond=torch.randn(shape, device=dev))
+    ops.CORRELATION_TF32 = False
 if "fused" in which:
     from eavsr_b200.model import MultiAdSTN, _RCAGroup
     from eavsr_b200.synthetic import seeded_parameters
@@ -55,6 +65,8 @@ if "fused" in which:
         g = _RCAGroup(64, 2)
         seeded_parameters(g)
         g = g.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
-        g(feats()[0])
+        g(feats()[0])                            # chained cooperative launch
+        g.chain = False
+        g(feats()[0])                            # one launch per convolution
 torch.cuda.synchronize()
 print("sanitize_target done:", which)
