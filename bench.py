@@ -358,6 +358,7 @@ class TrainWorkload:
             if self.graph and sync:
                 if self.trainer._graph is None:
                     self.trainer.capture(lr, hr, epoch=self.epoch)
+                    self.launches_per_step = self.trainer.captured_launches
                 return self.trainer.step_graphed(lr, hr)
             return self.trainer.step(lr, hr, epoch=self.epoch, sync=sync)
 
@@ -823,7 +824,17 @@ def main():
                           "sharding": "clip i -> rank i mod N (eavsr_b200.clip_parallel.shard)"}}
         print(json.dumps(line))
     if world > 1:
+        # A captured NCCL all-reduce (--train-graph) has been seen to hang the process-group teardown: drop the graph
+        # first, and never let a stuck teardown hold the GPUs -- the JSON line is already out.
+        sys.stdout.flush()
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        if hasattr(wl, "trainer"):
+            wl.trainer._graph = None
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

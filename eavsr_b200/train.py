@@ -82,8 +82,18 @@ class Trainer:
             if not (dist.is_available() and dist.is_initialized()):
                 raise RuntimeError("Trainer(ddp=True) needs torch.distributed.init_process_group first")
             from torch.nn.parallel import DistributedDataParallel
-            self.model = DistributedDataParallel(net, device_ids=device_ids, bucket_cap_mb=bucket_cap_mb,
-                                                 gradient_as_bucket_view=True, broadcast_buffers=False)
+            # constructed on a side stream so that the autograd hooks DDP stashes live on the stream the (optionally
+            # graph-captured) steps run on -- PyTorch's recipe for DDP under CUDA graphs
+            side = torch.cuda.Stream() if torch.cuda.is_available() and capturable else None
+            ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+            with ctx:
+                self.model = DistributedDataParallel(net, device_ids=device_ids, bucket_cap_mb=bucket_cap_mb,
+                                                     gradient_as_bucket_view=True, broadcast_buffers=False)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+            self._ddp_stream = side
         self.loss = None
 
     # -- pieces of optimize_parameters, exposed for tests and for the bench's overlap measurement --------------
@@ -133,20 +143,25 @@ class Trainer:
             raise RuntimeError("Trainer.capture needs Trainer(..., capturable=True) (Adam state on the device)")
         self._static = (lr_seq.clone(), hr_seq.clone())
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        side = getattr(self, "_ddp_stream", None) or torch.cuda.Stream()
         side.wait_stream(cur)
+        if hasattr(self.model, "no_sync"):
+            warmup = max(warmup, 11)            # DDP rebuilds its buckets during the first iterations
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
                 self.step(self._static[0], self._static[1], epoch)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.optimizer.zero_grad(set_to_none=True)
+        from . import _lib
         self._graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
         with torch.cuda.graph(self._graph):
             sr = self.forward(self._static[0], self._static[1], epoch)
             self.loss = self.compute_loss(sr, self._static[1])
             self.loss.backward()
             self.optimizer.step()
+        self.captured_launches = _lib.launch_count() - l0      # library kernels replayed by every step_graphed
         return self
 
     def step_graphed(self, lr_seq: torch.Tensor, hr_seq: torch.Tensor) -> torch.Tensor:
