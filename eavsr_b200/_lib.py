@@ -23,6 +23,7 @@ DCN_BLEND_FP32 = 8
 DCN_WS_PACKED = 16
 DCN_BWD_GENERIC_DATA = 32
 DCN_BWD_GENERIC_WEIGHT = 64
+DCN_FORCE_WIN1 = 128
 CONV_SUMS_PREZEROED = 1
 CORR_TF32 = 2
 

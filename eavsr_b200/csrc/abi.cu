@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace eavsr {
@@ -26,6 +28,30 @@ int check_launch(const char* what) {
     return EAVSR_ERR_CUDA;
   }
   return EAVSR_OK;
+}
+
+bool encode_tensor_map(void* tensor_map, int dtype, int rank, const void* base, const unsigned long long* dims,
+                       const unsigned long long* strides_bytes, const unsigned* box, int swizzle) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<Fn>(p);
+  }();
+  if (!fn || rank < 1 || rank > 5) return false;
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  return fn(reinterpret_cast<CUtensorMap*>(tensor_map),
+            dtype == EAVSR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+            const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace eavsr

@@ -30,6 +30,11 @@ struct DcnGeom {
   int N, Cin, H, W, Cout, KH, KW, SH, SW, PH, PW, DH, DW, G, DG, HO, WO;
 };
 size_t strided_extent_elems(const int64_t s[4], int n, int c, int h, int w);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda); returns false when unavailable / rejected.
+// dims / box / element strides have `rank` entries, strides_bytes rank - 1 (dimension 0 is contiguous).
+bool encode_tensor_map(void* tensor_map /* CUtensorMap* */, int dtype /* EAVSR_F32 | EAVSR_BF16 */, int rank, const void* base,
+                       const unsigned long long* dims, const unsigned long long* strides_bytes, const unsigned* box,
+                       int swizzle /* CUtensorMapSwizzle */);
 
 // ---- element access helpers -------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "dcn_fwd_ws.cuh"
 #include "dcn_fwd_win.cuh"
+#include "dcn_fwd_win2.cuh"
 
 namespace eavsr {
 
@@ -331,6 +332,29 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
       const int tpi = tiles_x * tiles_y, tot = tpi * n;
       const int g3 = tot < sms ? tot : sms;
       const bool b16 = !(flags & EAVSR_DCN_BLEND_FP32);
+      if constexpr (DG == 8) {
+        // fourth generation (dcn_fwd_win2.cuh): TMA-staged offsets, one pixel per lane.  Needs tensor maps over the
+        // offset / mask tensors, i.e. 16-byte aligned rows (w % 4 == 0)
+        if (vecw && !(flags & EAVSR_DCN_FORCE_WIN1)) {
+          CUtensorMap tmo, tmm;
+          const unsigned long long HWb = (unsigned long long)h * w * 4;
+          const unsigned long long od[5] = {(unsigned long long)w, (unsigned long long)h, 18, 8, (unsigned long long)n};
+          const unsigned long long os_[4] = {(unsigned long long)w * 4, HWb, 18 * HWb, 144 * HWb};
+          const unsigned long long md[5] = {(unsigned long long)w, (unsigned long long)h, 9, 8, (unsigned long long)n};
+          const unsigned long long ms_[4] = {(unsigned long long)w * 4, HWb, 9 * HWb, 72 * HWb};
+          const unsigned box[5] = {win2::TW, win2::TH, 1, 8, 1};
+          if (encode_tensor_map(&tmo, EAVSR_F32, 5, offset, od, os_, box, 0) &&
+              encode_tensor_map(&tmm, EAVSR_F32, 5, mask, md, ms_, box, 0)) {
+            auto k2 = b16 ? win2::dcn_fwd_win2_kernel<true> : win2::dcn_fwd_win2_kernel<false>;
+            cudaError_t e2 = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, win2::Smem::DYN);
+            if (e2 != cudaSuccess) { set_error("dcn_forward(win2): smem attr: %s", cudaGetErrorString(e2)); return EAVSR_ERR_CUDA; }
+            k2<<<g3, win2::THREADS, win2::Smem::DYN, st>>>((const __nv_bfloat16*)x, tmo, tmm, (const uint8_t*)workspace,
+                                                         (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, h, w, xs[0],
+                                                         os[0], tiles_x, tpi, tot);
+            return check_launch("dcn_forward(win2)");
+          }
+        }
+      }
       void (*k)(const __nv_bfloat16*, const float*, const float*, const uint8_t*, const __nv_bfloat16*,
                 __nv_bfloat16*, int, int, long long, long long, int, int, int, const __nv_bfloat16*,
                 const __nv_bfloat16*, int) =

@@ -267,6 +267,9 @@ def test_dcn_tc_kernels_agree(cuda, shape):
     xb, wb, bb = args[0].bfloat16(), wgt.to(cuda).bfloat16(), bias.to(cuda).bfloat16()
     run = lambda fl: _ModulatedDeformConv2dFn.apply(xb, *args[1:3], wb, bb, 1, 1, 1, 1, 8, fl)     # noqa: E731
     w16, w32, ws, v1 = run(0), run(L.DCN_BLEND_FP32), run(L.DCN_FORCE_WS), run(L.DCN_FORCE_V1)
+    # fourth generation (TMA-staged offsets, one pixel per lane; taken by run(0) when w % 4 == 0) == third generation
+    assert torch.equal(w16, run(L.DCN_FORCE_WIN1))
+    assert torch.equal(w32, run(L.DCN_BLEND_FP32 | L.DCN_FORCE_WIN1))
     assert torch.equal(ws, v1)              # same arithmetic, bit-identical
     assert torch.equal(w32, v1)             # the window only changes where the corners are read from
     ref = _dcn_ref(xb.cpu(), off, mask, wb.cpu(), bb.cpu(), dg=8)
