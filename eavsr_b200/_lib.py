@@ -24,6 +24,7 @@ DCN_WS_PACKED = 16
 DCN_BWD_GENERIC_DATA = 32
 DCN_BWD_GENERIC_WEIGHT = 64
 DCN_FORCE_WIN1 = 128
+DCN_FORCE_WIN2 = 256
 CONV_SUMS_PREZEROED = 1
 CORR_TF32 = 2
 

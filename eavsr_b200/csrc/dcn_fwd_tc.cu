@@ -20,6 +20,7 @@
 #include "dcn_fwd_ws.cuh"
 #include "dcn_fwd_win.cuh"
 #include "dcn_fwd_win2.cuh"
+#include "dcn_fwd_win3.cuh"
 
 namespace eavsr {
 
@@ -345,6 +346,23 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
           const unsigned box[5] = {win2::TW, win2::TH, 1, 8, 1};
           if (encode_tensor_map(&tmo, EAVSR_F32, 5, offset, od, os_, box, 0) &&
               encode_tensor_map(&tmm, EAVSR_F32, 5, mask, md, ms_, box, 0)) {
+            // fifth generation (dcn_fwd_win3.cuh): A tile in tensor memory, window by one 4-D tensor load of x
+            CUtensorMap tmx;
+            const unsigned long long xd[4] = {(unsigned long long)CH, (unsigned long long)w, (unsigned long long)h,
+                                              (unsigned long long)n};
+            const unsigned long long xst[3] = {(unsigned long long)CH * 2, (unsigned long long)w * CH * 2,
+                                               (unsigned long long)xs[0] * 2};
+            const unsigned xbox[4] = {CH, win3::WW, win3::WH, 1};
+            if (!(flags & EAVSR_DCN_FORCE_WIN2) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                encode_tensor_map(&tmx, EAVSR_BF16, 4, x, xd, xst, xbox, 0)) {
+              auto k3 = b16 ? win3::dcn_fwd_win3_kernel<true> : win3::dcn_fwd_win3_kernel<false>;
+              cudaError_t e3 = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, win3::Smem::DYN);
+              if (e3 != cudaSuccess) { set_error("dcn_forward(win3): smem attr: %s", cudaGetErrorString(e3)); return EAVSR_ERR_CUDA; }
+              k3<<<g3, win3::THREADS, win3::Smem::DYN, st>>>((const __nv_bfloat16*)x, tmx, tmo, tmm,
+                                                           (const uint8_t*)workspace, (const __nv_bfloat16*)bias,
+                                                           (__nv_bfloat16*)out, h, w, xs[0], os[0], tiles_x, tpi, tot);
+              return check_launch("dcn_forward(win3)");
+            }
             auto k2 = b16 ? win2::dcn_fwd_win2_kernel<true> : win2::dcn_fwd_win2_kernel<false>;
             cudaError_t e2 = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, win2::Smem::DYN);
             if (e2 != cudaSuccess) { set_error("dcn_forward(win2): smem attr: %s", cudaGetErrorString(e2)); return EAVSR_ERR_CUDA; }

@@ -49,6 +49,8 @@ extern "C" {
 #define EAVSR_DCN_BLEND_FP32 8u    /* flags bit: window kernel with fp32 blend instead of bf16x2 HFMA2 */
 #define EAVSR_DCN_FORCE_WIN1 128u  /* flags bit: third-generation window kernel (cp.async-staged offsets) instead of
                                       the fourth (TMA-staged offsets; deform_groups = 8, w % 4 == 0) -- A/B timing */
+#define EAVSR_DCN_FORCE_WIN2 256u  /* flags bit: fourth-generation window kernel (A tile in shared memory) instead of
+                                      the fifth (A tile in tensor memory, dcn_fwd_win3.cuh); A/B timing and tests */
 #define EAVSR_DCN_BWD_GENERIC_DATA 32u   /* flags bit (backward): d(x), d(offset), d(mask) on the generic kernel */
 #define EAVSR_DCN_BWD_GENERIC_WEIGHT 64u /* flags bit (backward): d(weight) on the generic kernel */
 #define EAVSR_DCN_WS_PACKED 16u    /* flags bit: `workspace` still holds the packed image of this same `weight`

@@ -250,7 +250,7 @@ def test_dcn_zero_offset_equals_conv2d(cuda):
     assert max_err(out, ref) < 1e-4
 
 
-@pytest.mark.parametrize("shape", [(1, 40, 72), (3, 67, 121), (1, 270, 480)])
+@pytest.mark.parametrize("shape", [(1, 40, 72), (3, 67, 121), (2, 37, 52), (1, 270, 480)])
 def test_dcn_tc_kernels_agree(cuda, shape):
     """warp-specialised tcgen05 kernel == first-generation tcgen05 kernel == generic SIMT kernel,
     including a multi-image batch with an odd width (scalar cp.async path) and the full bench size
@@ -270,6 +270,9 @@ def test_dcn_tc_kernels_agree(cuda, shape):
     # fourth generation (TMA-staged offsets, one pixel per lane; taken by run(0) when w % 4 == 0) == third generation
     assert torch.equal(w16, run(L.DCN_FORCE_WIN1))
     assert torch.equal(w32, run(L.DCN_BLEND_FP32 | L.DCN_FORCE_WIN1))
+    # fifth generation (A tile in tensor memory, taken by run(0)) == fourth (A tile in shared memory)
+    assert torch.equal(w16, run(L.DCN_FORCE_WIN2))
+    assert torch.equal(w32, run(L.DCN_BLEND_FP32 | L.DCN_FORCE_WIN2))
     assert torch.equal(ws, v1)              # same arithmetic, bit-identical
     assert torch.equal(w32, v1)             # the window only changes where the corners are read from
     ref = _dcn_ref(xb.cpu(), off, mask, wb.cpu(), bb.cpu(), dg=8)

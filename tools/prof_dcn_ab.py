@@ -21,7 +21,7 @@ for sigma in (2.0, 0.5):
     msks = [torch.sigmoid(torch.randn(1, dg * 9, h, w, generator=g)).to(dev) for _ in range(nb)]
     wgt = ((torch.rand(64, 64, 3, 3, generator=g) * 2 - 1) / 24).to(dev, torch.bfloat16)
     bias = torch.zeros(64, device=dev, dtype=torch.bfloat16)
-    for name, flags in (("win2 (TMA offsets)", 0), ("win1 (cp.async offsets)", L.DCN_FORCE_WIN1)):
+    for name, flags in (("win3", 0), ("win2", L.DCN_FORCE_WIN2), ("win1", L.DCN_FORCE_WIN1)):
         with torch.no_grad():
             call = lambda i: _ModulatedDeformConv2dFn.apply(xs[i % nb], offs[i % nb], msks[i % nb], wgt, bias, 1, 1, 1, 1, dg, flags)  # noqa: E731
             for i in range(3):
