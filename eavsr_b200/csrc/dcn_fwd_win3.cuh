@@ -42,17 +42,20 @@ using win2::tma_load_5d;
 constexpr int PWARPS = 16, SETS = 4;
 constexpr int THREADS = (PWARPS + 3) * 32;     // 16 producers, MMA issuer, offsets loader, window / weights loader
 constexpr int TH = 8, TW = 16, CH = 64, TAPS = 9, DG = 8;
-constexpr int PAD = 5, WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 18 x 26 window
-constexpr int WIN_BYTES = WH * WW * 128;       // 59 904
+#ifndef EAVSR_WIN3_PAD
+#define EAVSR_WIN3_PAD 6
+#endif
+constexpr int PAD = EAVSR_WIN3_PAD, WH = TH + 2 * PAD, WW = TW + 2 * PAD;   // 20 x 28 window
+constexpr int WIN_BYTES = WH * WW * 128;       // 71 680
 constexpr int B_TILE = CH * CH * 2;            // 8 KB
 #ifndef EAVSR_WIN3_NSA
 #define EAVSR_WIN3_NSA 12
 #endif
 #ifndef EAVSR_WIN3_NSB
-#define EAVSR_WIN3_NSB 3
+#define EAVSR_WIN3_NSB 2
 #endif
 #ifndef EAVSR_WIN3_NOS
-#define EAVSR_WIN3_NOS 6
+#define EAVSR_WIN3_NOS 5
 #endif
 #ifndef EAVSR_ABL3
 #define EAVSR_ABL3 0      // timing ablations (tools/abl_build.sh): wrong results on purpose, never set in the product build
@@ -109,6 +112,31 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r)
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+// mbarrier wait that parks the thread in hardware (try_wait with a suspend-time hint) instead of polling with
+// nanosleep: no issue slots burnt while waiting, and the wake-up is not quantised to the sleep period.  Bounded
+// like mbar_wait (a protocol bug must trap, not hang).
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (done) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000ll) __trap();
+  } while (!done);
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
@@ -170,7 +198,7 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
       for (int j = 0; j < n_iters; ++j) {
         if (tap == 0) tile_coords(tl, n, ty0, tx0);
         const int s = j % NOS;
-        if (j >= NOS) mbar_wait(bar_oempty + 8 * s, ((j / NOS) - 1) & 1);
+        if (j >= NOS) mbar_wait_park(bar_oempty + 8 * s, ((j / NOS) - 1) & 1);
         const uint32_t bar = bar_ofull + 8 * s, dst = sO + s * O_STAGE;
         if ((EAVSR_ABL3 & 1) && j >= NOS) {
           mbar_arrive(bar);
@@ -200,7 +228,7 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
       if (my_tiles > 1) load_window(1);
       for (int j = 0; j < n_iters; ++j) {
         const int s = j % NSB;
-        if (j >= NSB) mbar_wait(bar_bempty + 8 * s, ((j / NSB) - 1) & 1);
+        if (j >= NSB) mbar_wait_park(bar_bempty + 8 * s, ((j / NSB) - 1) & 1);
         if ((EAVSR_ABL3 & 64) && j >= NSB) {
           mbar_arrive(bar_bfull + 8 * s);
         } else {
@@ -210,7 +238,7 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
         if (tap == NSB && tl >= 1 && tl + 1 < my_tiles) {
           // window of tile tl+1 into the buffer tile tl-1 used.  This step runs after the MMAs of tap (tl-1, 8)
           // completed, i.e. after every producer's last gather of tile tl-1; the barrier makes that explicit.
-          mbar_wait(bar_wine + 8 * ((tl + 1) & 1), (((tl + 1) >> 1) - 1) & 1);
+          mbar_wait_park(bar_wine + 8 * ((tl + 1) & 1), (((tl + 1) >> 1) - 1) & 1);
           load_window(tl + 1);
         }
         if (++tap == TAPS) { tap = 0; ++tl; }
@@ -225,9 +253,9 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
       int tap = 0, tl = 0;
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % NSA, sb = it % NSB, buf = tl & 1;
-        if (tap == 0 && tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
-        mbar_wait(bar_bfull + 8 * sb, (it / NSB) & 1);
-        mbar_wait(bar_afull + 8 * s, (it / NSA) & 1);
+        if (tap == 0 && tl >= 2) mbar_wait_park(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
+        mbar_wait_park(bar_bfull + 8 * sb, (it / NSB) & 1);
+        mbar_wait_park(bar_afull + 8 * s, (it / NSA) & 1);
         tc_fence_after();
         const uint64_t b_d = b_base + (uint64_t)((sb * B_TILE) >> 4);
         const uint32_t d = tmem_d + buf * CH, a = tmem_d + A_COL0 + s * A_COLS;
@@ -250,7 +278,7 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
 
     auto epilogue = [&](int tl) {
       const int buf = tl & 1;
-      mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
+      mbar_wait_park(bar_accf + 8 * buf, (tl >> 1) & 1);
       tc_fence_after();
       const int cq = set;                                      // 16-column quarter
       uint32_t acc[16];
@@ -299,14 +327,33 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
         wy0 = ty0 - PAD; wx0 = tx0 - PAD;
         winl = (sWin + (tl & 1) * WIN_BYTES) | lsel16;         // window buffers are 128-byte aligned
         pyb = (float)(ty0 + trow - 1); pxb = (float)(tx0 + tcol - 1);     // (y - 1, x - 1) of this lane's pixel
-        mbar_wait(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);     // this tile's window has landed
+        mbar_wait_park(bar_winf + 8 * (tl & 1), (tl >> 1) & 1);     // this tile's window has landed
         taps_in_tile = 0;
         newtile = false;
       }
       const int ti = (tap * 11) >> 5, tj = tap - 3 * ti;
       const float pyt = pyb + (float)ti, pxt = pxb + (float)tj;
-      mbar_wait(bar_ofull + 8 * os, oph);                      // offsets / masks of this tap have landed
+      mbar_wait_park(bar_ofull + 8 * os, oph);                      // offsets / masks of this tap have landed
       const uint32_t obl = (sO + os * O_STAGE + (uint32_t)m * 4u) | lsel512;   // stage is 4 KB aligned, m * 4 < 512
+
+      // the tap's 8 x (dy, dx, mask) into registers first (they die one sample at a time while res[] fills up, so
+      // the peak register count does not move) and the stage goes straight back to the loader: the offsets ring is
+      // then NOS - 1 taps of pure prefetch instead of being held by the four warp sets for the length of a tap
+      float ody[DG], odx[DG], omk[DG];
+#pragma unroll
+      for (int u = 0; u < DG; ++u) {
+        const uint32_t oa = obl ^ (uint32_t)(u * O_PLANE);
+        if (EAVSR_ABL3 & 32) {
+          ody[u] = __uint_as_float(oa) * 1e-9f; odx[u] = ody[u] + 0.25f; omk[u] = 0.5f;
+        } else {
+          asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(ody[u]) : "r"(oa));
+          asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(odx[u]) : "r"(oa + O_COMP));
+          asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(omk[u]) : "r"(oa + 2 * O_COMP));
+        }
+      }
+      // mbarrier.arrive is a release at CTA scope and __syncwarp orders the other lanes' loads before lane 0's arrive
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_oempty + 8 * os);
 
       uint32_t v[2][4][4];                                     // corner chunks of the two samples in flight
       uint32_t wq[2][4];                                       // their bilinear weights (bf16x2 pairs or fp32 bits)
@@ -314,15 +361,7 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
       // coordinates + gather issue of sample u (group l ^ u)
       auto issue = [&](const int u) {
         const int b = u & 1;
-        const uint32_t oa = obl ^ (uint32_t)(u * O_PLANE);
-        float dy, dx, mk;
-        if (EAVSR_ABL3 & 32) {
-          dy = __uint_as_float(oa) * 1e-9f; dx = dy + 0.25f; mk = 0.5f;
-        } else {
-        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(dy) : "r"(oa));
-        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(dx) : "r"(oa + O_COMP));
-        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(mk) : "r"(oa + 2 * O_COMP));
-        }
+        const float dy = ody[u], dx = odx[u], mk = omk[u];
         const float py = pyt + dy, px = pxt + dx;
         // floor via a saturating float->int conversion (NaN -> 0, +-huge -> INT_MIN/MAX: such cells fail the window
         // test and are rejected by the validity tests of the far path)
@@ -400,10 +439,6 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
 #pragma unroll
       for (int u = 0; u < DG; ++u) {
         if (u + 1 < DG) issue(u + 1);
-        if (u == DG - 1) {                                     // every offset of this tap has been consumed
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_oempty + 8 * os);
-        }
         blend(u);
       }
       // un-permute: position g must hold group g; it holds group l ^ g.  XOR butterfly, one stage per bit of l.
@@ -421,7 +456,7 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
           }
         }
       }
-      if (it >= NSA) mbar_wait(bar_aempty + 8 * as, aph ^ 1);  // the MMAs that read this ring slot have completed
+      if (it >= NSA) mbar_wait_park(bar_aempty + 8 * as, aph ^ 1);  // the MMAs that read this ring slot have completed
       tc_fence_after();
       tmem_st_32x32(tmem_d + ((uint32_t)(qd * 32) << 16) + A_COL0 + as * A_COLS, &res[0][0]);
       tmem_st_wait();
