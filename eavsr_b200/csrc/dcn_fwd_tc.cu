@@ -354,6 +354,7 @@ int launch_tc(const void* x, const int64_t* xs, const float* offset, const float
                                                (unsigned long long)xs[0] * 2};
             const unsigned xbox[4] = {CH, win3::WW, win3::WH, 1};
             if (!(flags & EAVSR_DCN_FORCE_WIN2) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                (reinterpret_cast<uintptr_t>(bias) & 15u) == 0 && tot < (1 << 22) &&
                 encode_tensor_map(&tmx, EAVSR_BF16, 4, x, xd, xst, xbox, 0)) {
               auto k3 = b16 ? win3::dcn_fwd_win3_kernel<true> : win3::dcn_fwd_win3_kernel<false>;
               cudaError_t e3 = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, win3::Smem::DYN);

@@ -92,13 +92,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]: A is 128 lanes x (K / 2) columns, row m in lane m, elements 2j, 2j + 1 of the
 // row in column j (low half = even element).
+// `off_mask`: bit i of the byte = 1 keeps accumulator rows 8j + i (all j) untouched (disable-output-lane vector).
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
+                                             uint32_t accumulate, uint32_t off_mask) {
+  const uint32_t mk = off_mask * 0x01010101u;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(mk)
       : "memory");
 }
 // thread i of the warp writes 32 consecutive columns of TMEM lane (quadrant base + i)
@@ -181,12 +183,22 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
   const int first = blockIdx.x;
   const int my_tiles = (total_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_iters = my_tiles * TAPS;
+  // tile -> (image, tile row, tile column) without integer division (it ran once per warp and tile, ~50 instructions
+  // each): float reciprocal + one-step correction, exact for tile counts below 2^22
+  const float rcp_tpi = 1.f / (float)tiles_per_img, rcp_tx = 1.f / (float)tiles_x;
+  auto divmod = [](int a, int d, float rcp, int& q, int& r) {
+    q = __float2int_rz((float)a * rcp);
+    r = a - q * d;
+    if (r < 0) { r += d; --q; }
+    if (r >= d) { r -= d; ++q; }
+  };
   auto tile_coords = [&](int tl, int& n, int& ty0, int& tx0) {
     const int tile = first + tl * (int)gridDim.x;
-    n = tile / tiles_per_img;
-    const int rem = tile - n * tiles_per_img;
-    ty0 = (rem / tiles_x) * TH;
-    tx0 = (rem % tiles_x) * TW;
+    int rem, ty, tx;
+    divmod(tile, tiles_per_img, rcp_tpi, n, rem);
+    divmod(rem, tiles_x, rcp_tx, ty, tx);
+    ty0 = ty * TH;
+    tx0 = tx * TW;
   };
 
   if (warp == PWARPS + 1) {
@@ -259,8 +271,15 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
         tc_fence_after();
         const uint64_t b_d = b_base + (uint64_t)((sb * B_TILE) >> 4);
         const uint32_t d = tmem_d + buf * CH, a = tmem_d + A_COL0 + s * A_COLS;
+        // Rows are in four classes c = (pixel >> 1) & 3: a class-c row keeps the group pair j at column block j ^ c
+        // (the producers only undo bit 0 of their sampling order, see below).  One MMA per (group pair j, class c)
+        // with the other classes' accumulator rows masked off: 4x the tensor work on a pipe that was 7 % busy, for
+        // 64 fewer selects per pixel and tap in the producers.  Every row still accumulates j = 0..3 in order.
 #pragma unroll
-        for (int k = 0; k < CH / 16; ++k) umma_bf16_ts(d, a + 8 * k, b_d + 2 * k, IDESC, (tap | k) != 0);
+        for (int j = 0; j < CH / 16; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            umma_bf16_ts(d, a + 8 * (j ^ c), b_d + 2 * j, IDESC, (tap | j) != 0, 0xFFu ^ (3u << (2 * c)));
         umma_commit(bar_aempty + 8 * s);
         umma_commit(bar_bempty + 8 * sb);
         if (tap == TAPS - 1) umma_commit(bar_accf + 8 * buf);
@@ -300,8 +319,17 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
       if (gy < H && gx < W) {
         __nv_bfloat16* op = out + (size_t)n * os_n + ((size_t)gy * W + gx) * CH + cq * 16;
         float f[16];
+        uint32_t bw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (bias) {
+          const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(bias + cq * 16));
+          const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(bias + cq * 16) + 1);
+          bw[0] = b0.x; bw[1] = b0.y; bw[2] = b0.z; bw[3] = b0.w; bw[4] = b1.x; bw[5] = b1.y; bw[6] = b1.z; bw[7] = b1.w;
+        }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(acc[e]) + (bias ? __bfloat162float(bias[cq * 16 + e]) : 0.f);
+        for (int e = 0; e < 16; e += 2) {
+          f[e] = __uint_as_float(acc[e]) + bf16lo_to_f32(bw[e >> 1]);
+          f[e + 1] = __uint_as_float(acc[e + 1]) + bf16hi_to_f32(bw[e >> 1]);
+        }
 #pragma unroll
         for (int e = 0; e < 16; e += 8) {
           uint4 u;
@@ -441,9 +469,10 @@ dcn_fwd_win3_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__
         if (u + 1 < DG) issue(u + 1);
         blend(u);
       }
-      // un-permute: position g must hold group g; it holds group l ^ g.  XOR butterfly, one stage per bit of l.
+      // position u holds group l ^ u.  Bit 0 of the permutation is undone here (one stage of an XOR butterfly of
+      // selects); bits 1 and 2 move whole 16-channel MMA K-blocks and are undone by the MMA issuer's row classes.
 #pragma unroll
-      for (int bit = (EAVSR_ABL3 & 128) ? DG : 1; bit < DG; bit <<= 1) {
+      for (int bit = (EAVSR_ABL3 & 128) ? DG : 1; bit < 2; bit <<= 1) {
         const bool sw = (l & bit) != 0;
 #pragma unroll
         for (int u = 0; u < DG; ++u) {
