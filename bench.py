@@ -487,6 +487,9 @@ def dcn_affine_us(device, peaks, iters=40):
             "tensor_frac": round(flops / sec / 1e12 / peaks["bf16_tflops"], 4)}
 
 
+DCN_WIN3_NCU_TRAFFIC = 138.66e6     # bytes per launch, profiles/r2_dcn_fwd_win3_ncu.txt
+
+
 def dcn_roofline(device, peaks, dg=8, iters=60, nested=True):
     import eavsr_b200 as E
     h, w = LR_H, LR_W
@@ -526,10 +529,11 @@ def dcn_roofline(device, peaks, dg=8, iters=60, nested=True):
     flops = 2.0 * px * 64 * 64 * 9
     ach = bytes_alg / sec / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
-    # capture summarised in profiles/r1_dcn_fwd_win_ncu.txt (128.7 MB read + 9.0 MB written; the 16.6 MB
+    # capture summarised in profiles/r2_dcn_fwd_win3_ncu.txt (128.75 MB read + 9.91 MB written; the 16.6 MB
     # output is only partly evicted from L2 within the launch)
-    traffic = 137.7e6 if dg == 8 else None
-    res = {"kernel": "win::dcn_fwd_win_kernel<dg=%d,bf16> 1x64x270x480" % dg, "bound": "hbm", "achieved": round(ach, 1),
+    traffic = DCN_WIN3_NCU_TRAFFIC if dg == 8 else None
+    kname = "win3::dcn_fwd_win3_kernel<bf16> dg=8" if dg == 8 else "win::dcn_fwd_win_kernel<dg=%d,bf16>" % dg
+    res = {"kernel": kname + " 1x64x270x480", "bound": "hbm", "achieved": round(ach, 1),
            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
            "peak_source": peaks["source"], "us_per_launch": round(sec * 1e6, 2),
            "algorithmic_bytes_per_launch": bytes_alg,

@@ -33,6 +33,8 @@
 // Two TMEM accumulators (2 x 64 columns) decouple the epilogues from the next tile's MMAs.
 #include <cstdlib>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace eavsr {
@@ -44,14 +46,16 @@ constexpr int CV_PW = 32;                       // halo pitch in pixels (= MMA r
 constexpr int CV_HROWS = (CV_TR + 2) * CV_PW;   // 192 staged halo positions
 constexpr int CV_ROWS = 200;                    // + padding rows read by the wrap-around outputs
 constexpr int CV_ASTAGE = CV_ROWS * 128;        // 200 rows of 64 bf16 (25 x 1024 B: stages stay atom-aligned)
-constexpr int CV_NS = 4;                        // one stage per producer warp
+constexpr int CV_NS = 6;                        // halo stages (plain layers: one TMA tensor load per tile and stage)
+constexpr int CV_NSF = 4;                       // stages used when producer WARPS build the tile: one per warp
 constexpr int CV_BTILE = CV_CH * CV_CH * 2;     // 8 KB per tap
 constexpr int CV_PRODUCERS = 128;
 // 4 producer + 1 MMA + 2 x 4 epilogue + 4 helper-producer warps.  17 warps put 5 on one SM sub-partition
 // (16 K registers each), so the kernel is held to 96 registers per thread -- 116 would compile for a
 // 64 K register file but fails to launch.
 constexpr int CV_THREADS = 544;
-constexpr int CV_TMEM = 128;
+constexpr int CV_ACC = 3 * CV_CH;              // accumulator columns per buffer: one 64-column block per tap column c
+constexpr int CV_TMEM = 512;                    // two buffers of 192 (allocations are powers of two)
 constexpr int CV_MAXN = 8;                      // images per call in the fused channel-attention mode
 
 struct CvSmem {
@@ -59,7 +63,7 @@ struct CvSmem {
   static constexpr int A_OFF = B_OFF + 9 * CV_BTILE;               // 3 stages
   static constexpr int BIAS_OFF = ((A_OFF + CV_NS * CV_ASTAGE + 15) / 16) * 16;   // 64 fp32
   static constexpr int RED_OFF = BIAS_OFF + CV_CH * 4;             // 64 fp32: per-CTA channel sums before the atomics
-  static constexpr int SCALE_OFF = RED_OFF + CV_CH * 4;            // fused channel attention: CV_MAXN x 64 fp32 scales
+  static constexpr int SCALE_OFF = RED_OFF + 2 * CV_CH * 4;        // (one RED region per epilogue team)            // fused channel attention: CV_MAXN x 64 fp32 scales
   static constexpr int BAR_OFF = SCALE_OFF + CV_MAXN * CV_CH * 4;
   // two sets (layers alternate; the idle set is re-initialised off the critical path) of
   // full[NS], empty[NS], accf[2], acce[2], wbar; then the tmem slot
@@ -96,14 +100,17 @@ struct ConvLayerDev {
   const __nv_bfloat16 *w1, *b1, *w2, *b2;
   __nv_bfloat16* y_out;
   float slope;
-  int pad_;
+  int tma;                         // plain layer whose halo tiles come by tensor loads through `tm`
+  // (64 ch, W, H, N) bf16 view of x, box (64, 32, 6, 1), 128-byte swizzle: the box lands in a stage exactly as the
+  // K-major SW128 operand layout the MMA descriptors describe, out-of-image pixels zero-filled (= the padding)
+  alignas(64) CUtensorMap tm;
 };
 // A whole residual group in ONE launch (RCAGroup = 61 chained 64->64 convolutions,
 // models/networks.py:467-482): the persistent CTAs walk the layers, separated by a grid-wide barrier (every layer
 // reads what all CTAs of the previous one wrote).  What a launch per convolution pays 61 times -- launch gap, TMEM
 // allocation, a cold 72 KB weight load in front of the first MMA, pipeline drain -- is paid once or hidden: the next
 // layer's weights stream in while the CTA waits at the barrier.  Kernel parameters are the layer table itself
-// (<= 64 layers, 6.7 KB of the 32 KB parameter space), so nothing has to be staged in device memory.
+// (<= 64 layers, 16 KB of the 32 KB parameter space with the tensor maps), so nothing has to be staged in device memory.
 constexpr int CV_MAXL = 64;
 struct ChainParams {
   int nlayers, H, W, tiles_x, tiles_per_img, total_tiles, nimg;
@@ -136,9 +143,10 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
   const uint32_t sB = base + CvSmem::B_OFF, sA = base + CvSmem::A_OFF, bars0 = base + CvSmem::BAR_OFF;
   const uint32_t tmem_slot_addr = bars0 + 2 * CvSmem::NBARS * 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CvSmem::BAR_OFF + 2 * CvSmem::NBARS * 8);
-  auto init_bar_set = [&](uint32_t b0, bool fused_layer) {
+  auto init_bar_set = [&](uint32_t b0, const ConvLayerDev& l) {
+    const uint32_t full_count = l.res ? 64 : (l.tma ? 1 : 32);  // two warps / the TMA-issuing thread / one warp per stage
     for (int s = 0; s < CV_NS; ++s) {
-      mbar_init(b0 + 8 * s, fused_layer ? 64 : 32);           // full: fused input transform = two warps fill a stage
+      mbar_init(b0 + 8 * s, full_count);
       mbar_init(b0 + (CV_NS + s) * 8, 1);                     // empty
     }
     for (int b = 0; b < 2; ++b) {
@@ -165,6 +173,8 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
   for (int li = 0; li < P.nlayers; ++li) {
     const ConvLayerDev& Ly = P.L[li];
     const bool fused = Ly.res != nullptr;
+    const bool tma = !fused && Ly.tma != 0;
+    const int NS = tma ? CV_NS : CV_NSF;                        // stages in use this layer
     const __nv_bfloat16* __restrict__ x = Ly.x;
     // ---------------- layer prologue ----------------
     // Layers alternate between two mbarrier sets: this layer's set was initialised while the previous layer ran.
@@ -173,7 +183,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
     const uint32_t bar_acce = bar_accf + 16, bar_w = bar_acce + 16;
     if (li == 0) {
       if (tid == 0) {
-        init_bar_set(bars, fused);
+        init_bar_set(bars, Ly);
         fence_mbar_init();
       }
       fence_proxy_async_smem();                                 // the zeroed padding rows, before any MMA reads them
@@ -205,7 +215,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
       const uint32_t nb = bars0 + ((li + 1) & 1) * CvSmem::NBARS * 8;
       if (li > 0)
         for (int b = 0; b < CvSmem::NBARS; ++b) mbar_inval(nb + 8 * b);
-      init_bar_set(nb, P.L[li + 1].res != nullptr);
+      init_bar_set(nb, P.L[li + 1]);
       fence_mbar_init();
     }
 
@@ -230,7 +240,27 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
     // start at once, and four tiles per SM (14 MB) in one burst delay the first tile, the one the MMA warp is
     // waiting for, by ~1.5 us of L2 bandwidth (phase timestamps, tools/prof_chain.py).  Warps 1-3 start their
     // tiles when tile 0 has landed; those land while tile 0 is being multiplied.
-    if (!fused && warp == 0 && my_tiles > 0) issue_tile(0);
+    // Tensor-load layers: one thread requests the first NS tiles back to back (the TMA unit serves them in order, so
+    // tile 0 still lands first) and keeps the ring full from the producer branch below.
+    auto issue_tile_tma = [&](int tl) {
+      const int tile = first + tl * (int)gridDim.x;
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+      const int s = tl % CV_NS;
+      mbar_arrive_expect_tx(bar_full + 8 * s, CV_HROWS * 128);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+              "r"(sA + s * CV_ASTAGE),
+          "l"(reinterpret_cast<uint64_t>(&Ly.tm)), "r"(0), "r"(x0), "r"(y0), "r"(n), "r"(bar_full + 8 * s)
+          : "memory");
+    };
+    if (tma) {
+      if (warp == 4 && elect_one()) {
+        // (reader side of the cross-proxy hand-over: the acquire of the grid barrier was a generic-proxy operation)
+        if (li > 0) asm volatile("fence.proxy.async.global;\n" ::: "memory");
+        for (int tl = 0; tl < my_tiles && tl < CV_NS; ++tl) issue_tile_tma(tl);
+      }
+    } else if (!fused && warp == 0 && my_tiles > 0) issue_tile(0);
     if (fused && warp >= 5 && warp < 13) {
       // squeeze-excite MLP of the previous block, once per CTA: 256 threads = 4 hidden units x 64 channels
       float* scale = reinterpret_cast<float*>(smem + CvSmem::SCALE_OFF);
@@ -258,8 +288,10 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
     tmem_d = *tmem_slot;
     if (tid == 0) CV_TRACE(li, 2);
 
-    if (warp < 4 || warp >= 13) {
+    if (!tma && (warp < 4 || warp >= 13)) {
       // ===================== producers =====================
+      // (tensor-load layers have no producer warps: the MMA thread re-issues a stage's load when the MMAs that read
+      // it have completed, and warps 0-3 / 13-16 form a second epilogue team)
       // (warps 13-16 only work in the fused-input mode, where they build the second half of the halo tile of
       // "their" stage: the transform is load-latency bound, two warps per stage keep enough loads in flight)
       const int phalf = warp >= 13 ? 1 : 0;
@@ -268,8 +300,8 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
       // halo tile in, waits for ITS copies only and publishes.  The four warps are independent, so up
       // to four tiles are in flight and a late MMA never delays the publication of a landed tile.
       const float* scale = reinterpret_cast<const float*>(smem + CvSmem::SCALE_OFF);
-      for (int tl = (phalf && !fused) ? my_tiles : warp_s; tl < my_tiles; tl += CV_NS) {
-        const int u = tl / CV_NS;
+      for (int tl = (phalf && !fused) ? my_tiles : warp_s; tl < my_tiles; tl += CV_NSF) {
+        const int u = tl / CV_NSF;
         if (u >= 1) mbar_wait(bar_empty + 8 * warp_s, (u - 1) & 1);
         if (!fused) {
           if (u == 0 && warp_s > 0) mbar_wait(bar_full, 0);      // tile 0 first (see the prologue)
@@ -332,40 +364,60 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
       if (elect_one()) {
         mbar_wait(bar_w, 0);
         CV_TRACE(li, 3);
-        constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_CH);
+        // One MMA covers the three taps of a kernel ROW: the A operand is the halo tile advanced by r whole halo
+        // rows (32 pixel rows = 4 swizzle atoms, so every view is atom-aligned) and the B operand is the three
+        // 64 x 64 weight tiles of taps (r, 0..2) read as one N = 192 tile (they are contiguous in shared memory).
+        // Accumulator block c then holds D_c[m] = sum_r halo(32 r + m) . W(r, c), and the output at halo position p
+        // is D_0[p] + D_1[p + 1] + D_2[p + 2] -- the epilogue's job (a tile row is one 32-lane TMEM quadrant and only
+        // its first 30 positions are outputs, so p + 2 never leaves the warp).  Per K = 16 step an SS-mode MMA now
+        // fetches A 4 KB + B 6 KB for 96 cycles of tensor work instead of 3 x (4 + 2) KB for 3 x 32: the operand
+        // fetch that bounded the N = 64 form (67 cycles per MMA, 36 per tile) is off the critical path.
+        constexpr uint32_t IDESC = umma_idesc_bf16(128, CV_ACC);
         const uint64_t b_base = umma_desc_sw128_kmajor(sB);
         for (int tl = 0; tl < my_tiles; ++tl) {
-          const int s = tl % CV_NS, buf = tl & 1;
+          const int s = tl % NS, buf = tl & 1;
           if (tl >= 2) mbar_wait(bar_acce + 8 * buf, ((tl >> 1) - 1) & 1);
-          mbar_wait(bar_full + 8 * s, (tl / CV_NS) & 1);
+          mbar_wait(bar_full + 8 * s, (tl / NS) & 1);
           if (tl == 0) CV_TRACE(li, 4);
           if (tl == 1) CV_TRACE(li, 5);
           if (tl == my_tiles - 1) CV_TRACE(li, 6);
           tc_fence_after();
           const uint64_t a_base = umma_desc_sw128_kmajor(sA + s * CV_ASTAGE);
-          const uint32_t d = tmem_d + buf * CV_CH;
+          const uint32_t d = tmem_d + buf * CV_ACC;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
+          for (int r = 0; r < 3; ++r) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              // tap view: start (r*32 + s) rows further; K step = 32 B.  The swizzle XOR is taken from the
-              // absolute shared-memory address bits, so the shifted view needs no base_offset (measured:
-              // base_offset = s gives wrong results, 0 is exact).
-              const uint64_t adesc = a_base + (uint64_t)((((t / 3) * CV_PW + (t % 3)) * 128) >> 4) + 2 * k;
-              const uint64_t bdesc = b_base + (uint64_t)((t * CV_BTILE) >> 4) + 2 * k;
-              umma_bf16(d, adesc, bdesc, IDESC, (t | k) != 0);
+              // the swizzle XOR is taken from the absolute shared-memory address bits, so a shifted view needs no
+              // base_offset (measured in round 1 on the per-tap views)
+              const uint64_t adesc = a_base + (uint64_t)((r * CV_PW * 128) >> 4) + 2 * k;
+              const uint64_t bdesc = b_base + (uint64_t)((r * 3 * CV_BTILE) >> 4) + 2 * k;
+              umma_bf16(d, adesc, bdesc, IDESC, (r | k) != 0);
             }
           }
           umma_commit(bar_empty + 8 * s);
           umma_commit(bar_accf + 8 * buf);
           if (tl == my_tiles - 1) CV_TRACE(li, 7);
+          // tensor-load layers: refill the stage tile tl-1 used.  Its MMAs complete while tile tl's execute, so this
+          // wait returns long before the tensor pipe runs dry and the ring stays CV_NS - 1 tiles ahead.
+          if (tma && tl >= 1 && tl - 1 + CV_NS < my_tiles) {
+            mbar_wait(bar_empty + 8 * ((tl - 1) % CV_NS), ((tl - 1) / CV_NS) & 1);
+            issue_tile_tma(tl - 1 + CV_NS);
+          }
         }
       }
       __syncwarp();
-    } else if (warp < 13) {
-      // ===================== epilogue (warps 5..12 -> TMEM lane quadrants 1,2,3,0, 1,2,3,0) =====================
+    } else {
+      // ===================== epilogue =====================
+      // Team 0 = warps 5..12 (TMEM lane quadrants 1,2,3,0, 1,2,3,0).  A tile's epilogue is ~450 dependent instructions
+      // of ONE warp per (quadrant, channel half) -- 1.5 us, the step that paced the whole pipeline (the MMA thread sat
+      // waiting for a free accumulator; ncu: profiles/r2_conv3x3_tc_ncu.txt) -- so in tensor-load layers the idle
+      // producer warps 0..3 and 13..16 (quadrants 0,1,2,3, 1,2,3,0) form team 1 and the teams alternate tiles: team t
+      // always drains accumulator buffer t.
+      const int team = (warp >= 5 && warp < 13) ? 0 : 1;
+      const int nteams = tma ? 2 : 1;
       const int q = warp & 3;                       // output row of the tile handled by this warp
-      const int chalf = (warp - 5) >> 2;            // this group's 32 output channels
+      const int chalf = team == 0 ? (warp - 5) >> 2 : (warp >= 13 ? 1 : 0);   // this warp's 32 output channels
       constexpr int HC = CV_CH / 2;
       float* const chan_sums = Ly.chan_sums;
       __nv_bfloat16* const out = Ly.out;
@@ -394,59 +446,80 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
           }
           // four warps hold the same 32 channels: combine them in shared memory, one global atomic per
           // channel and CTA (148 instead of 592 reductions on each of the 64 addresses)
-          float* red = reinterpret_cast<float*>(smem + CvSmem::RED_OFF);
-          asm volatile("bar.sync 2, 256;\n" ::: "memory");       // previous flush fully drained
+          float* red = reinterpret_cast<float*>(smem + CvSmem::RED_OFF) + team * CV_CH;
+          const int bar_id = 2 + team;                         // the team's own named barrier
+          asm volatile("bar.sync %0, 256;\n" ::"r"(bar_id) : "memory");       // previous flush fully drained
           if (q == 0) red[chalf * HC + lane] = csum[0];
-          asm volatile("bar.sync 2, 256;\n" ::: "memory");
+          asm volatile("bar.sync %0, 256;\n" ::"r"(bar_id) : "memory");
           if (q != 0) atomicAdd(red + chalf * HC + lane, csum[0]);
-          asm volatile("bar.sync 2, 256;\n" ::: "memory");
+          asm volatile("bar.sync %0, 256;\n" ::"r"(bar_id) : "memory");
           if (q == 0) atomicAdd(chan_sums + cur_n * CV_CH + chalf * HC + lane, red[chalf * HC + lane]);
         }
 #pragma unroll
         for (int c = 0; c < HC; ++c) csum[c] = 0.f;
       };
-      for (int tl = 0; tl < my_tiles; ++tl) {
+      const float rcp_tpi = 1.f / (float)tiles_per_img, rcp_tx = 1.f / (float)tiles_x;
+      auto divmod = [](int a, int d, float rcp, int& qo, int& r) {   // exact for a < 2^22: float estimate + one correction
+        qo = __float2int_rz((float)a * rcp);
+        r = a - qo * d;
+        if (r < 0) { r += d; --qo; }
+        if (r >= d) { r -= d; ++qo; }
+      };
+      for (int tl = team; tl < my_tiles; tl += nteams) {
         const int buf = tl & 1;
         const int tile = first + tl * (int)gridDim.x;
-        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        int n, rem, ty, tx;
+        divmod(tile, tiles_per_img, rcp_tpi, n, rem);
+        divmod(rem, tiles_x, rcp_tx, ty, tx);
         if (n != cur_n) { flush(); cur_n = n; }
-        const int oy = (rem / tiles_x) * CV_TR + q, ox = (rem % tiles_x) * CV_TC + lane;
+        const int oy = ty * CV_TR + q, ox = tx * CV_TC + lane;
         const bool valid = lane < CV_TC && oy < H && ox < W;
         mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
-        if (warp == 5 && lane == 0) { if (tl == 0) CV_TRACE(li, 8); if (tl == my_tiles - 1) CV_TRACE(li, 9); }
+        if ((warp == 5 || warp == 0) && lane == 0) { if (tl == 0) CV_TRACE(li, 8); if (tl == my_tiles - 1) CV_TRACE(li, 9); }
         tc_fence_after();
-        uint32_t acc[HC];
-        tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_CH + chalf * HC, acc);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-        float f[HC];
+        // out(p) = D_0(p) + D_1(p + 1) + D_2(p + 2): three accumulator blocks, the second and third read one and two
+        // TMEM lanes (= lanes of this warp) further.  16 channels (one 32-byte sector of the NHWC row) at a time.
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + buf * CV_ACC + chalf * HC;
+        __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH + chalf * HC;
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-          const float t = __uint_as_float(acc[c]) + bsm[c];
-          f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
-        }
-        if (valid) {
-          __nv_bfloat16* op = out + ((size_t)n * H * W + (size_t)oy * W + ox) * CV_CH + chalf * HC;
+        for (int j = 0; j < HC; j += 16) {
+          uint32_t a0[16], a1[16], a2[16];
+          tmem_ld_32x16(tbase + j, a0);
+          tmem_ld_32x16(tbase + CV_CH + j, a1);
+          tmem_ld_32x16(tbase + 2 * CV_CH + j, a2);
+          tmem_ld_wait();
+          if (j + 16 == HC) {                                  // accumulator drained: the MMAs of tile tl + 2 may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+          }
+          float f[16];
 #pragma unroll
-          for (int c = 0; c < HC; c += 16) {                   // one full 32-byte sector per store
+          for (int c = 0; c < 16; ++c) {
+            const float t = __uint_as_float(a0[c]) + __shfl_down_sync(0xffffffffu, __uint_as_float(a1[c]), 1) +
+                            __shfl_down_sync(0xffffffffu, __uint_as_float(a2[c]), 2) + bsm[j + c];
+            f[c] = valid ? (t > 0.f ? t : t * slope) : 0.f;
+          }
+          if (valid) {                                         // one full 32-byte sector per store
             uint32_t u[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[c + 2 * e], f[c + 2 * e + 1]);
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(op + c), "r"(u[0]), "r"(u[1]),
+            for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(op + j), "r"(u[0]), "r"(u[1]),
                          "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
                          : "memory");
           }
-        }
-        if (chan_sums) {
+          if (chan_sums) {
 #pragma unroll
-          for (int c = 0; c < HC; ++c) csum[c] += f[c];
+            for (int c = 0; c < 16; ++c) csum[j + c] += f[c];
+          }
         }
       }
       flush();
       if (warp == 5 && lane == 0) CV_TRACE(li, 10);
     }
+    // What this thread stored (outputs, y_out) may be read by another CTA's TENSOR loads in the next layer: order the
+    // generic-proxy writes before the async proxy, ahead of the barrier (A) / the grid-barrier arrive that publish them.
+    if (li + 1 < P.nlayers) asm volatile("fence.proxy.async.global;\n" ::: "memory");
   }
 
   tc_fence_before();
@@ -505,13 +578,22 @@ int conv3x3_launch_chain(ChainParams& P, int n, int h, int w, int dtype, cudaStr
   const int tiles_x = ceil_div(w, CV_TC), tiles_y = ceil_div(h, CV_TR);
   const int tiles_per_img = tiles_x * tiles_y;
   const long long total = (long long)tiles_per_img * n;
-  EAVSR_REQUIRE(total < (1ll << 30), "%s: too many tiles", who);
+  EAVSR_REQUIRE(total < (1ll << 22), "%s: too many tiles", who);   // (float-reciprocal tile coordinates are exact below 2^22)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(total < sms ? total : sms);
   P.H = h; P.W = w; P.tiles_x = tiles_x; P.tiles_per_img = tiles_per_img; P.total_tiles = (int)total; P.nimg = n;
   P.inv_hw = 1.f / ((float)h * (float)w);
+  for (int i = 0; i < P.nlayers; ++i) {
+    ConvLayerDev& L = P.L[i];
+    L.tma = 0;
+    if (L.res) continue;
+    const unsigned long long dims[4] = {CV_CH, (unsigned long long)w, (unsigned long long)h, (unsigned long long)n};
+    const unsigned long long str[3] = {CV_CH * 2ull, (unsigned long long)w * CV_CH * 2, (unsigned long long)h * w * CV_CH * 2};
+    const unsigned box[4] = {CV_CH, CV_PW, CV_TR + 2, 1};
+    if (encode_tensor_map(&L.tm, EAVSR_BF16, 4, L.x, dims, str, box, 3 /* CU_TENSOR_MAP_SWIZZLE_128B */)) L.tma = 1;
+  }
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem::DYN);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
   if (P.nlayers == 1) {

@@ -317,10 +317,15 @@ def test_rca_group_chain_equals_launch_per_convolution(cuda, nb, shape):
         again = grp(xb)                      # recycled buffers / re-armed grid barrier: a second call is the same
     assert n1 - n0 == 2 * nb + 1 and n2 - n1 == 1
     rms = per_conv.float().pow(2).mean().sqrt().item()
-    # the channel sums are accumulated with atomics in a different order: equal up to that rounding
-    assert (chained.float() - per_conv.float()).abs().max().item() <= 2e-2 * rms
+    # the channel sums are accumulated with atomics in a different order (more so with two epilogue teams): equal up
+    # to that rounding -- worst element within 2 % of the RMS or two bf16 ulps of its own magnitude, bulk within 0.2 %
+    def close(a, b):
+        a, b = a.float(), b.float()
+        return bool(((a - b).abs() <= torch.maximum(torch.full_like(b, 2e-2 * rms), b.abs() * 2.0 ** -6)).all())
+    assert close(chained, per_conv)
     assert (chained.float() - per_conv.float()).pow(2).mean().sqrt().item() <= 2e-3 * rms
-    assert (again.float() - chained.float()).abs().max().item() <= 2e-2 * rms
+    assert close(again, chained)
+    assert (again.float() - chained.float()).pow(2).mean().sqrt().item() <= 2e-3 * rms
     if ref is not None:
         assert (chained.double().cpu() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
 

@@ -16,6 +16,11 @@ from bench import load_peaks  # noqa: E402
 dev = torch.device("cuda:0")
 peaks = load_peaks()
 res = []
+# Everything -- input creation, forwards kept for the backward timings, graph capture, events -- runs on ONE side
+# stream: autograd runs a backward node on the stream its forward ran on, and a forward left on the legacy default
+# stream cannot be joined from a capturing stream (cudaErrorStreamCaptureImplicit).
+SIDE = torch.cuda.Stream(dev)
+torch.cuda.set_stream(SIDE)
 
 
 def timeit(fn, iters, warm=3, graph=True):
@@ -29,7 +34,7 @@ def timeit(fn, iters, warm=3, graph=True):
     if graph:
         g = torch.cuda.CUDAGraph()
         keep = []
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=SIDE):
             for i in range(iters):
                 keep.append(fn(i))
         g.replay()

@@ -33,6 +33,14 @@ elif what in ("dcn", "dcn_bwd", "dcn_bwd_nox"):
         for _ in range(2):
             out = E.modulated_deform_conv2d(x, off, msk, wgt, bias, 1, 1, 1, 1, dg)
             out.backward(torch.ones_like(out))
+elif what == "conv":
+    from eavsr_b200 import ops
+    h, w = (272, 480) if len(sys.argv) < 3 else (int(sys.argv[2]), int(sys.argv[3]))
+    conv = torch.nn.Conv2d(64, 64, 3, padding=1).to(dev, torch.bfloat16).to(memory_format=torch.channels_last)
+    xs = [torch.randn(1, 64, h, w, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(3)]
+    with torch.no_grad():
+        for i in range(3):
+            ops.conv3x3_64(conv, xs[i], 0.0)
 elif what == "warp_bwd":
     x = torch.randn(1, 64, 270, 480, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
     flow = (torch.randn(1, 2, 270, 480, generator=g) * 3).to(dev).requires_grad_()

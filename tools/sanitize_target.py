@@ -41,6 +41,14 @@ if "dcn" in which:
         leaves = [cl(x.to(dev, dtype)).requires_grad_(), off.to(dev).requires_grad_(), mask.to(dev).requires_grad_(),
                   w.to(dev, dtype).requires_grad_(), b.to(dev, dtype).requires_grad_()]
         E.modulated_deform_conv2d(*leaves, 1, 1, 1, 1, dg).float().square().mean().backward()
+    # w % 4 == 0, bf16, dg = 8: the TMA-fed window kernels (fifth generation, and the fourth via its force flag)
+    from eavsr_b200 import _lib as L
+    from eavsr_b200.ops import _ModulatedDeformConv2dFn
+    x, off, mask, w, b = dcn_inputs(2, 64, 21, 36, 64, 8, seed=5)
+    args = (cl(x.to(dev, torch.bfloat16)), off.to(dev), mask.to(dev), w.to(dev, torch.bfloat16), b.to(dev, torch.bfloat16))
+    with torch.no_grad():
+        for fl in (0, L.DCN_FORCE_WIN2, L.DCN_BLEND_FP32):
+            _ModulatedDeformConv2dFn.apply(*args, 1, 1, 1, 1, 8, fl)
     x, off, mask, w, b = dcn_inputs(1, 12, 9, 11, 8, 3, seed=4, groups=2)
     leaves = [t.to(dev).requires_grad_() for t in (x, off, mask, w, b)]
     E.modulated_deform_conv2d(*leaves, 1, 1, 1, 2, 3).square().mean().backward()
