@@ -67,7 +67,8 @@ struct CvSmem {
   static constexpr int BAR_OFF = SCALE_OFF + CV_MAXN * CV_CH * 4;
   // two sets (layers alternate; the idle set is re-initialised off the critical path) of
   // full[NS], empty[NS], accf[2], acce[2], wbar; then the tmem slot
-  static constexpr int NBARS = 2 * CV_NS + 5;
+  // ... + lfull[NSF] (fused tensor-load layers: raw skip / res tiles landed) + rempty[2] (raw res buffer drained)
+  static constexpr int NBARS = 2 * CV_NS + 5 + CV_NSF + 2;
   static constexpr int TOTAL = BAR_OFF + 2 * NBARS * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
 };
@@ -100,17 +101,18 @@ struct ConvLayerDev {
   const __nv_bfloat16 *w1, *b1, *w2, *b2;
   __nv_bfloat16* y_out;
   float slope;
-  int tma;                         // plain layer whose halo tiles come by tensor loads through `tm`
+  int tma;                         // halo tiles come by tensor loads: `tm` over x (and `tm2` over res in the fused mode)
   // (64 ch, W, H, N) bf16 view of x, box (64, 32, 6, 1), 128-byte swizzle: the box lands in a stage exactly as the
   // K-major SW128 operand layout the MMA descriptors describe, out-of-image pixels zero-filled (= the padding)
   alignas(64) CUtensorMap tm;
+  alignas(64) CUtensorMap tm2;
 };
 // A whole residual group in ONE launch (RCAGroup = 61 chained 64->64 convolutions,
 // models/networks.py:467-482): the persistent CTAs walk the layers, separated by a grid-wide barrier (every layer
 // reads what all CTAs of the previous one wrote).  What a launch per convolution pays 61 times -- launch gap, TMEM
 // allocation, a cold 72 KB weight load in front of the first MMA, pipeline drain -- is paid once or hidden: the next
 // layer's weights stream in while the CTA waits at the barrier.  Kernel parameters are the layer table itself
-// (<= 64 layers, 16 KB of the 32 KB parameter space with the tensor maps), so nothing has to be staged in device memory.
+// (<= 64 layers, 24 KB of the 32 KB parameter space with the tensor maps), so nothing has to be staged in device memory.
 constexpr int CV_MAXL = 64;
 struct ChainParams {
   int nlayers, H, W, tiles_x, tiles_per_img, total_tiles, nimg;
@@ -122,8 +124,13 @@ struct ChainParams {
 #ifdef EAVSR_CONV_TRACE   // development only: per-phase timestamps of CTA 0 (tools/abl_build.sh, tools/prof_chain.py)
 __device__ unsigned long long g_conv_trace[CV_MAXL * 16];
 #define CV_TRACE(li, slot) do { if (blockIdx.x == 0) g_conv_trace[(li) * 16 + (slot)] = clock64(); } while (0)
+// per-tile stamps of CTA 0, layers 0..7, tiles 0..7: k = 0 loads landed (transform warp 0), 1 tile staged / transform
+// done (MMA thread past `full`), 2 MMAs issued, 3 accumulator ready (epilogue warp 5 or 0), 4 accumulator drained, 5 tile stored
+__device__ unsigned long long g_conv_trace2[8 * 8 * 8];
+#define CV_TRACE2(li, tl, k) do { if (blockIdx.x == 0 && (li) < 8 && (tl) < 8) g_conv_trace2[((li) * 8 + (tl)) * 8 + (k)] = clock64(); } while (0)
 #else
 #define CV_TRACE(li, slot) do { } while (0)
+#define CV_TRACE2(li, tl, k) do { } while (0)
 #endif
 
 __device__ __forceinline__ void mbar_inval(uint32_t bar) {
@@ -144,7 +151,8 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
   const uint32_t tmem_slot_addr = bars0 + 2 * CvSmem::NBARS * 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CvSmem::BAR_OFF + 2 * CvSmem::NBARS * 8);
   auto init_bar_set = [&](uint32_t b0, const ConvLayerDev& l) {
-    const uint32_t full_count = l.res ? 64 : (l.tma ? 1 : 32);  // two warps / the TMA-issuing thread / one warp per stage
+    // full: two warps of lanes (register path) or 8 transform warps (fused) / the TMA-issuing thread or one warp (plain)
+    const uint32_t full_count = l.res ? (l.tma ? 8 : 64) : (l.tma ? 1 : 32);
     for (int s = 0; s < CV_NS; ++s) {
       mbar_init(b0 + 8 * s, full_count);
       mbar_init(b0 + (CV_NS + s) * 8, 1);                     // empty
@@ -154,6 +162,8 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
       mbar_init(b0 + (2 * CV_NS + 2 + b) * 8, 8);             // acce
     }
     mbar_init(b0 + (2 * CV_NS + 4) * 8, 1);                   // weights
+    for (int s = 0; s < CV_NSF; ++s) mbar_init(b0 + (2 * CV_NS + 5 + s) * 8, 1);          // lfull
+    for (int r = 0; r < 2; ++r) mbar_init(b0 + (2 * CV_NS + 5 + CV_NSF + r) * 8, 8);      // rempty
   };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -174,6 +184,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
     const ConvLayerDev& Ly = P.L[li];
     const bool fused = Ly.res != nullptr;
     const bool tma = !fused && Ly.tma != 0;
+    const bool ftma = fused && Ly.tma != 0;                     // fused input built from TMA-staged skip / res tiles
     const int NS = tma ? CV_NS : CV_NSF;                        // stages in use this layer
     const __nv_bfloat16* __restrict__ x = Ly.x;
     // ---------------- layer prologue ----------------
@@ -181,6 +192,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
     const uint32_t bars = bars0 + (li & 1) * CvSmem::NBARS * 8;
     const uint32_t bar_full = bars, bar_empty = bars + CV_NS * 8, bar_accf = bars + 2 * CV_NS * 8;
     const uint32_t bar_acce = bar_accf + 16, bar_w = bar_acce + 16;
+    const uint32_t bar_lfull = bar_w + 8, bar_rempty = bar_lfull + CV_NSF * 8;
     if (li == 0) {
       if (tid == 0) {
         init_bar_set(bars, Ly);
@@ -254,7 +266,32 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
           "l"(reinterpret_cast<uint64_t>(&Ly.tm)), "r"(0), "r"(x0), "r"(y0), "r"(n), "r"(bar_full + 8 * s)
           : "memory");
     };
-    if (tma) {
+    // Fused tensor-load layers: the skip tile lands in A stage tl % 4 (operand layout), the residual tile in one of
+    // two raw buffers (A stages 4 and 5, same swizzle, so y = res * scale + skip is an address-wise update).
+    auto issue_tile_fused = [&](int tl) {
+      const int tile = first + tl * (int)gridDim.x;
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+      const int s = tl % CV_NSF, r = tl & 1;
+      const uint32_t bar = bar_lfull + 8 * s;
+      mbar_arrive_expect_tx(bar, 2 * CV_HROWS * 128);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+              "r"(sA + s * CV_ASTAGE),
+          "l"(reinterpret_cast<uint64_t>(&Ly.tm)), "r"(0), "r"(x0), "r"(y0), "r"(n), "r"(bar)
+          : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+              "r"(sA + (CV_NSF + r) * CV_ASTAGE),
+          "l"(reinterpret_cast<uint64_t>(&Ly.tm2)), "r"(0), "r"(x0), "r"(y0), "r"(n), "r"(bar)
+          : "memory");
+    };
+    if (ftma) {
+      if (warp == 4 && elect_one()) {
+        if (li > 0) asm volatile("fence.proxy.async.global;\n" ::: "memory");
+        for (int tl = 0; tl < my_tiles && tl < 2; ++tl) issue_tile_fused(tl);
+      }
+    } else if (tma) {
       if (warp == 4 && elect_one()) {
         // (reader side of the cross-proxy hand-over: the acquire of the grid barrier was a generic-proxy operation)
         if (li > 0) asm volatile("fence.proxy.async.global;\n" ::: "memory");
@@ -288,7 +325,64 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
     tmem_d = *tmem_slot;
     if (tid == 0) CV_TRACE(li, 2);
 
-    if (!tma && (warp < 4 || warp >= 13)) {
+    if (ftma && (warp < 4 || warp >= 13)) {
+      // ===================== fused input, tensor-load form: y = res * scale + skip, shared memory -> shared memory =====================
+      // The register path below is bound by the round trips of its global loads (first tile 5 us after the set-up,
+      // 1.56 us per tile: profiles/r2_conv_chain_trace.txt).  Here the TMA unit brings both tiles, two tiles ahead,
+      // and the eight warps only transform: lane l owns channel chunk l & 7 (its 8 scales stay in registers) of rows
+      // 24 w + (l >> 3) + 4 k; a quarter warp covers one 128-byte row, so every access is conflict-free.
+      const int widx = warp >= 13 ? warp - 9 : warp;            // 0..7
+      const int ch = lane & 7;
+      const float* scale = reinterpret_cast<const float*>(smem + CvSmem::SCALE_OFF);
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int s = tl % CV_NSF, r = tl & 1;
+        const int tile = first + tl * (int)gridDim.x;
+        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        const int y0 = (rem / tiles_x) * CV_TR - 1, x0 = (rem % tiles_x) * CV_TC - 1;
+        const size_t img = (size_t)n * H * W * CV_CH;
+        float s8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s8[e] = scale[n * CV_CH + ch * 8 + e];
+        mbar_wait(bar_lfull + 8 * s, (tl / CV_NSF) & 1);
+        if (warp == 0 && lane == 0) CV_TRACE2(li, tl, 0);
+        const uint32_t aS = sA + s * CV_ASTAGE, rS = sA + (CV_NSF + r) * CV_ASTAGE;
+        constexpr int NB = CV_HROWS / 8 / 4;                    // 6 rows per lane
+        uint4 rv[NB], sv[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int p = widx * (CV_HROWS / 8) + (lane >> 3) + 4 * b;
+          const uint32_t o = (uint32_t)p * 128u + (uint32_t)((ch ^ (p & 7)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                       : "=r"(sv[b].x), "=r"(sv[b].y), "=r"(sv[b].z), "=r"(sv[b].w) : "r"(aS + o));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                       : "=r"(rv[b].x), "=r"(rv[b].y), "=r"(rv[b].z), "=r"(rv[b].w) : "r"(rS + o));
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int p = widx * (CV_HROWS / 8) + (lane >> 3) + 4 * b;
+          const uint32_t o = (uint32_t)p * 128u + (uint32_t)((ch ^ (p & 7)) << 4);
+          const int hr = p >> 5, hc = p & 31;
+          const int gy = y0 + hr, gx = x0 + hc;
+          const uint32_t rw[4] = {rv[b].x, rv[b].y, rv[b].z, rv[b].w}, sw[4] = {sv[b].x, sv[b].y, sv[b].z, sv[b].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            ow[e] = pack_bf16x2(bf16lo_to_f32(rw[e]) * s8[2 * e] + bf16lo_to_f32(sw[e]),
+                                bf16hi_to_f32(rw[e]) * s8[2 * e + 1] + bf16hi_to_f32(sw[e]));
+          // (outside the image both tiles were zero-filled: y = 0 = the convolution's padding)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(aS + o), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3])
+                       : "memory");
+          if (hr >= 1 && hr <= CV_TR && hc >= 1 && hc <= CV_TC && gy < H && gx < W)      // this tile owns the pixel
+            *reinterpret_cast<uint4*>(Ly.y_out + img + ((size_t)gy * W + gx) * CV_CH + ch * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_full + 8 * s);
+          mbar_arrive(bar_rempty + 8 * r);
+        }
+      }
+    } else if (!tma && (warp < 4 || warp >= 13)) {
       // ===================== producers =====================
       // (tensor-load layers have no producer warps: the MMA thread re-issues a stage's load when the MMAs that read
       // it have completed, and warps 0-3 / 13-16 form a second epilogue team)
@@ -382,6 +476,16 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
           if (tl == 1) CV_TRACE(li, 5);
           if (tl == my_tiles - 1) CV_TRACE(li, 6);
           tc_fence_after();
+          CV_TRACE2(li, tl, 1);
+          // fused tensor-load layers: request tile tl+2 now, BEFORE this tile's MMAs (their issue blocks while the
+          // tensor pipe still works on tile tl-1, and the raw ring is only two deep).  Its raw buffer was drained by
+          // the transform of tile tl (just waited for), its A stage by the MMAs of tile tl-2.
+          if (ftma && tl + 2 < my_tiles) {
+            const int nt = tl + 2;
+            if (nt >= CV_NSF) mbar_wait(bar_empty + 8 * (nt % CV_NSF), ((nt / CV_NSF) - 1) & 1);
+            mbar_wait(bar_rempty + 8 * (nt & 1), ((nt >> 1) - 1) & 1);
+            issue_tile_fused(nt);
+          }
           const uint64_t a_base = umma_desc_sw128_kmajor(sA + s * CV_ASTAGE);
           const uint32_t d = tmem_d + buf * CV_ACC;
 #pragma unroll
@@ -397,6 +501,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
           }
           umma_commit(bar_empty + 8 * s);
           umma_commit(bar_accf + 8 * buf);
+          CV_TRACE2(li, tl, 2);
           if (tl == my_tiles - 1) CV_TRACE(li, 7);
           // tensor-load layers: refill the stage tile tl-1 used.  Its MMAs complete while tile tl's execute, so this
           // wait returns long before the tensor pipe runs dry and the ring stays CV_NS - 1 tiles ahead.
@@ -404,6 +509,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
             mbar_wait(bar_empty + 8 * ((tl - 1) % CV_NS), ((tl - 1) / CV_NS) & 1);
             issue_tile_tma(tl - 1 + CV_NS);
           }
+
         }
       }
       __syncwarp();
@@ -475,7 +581,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
         const int oy = ty * CV_TR + q, ox = tx * CV_TC + lane;
         const bool valid = lane < CV_TC && oy < H && ox < W;
         mbar_wait(bar_accf + 8 * buf, (tl >> 1) & 1);
-        if ((warp == 5 || warp == 0) && lane == 0) { if (tl == 0) CV_TRACE(li, 8); if (tl == my_tiles - 1) CV_TRACE(li, 9); }
+        if ((warp == 5 || warp == 0) && lane == 0) { if (tl == 0) CV_TRACE(li, 8); if (tl == my_tiles - 1) CV_TRACE(li, 9); CV_TRACE2(li, tl, 3); }
         tc_fence_after();
         // out(p) = D_0(p) + D_1(p + 1) + D_2(p + 2): three accumulator blocks, the second and third read one and two
         // TMEM lanes (= lanes of this warp) further.  16 channels (one 32-byte sector of the NHWC row) at a time.
@@ -492,6 +598,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+            if ((warp == 5 || warp == 0) && lane == 0) CV_TRACE2(li, tl, 4);
           }
           float f[16];
 #pragma unroll
@@ -513,6 +620,7 @@ conv3x3_tc_kernel(const __grid_constant__ ChainParams P) {
             for (int c = 0; c < 16; ++c) csum[j + c] += f[c];
           }
         }
+        if ((warp == 5 || warp == 0) && lane == 0) CV_TRACE2(li, tl, 5);
       }
       flush();
       if (warp == 5 && lane == 0) CV_TRACE(li, 10);
@@ -588,11 +696,16 @@ int conv3x3_launch_chain(ChainParams& P, int n, int h, int w, int dtype, cudaStr
   for (int i = 0; i < P.nlayers; ++i) {
     ConvLayerDev& L = P.L[i];
     L.tma = 0;
-    if (L.res) continue;
     const unsigned long long dims[4] = {CV_CH, (unsigned long long)w, (unsigned long long)h, (unsigned long long)n};
     const unsigned long long str[3] = {CV_CH * 2ull, (unsigned long long)w * CV_CH * 2, (unsigned long long)h * w * CV_CH * 2};
     const unsigned box[4] = {CV_CH, CV_PW, CV_TR + 2, 1};
-    if (encode_tensor_map(&L.tm, EAVSR_BF16, 4, L.x, dims, str, box, 3 /* CU_TENSOR_MAP_SWIZZLE_128B */)) L.tma = 1;
+    // development switches (A/B timing): EAVSR_CONV_NO_TMA=1 keeps every layer on the cp.async / register paths,
+    // EAVSR_CONV_NO_FTMA=1 only the fused-input layers
+    static const bool no_tma = getenv("EAVSR_CONV_NO_TMA") != nullptr, no_ftma = getenv("EAVSR_CONV_NO_FTMA") != nullptr;
+    if (no_tma || (L.res && no_ftma)) continue;
+    if (encode_tensor_map(&L.tm, EAVSR_BF16, 4, L.x, dims, str, box, 3 /* CU_TENSOR_MAP_SWIZZLE_128B */) &&
+        (!L.res || encode_tensor_map(&L.tm2, EAVSR_BF16, 4, L.res, dims, str, box, 3)))
+      L.tma = 1;
   }
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem::DYN);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
@@ -674,5 +787,8 @@ extern "C" int eavsr_conv3x3_chain_forward(const EavsrConvLayer* layers, int nla
 #ifdef EAVSR_CONV_TRACE
 extern "C" int eavsr_debug_conv_trace(unsigned long long* host, int count) {
   return (int)cudaMemcpyFromSymbol(host, g_conv_trace, sizeof(unsigned long long) * count);
+}
+extern "C" int eavsr_debug_conv_trace2(unsigned long long* host, int count) {
+  return (int)cudaMemcpyFromSymbol(host, g_conv_trace2, sizeof(unsigned long long) * count);
 }
 #endif

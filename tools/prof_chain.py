@@ -100,3 +100,13 @@ if hasattr(lib, "eavsr_debug_conv_trace"):
         for li in range(8):
             row = [buf[li * 16 + k] for k in range(11)]
             print(f"rca layer {li}: " + "  ".join(f"{nm}={(v - t0) / 1965.0:.2f}us" for nm, v in zip(names, row)))
+
+        if hasattr(lib, "eavsr_debug_conv_trace2"):
+            b2 = (ctypes.c_ulonglong * 512)()
+            lib.eavsr_debug_conv_trace2(b2, 512)
+            for li in (2, 3):
+                print(f"rca layer {li} per tile (us since layer's first stamp): landed | staged | MMAs issued | acc ready | acc drained | stored")
+                base = min(v for v in b2[li * 64:(li + 1) * 64] if v)
+                for tl in range(8):
+                    row = b2[(li * 8 + tl) * 8:(li * 8 + tl) * 8 + 6]
+                    print(f"  tile {tl}: " + "  ".join(f"{(v - base) / 1965.0:6.2f}" if v else "   -  " for v in row))
