@@ -641,12 +641,13 @@ def main():
     ap.set_defaults(train_graph=True)
     ap.add_argument("--train-pwc", action="store_true",
                     help="--workload train: run the epoch >= npost branch too (PWC-Net cost volume + backwarp)")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=1,
                     help="run the clips of a step as this many concurrent forwards (CUDA streams) instead of one batch")
-    ap.add_argument("--clips-per-step", type=int, default=4,
-                    help="clips in flight per GPU and step (BASELINE config 4 gives every GPU 8+ clips): clips-per-step / "
-                         "streams are batched into one forward, the forwards run on `streams` CUDA streams; default 4 on 2 "
-                         "streams (+5 %% over one clip at a time, which is reported next to it as `single_clip`)")
+    ap.add_argument("--clips-per-step", type=int, default=8,
+                    help="clips in flight per GPU and step (BASELINE config 4 gives every GPU 8 clips): clips-per-step / "
+                         "streams are batched into one forward, the forwards run on `streams` CUDA streams; default: the 8 "
+                         "clips of config 4 as ONE batch (+12 %% over one clip at a time, which is reported next to it as "
+                         "`single_clip`: the per-layer barrier / set-up of the chained convolutions is amortised over 8 images)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
