@@ -23,7 +23,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, conv2d_bias_act, conv2d_bias_act_shuffle,
+from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, cat_channels, conv2d_bias_act,
+                  conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
                   conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, conv3x3_chain_eligible, rca_group_chain,
                   flow_warp, flow_warp2, flow_warp_nhw2, flow_warp_pyramid, flow_warp_pyramid_eligible, fused_inference_ok,
@@ -458,15 +459,15 @@ class EAVSRP(nn.Module):
                     cond2 = torch.zeros_like(cond1)
                 if cat3 is not None:
                     if cond1.data_ptr() != cat3.data_ptr():
-                        cat3[:, :nf].copy_(cond1)
-                    cat3[:, nf:2 * nf].copy_(cur)
+                        cat_channels([cond1], out=cat3, channel_offset=0)
+                    cat_channels([cur], out=cat3, channel_offset=nf)
                     if cond2.data_ptr() != cat3[:, 2 * nf:].data_ptr():
-                        cat3[:, 2 * nf:].copy_(cond2)
+                        cat_channels([cond2], out=cat3, channel_offset=2 * nf)
                     prop = conv2d_bias_act(fuse, cat3, 1.0)
                 else:
                     prop = conv2d_bias_act(fuse, torch.cat([cond1, cur, cond2], 1), 1.0)
                 prev_flow = flow1
-            x = torch.cat([cur] + [feats[k][idx] for k in others] + [prop], 1)
+            x = cat_channels([cur] + [feats[k][idx] for k in others] + [prop])
             prop = prop + body(x)
             outs.append(prop)
         feats[branch] = outs[::-1] if backward else outs
@@ -475,7 +476,7 @@ class EAVSRP(nn.Module):
     def _upsample(self, lrs, feats):
         outs = []
         for i in range(lrs.shape[1]):
-            x = torch.cat([feats["spatial"][i]] + [feats[b][i] for b in _BRANCHES], 1)
+            x = cat_channels([feats["spatial"][i]] + [feats[b][i] for b in _BRANCHES])
             x = self.reconstruction(x)
             # LeakyReLU commutes with PixelShuffle: fold it into the conv epilogue
             x = conv2d_bias_act_shuffle(self.upsample1[0], x, 0.1)

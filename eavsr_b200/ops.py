@@ -26,6 +26,8 @@ from typing import Optional, Tuple, Union
 import threading
 import weakref
 
+import ctypes
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -37,7 +39,7 @@ from . import _lib as L
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
     "backwarp", "get_backwarp", "invalidate_caches", "flow_warp_pyramid", "flow_warp_pyramid_eligible",
-    "spynet_level_input",
+    "spynet_level_input", "cat_channels",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
@@ -761,6 +763,40 @@ def bias_act_(x, bias, negative_slope: float = 1.0):
                 "bias_act")
         del bd
     return x
+
+
+def cat_channels(tensors, out=None, channel_offset: int = 0):
+    """``torch.cat(tensors, 1)`` for channels_last tensors in one coalesced pass (inference: no autograd), optionally
+    straight into the channel slice ``[channel_offset, +sum C_i)`` of an existing channels_last buffer ``out``
+    (returned).  Falls back to ``torch.cat`` / ``copy_`` whenever the layout, dtype or a needed gradient rules the
+    kernel out (models/eavsrp_model.py:271-324, 350-364)."""
+    ts = list(tensors)
+    x0 = ts[0]
+    vec = 16 // x0.element_size() if x0.dtype in (torch.float32, torch.bfloat16) else 0
+    ok = (vec > 0 and 1 <= len(ts) <= 8 and x0.is_cuda and fused_inference_ok(*ts)
+          and all(t.dim() == 4 and t.dtype == x0.dtype and t.device == x0.device and t.shape[0] == x0.shape[0]
+                  and t.shape[2:] == x0.shape[2:] and t.shape[1] % vec == 0
+                  and t.is_contiguous(memory_format=torch.channels_last) and t.data_ptr() % 16 == 0 for t in ts))
+    ctot = sum(t.shape[1] for t in ts)
+    if out is not None:
+        ok = ok and (out.dtype == x0.dtype and out.device == x0.device and out.dim() == 4 and out.shape[0] == x0.shape[0]
+                     and out.shape[2:] == x0.shape[2:] and out.is_contiguous(memory_format=torch.channels_last)
+                     and out.shape[1] % vec == 0 and channel_offset % vec == 0 and channel_offset + ctot <= out.shape[1])
+    if not ok:
+        if out is None:
+            return torch.cat(ts, 1)
+        out[:, channel_offset:channel_offset + ctot].copy_(torch.cat(ts, 1) if len(ts) > 1 else x0)
+        return out
+    lib = L.load()
+    n, _, h, w = x0.shape
+    with torch.cuda.device(x0.device):
+        if out is None:
+            out = torch.empty((n, ctot, h, w), dtype=x0.dtype, device=x0.device, memory_format=torch.channels_last)
+        ptrs = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        chans = (ctypes.c_int * len(ts))(*[t.shape[1] for t in ts])
+        L.check(lib.eavsr_nhwc_cat_forward(ptrs, chans, len(ts), out.data_ptr(), out.shape[1], channel_offset,
+                                           n * h * w, _dtype_code("cat_channels", x0), _stream(x0)), "nhwc_cat")
+    return out
 
 
 def conv2d_bias_act(conv: nn.Conv2d, x, negative_slope: float = 1.0):

@@ -246,6 +246,13 @@ int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1,
 int eavsr_bias_act_forward(void* x, const void* bias, int c, long long pixels, float negative_slope, int dtype,
                            void* stream);
 
+/* nhwc_cat: torch.cat(dim=1) of `nsrc` (<= 8) dense NHWC tensors of `pixels` = n*h*w pixels into the channel slice
+ *   [out_channel_offset, +sum(src_channels)) of a dense NHWC buffer with out_channels channels -- the inputs of the
+ *   fusion / backbone / reconstruction convolutions, models/eavsrp_model.py:271-324 (torch.cat([cond1, cur, cond2])),
+ *   :315 (torch.cat([cur, *others, prop])), :350-364.  All channel counts and the offset multiples of 16 bytes. */
+int eavsr_nhwc_cat_forward(const void* const* srcs, const int* src_channels, int nsrc, void* out, int out_channels,
+                           int out_channel_offset, long long pixels, int dtype, void* stream);
+
 /* bias_act_shuffle: PixelShuffle(2) with the producing convolution's bias and LeakyReLU folded in
  *   (the upsample1/upsample2 stages of EAVSRP.upsample, models/eavsrp_model.py:350-364):
  *   out[n, c, 2h+i, 2w+j] = LeakyReLU_slope(x[n, 4c+2i+j, h, w] + bias[4c+2i+j]);

@@ -400,3 +400,29 @@ def test_multi_adstn_pyramid_folding_matches_unfolded_path(cuda):
         b = m(nbr, ref, prop, flow).float()
     rms = b.pow(2).mean().sqrt().item()
     assert (a - b).pow(2).mean().sqrt().item() < 1e-2 * rms        # same arithmetic up to fp32 summation order of the flows
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_cat_channels_equals_torch_cat(cuda, dtype):
+    """nhwc_cat (the concatenations in front of the fusion / backbone / reconstruction convolutions,
+    models/eavsrp_model.py:271-324, 350-364): bit-exact copy, whole buffer and channel slice, odd pixel counts,
+    and the torch.cat fallback when a gradient is needed or the layout is not channels_last."""
+    from eavsr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for n, h, w, cs in ((2, 19, 23, (64, 64, 128)), (1, 270, 480, (64, 64, 64, 64, 64)), (1, 5, 7, (8,))):
+        ts = [_cl(torch.randn(n, c, h, w, generator=g).to(cuda, dtype)) for c in cs]
+        with torch.no_grad():
+            out = ops.cat_channels(ts)
+            assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, torch.cat(ts, 1))
+            buf = torch.full((n, sum(cs) + 16, h, w), 7.0, device=cuda, dtype=dtype).contiguous(memory_format=torch.channels_last)
+            ops.cat_channels(ts, out=buf, channel_offset=8)
+            assert torch.equal(buf[:, 8:8 + sum(cs)], torch.cat(ts, 1))
+            assert bool((buf[:, :8] == 7).all()) and bool((buf[:, 8 + sum(cs):] == 7).all())
+    a = torch.randn(1, 8, 6, 6, device=cuda, requires_grad=True)
+    b = torch.randn(1, 8, 6, 6, device=cuda)
+    y = ops.cat_channels([a, b])                                       # autograd on: torch.cat
+    y.sum().backward()
+    assert a.grad is not None and torch.equal(y, torch.cat([a, b], 1))
+    with torch.no_grad():                                              # NCHW-contiguous inputs: torch.cat
+        c = torch.randn(2, 12, 6, 6, device=cuda)
+        assert torch.equal(ops.cat_channels([c, c]), torch.cat([c, c], 1))
