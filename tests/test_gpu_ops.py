@@ -281,6 +281,37 @@ def test_dcn_tc_kernels_agree(cuda, shape):
     print(f"dcn bf16 rel err: fp32-blend {rel_err(w32, ref):.2e}  bf16x2-blend {rel_err(w16, ref):.2e}")
 
 
+@pytest.mark.parametrize("with_nan", [False, True])
+@pytest.mark.parametrize("shape", [(1, 1, 4), (1, 3, 8), (2, 8, 16), (3, 9, 20), (1, 17, 132)])
+def test_dcn_fifth_generation_edge_shapes_and_wild_offsets(cuda, shape, with_nan):
+    """The TMEM-operand kernel (dcn_fwd_win3.cuh) on images smaller than / not a multiple of its 8 x 16 tile, a batch
+    taken as a slice of a larger one (image stride != H*W*C), and offsets that are +-inf or astronomically large:
+    bit-identical to the fourth generation and equal to the generic kernel (such samples contribute 0, as in mmcv's
+    `h_im > -1 && h_im < height` test).  NaN offsets: the tcgen05 kernels propagate the NaN where mmcv's comparison
+    would drop the sample -- a known, documented divergence; only the equality of the two generations
+    is asserted for them."""
+    n, h, w = shape
+    x, off, mask, wgt, bias = dcn_inputs(n + 1, 64, h, w, 64, 8, seed=21)
+    g = torch.Generator().manual_seed(3)
+    r = torch.rand(off.shape, generator=g)
+    if with_nan:
+        off = torch.where(r < 0.0005, torch.full_like(off, float("nan")), off)          # ~7 % of the pixels
+    off = torch.where((r >= 0.0005) & (r < 0.001), torch.full_like(off, float("inf")), off)
+    off = torch.where((r >= 0.001) & (r < 0.003), torch.full_like(off, -3e38), off)
+    off = torch.where((r >= 0.003) & (r < 0.005), torch.full_like(off, 2.0e9), off)
+    xb = _cl(x.to(cuda).bfloat16())[1:]                       # images 1..n of a batch of n+1
+    assert xb.stride(0) == h * w * 64 and xb.data_ptr() != xb.untyped_storage().data_ptr()
+    args = (xb, off[1:].to(cuda).contiguous(), mask[1:].to(cuda).contiguous(), wgt.to(cuda).bfloat16(),
+            bias.to(cuda).bfloat16(), 1, 1, 1, 1, 8)
+    new, old = _ModulatedDeformConv2dFn.apply(*args, 0), _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_WIN2)
+    assert torch.equal(torch.nan_to_num(new.float(), nan=123.0), torch.nan_to_num(old.float(), nan=123.0))
+    if not with_nan:
+        gen = _ModulatedDeformConv2dFn.apply(*args, L.DCN_FORCE_GENERIC).float()
+        assert bool(torch.isfinite(gen).all()) and bool(torch.isfinite(new.float()).all())
+        rms = gen.pow(2).mean().sqrt().item()
+        assert (new.float() - gen).abs().max().item() <= 3e-2 * max(rms, 1e-3)
+
+
 @pytest.mark.parametrize("shape", [(1, 40, 72), (2, 37, 53), (1, 270, 480)])
 def test_dcn_window_kernel_deform_groups_16(cuda, shape):
     """BASELINE config 2 (deform_groups = 16): two 4-channel groups per 16-byte chunk in the window
