@@ -64,7 +64,12 @@ def _dtype_code(name: str, t: torch.Tensor) -> int:
 
 
 def _strides(t: torch.Tensor):
-    return L.Strides(*t.stride())
+    s = list(t.stride())
+    if t.dim() == 4 and t.shape[0] == 1:
+        # the stride of a size-1 batch dimension is arbitrary in PyTorch (views such as `x.view(t, 1, ...).unbind(0)`
+        # report 64 or t*C*H*W); the library checks `stride[0] >= extent of one image`, so hand it exactly that
+        s[0] = max(t.shape[i] * s[i] for i in (1, 2, 3))       # also right for a channel slice of a wider buffer
+    return L.Strides(*s)
 
 
 def _stream(t: torch.Tensor) -> int:

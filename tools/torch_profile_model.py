@@ -11,7 +11,7 @@ import bench  # noqa: E402
 
 T = int(os.environ.get("FRAMES", "6"))
 bench.T_FRAMES = T
-wl = bench.ModelWorkload(torch.device("cuda:0"), t=T, graph=False)
+wl = bench.ModelWorkload(torch.device("cuda:0"), t=T, graph=False, clips_per_step=int(os.environ.get("CLIPS", "1")))
 with torch.no_grad():
     for _ in range(2):
         wl.step()
