@@ -76,5 +76,9 @@ if "fused" in which:
         g(feats()[0])                            # chained cooperative launch
         g.chain = False
         g(feats()[0])                            # one launch per convolution
+        xs = [cl(torch.randn(2, c, 9, 13, device=dev).bfloat16()) for c in (64, 8, 128)]
+        ops.cat_channels(xs)                     # nhwc_cat, whole buffer and channel slice
+        buf = torch.zeros(2, 256, 9, 13, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ops.cat_channels(xs, out=buf, channel_offset=16)
 torch.cuda.synchronize()
 print("sanitize_target done:", which)
