@@ -86,6 +86,10 @@ _SIGNATURES = {
                                              c_void_p, _PF, _PF] + [c_int] * 5 + [c_void_p]),
     "eavsr_ca_residual_forward": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_void_p]),
     "eavsr_bias_act_forward": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_float, c_int, c_void_p]),
+    "eavsr_grouped_conv3x3_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                              c_int, c_void_p]),
+    "eavsr_grouped_conv3x3_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                               c_int, c_int, c_int, c_int, c_void_p]),
     "eavsr_nhwc_cat_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, ctypes.c_longlong, c_int,
                                        c_void_p]),
     "eavsr_bias_act_shuffle_forward": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_int, c_void_p]),

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, affine_offsets_mask, ca_residual, ca_scale, cat_channels, conv2d_bias_act,
+from .ops import (ModulatedDeformConv2d, adapt_mix, grouped_conv3x3, grouped_conv3x3_eligible, affine_offsets_mask, ca_residual, ca_scale, cat_channels, conv2d_bias_act,
                   conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
                   conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, conv3x3_chain_eligible, rca_group_chain,
@@ -160,6 +160,8 @@ def _affine_offsets(T, t, D, R=None):
 
 
 class _AdaptBase(nn.Module):
+    native_grouped = True      # differentiable grouped 3x3 convolutions on the library's kernels (False: nn.Conv2d)
+
     def __init__(self, ch, n_mat, n_trans, k):
         super().__init__()
         self.register_buffer("regular_matrix", torch.tensor(_R))
@@ -183,7 +185,16 @@ class _AdaptBase(nn.Module):
         if x.shape[1] == 64 and fused_inference_ok(x, ref):      # both grouped convs in one pass
             return adapt_mix(x, ref, self.concat[0].weight, self.concat[0].bias, self.concat2[0].weight,
                              self.concat2[0].bias, 0.2)
-        return self.concat2(self.concat(torch.cat([x, ref], 1)))
+        xr = torch.cat([x, ref], 1)
+        c1, c2 = self.concat[0], self.concat2[0]
+        if self.native_grouped and grouped_conv3x3_eligible(c1, xr) and xr.dtype in (torch.float32, torch.bfloat16):
+            # training path: cuDNN's grouped kernels (forward, and above all backward: 647 us per call on 8 MB
+            # tensors + layout transforms) were ~30 % of the training step
+            y = F.leaky_relu(grouped_conv3x3(c1, xr), 0.2)
+            if grouped_conv3x3_eligible(c2, y):
+                return F.leaky_relu(grouped_conv3x3(c2, y), 0.2)
+            return self.concat2(y)
+        return self.concat2(self.concat(xr))
 
 
 class _AdaptBlock2_3x3(_AdaptBase):

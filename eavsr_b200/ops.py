@@ -39,7 +39,7 @@ from . import _lib as L
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
     "backwarp", "get_backwarp", "invalidate_caches", "flow_warp_pyramid", "flow_warp_pyramid_eligible",
-    "spynet_level_input", "cat_channels",
+    "spynet_level_input", "cat_channels", "grouped_conv3x3", "grouped_conv3x3_eligible",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
@@ -768,6 +768,74 @@ def bias_act_(x, bias, negative_slope: float = 1.0):
                 "bias_act")
         del bd
     return x
+
+
+class _GroupedConv3x3Fn(Function):
+    """Grouped 3x3 convolution (groups = out channels, 1 or 2 inputs per group) with its backward on the library's
+    kernels (csrc/grouped_conv.cu).  NHWC, fp32 / bf16; gradients of weight and bias are accumulated in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = L.load()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        with torch.cuda.device(x.device):
+            xd = x.contiguous(memory_format=torch.channels_last)
+            wd = weight.detach().to(xd.dtype).contiguous()
+            bd = None if bias is None else bias.detach().to(xd.dtype).contiguous()
+            out = torch.empty((n, cout, h, w), dtype=xd.dtype, device=xd.device, memory_format=torch.channels_last)
+            L.check(lib.eavsr_grouped_conv3x3_forward(xd.data_ptr(), wd.data_ptr(), _ptr(bd), out.data_ptr(), n, cin, cout,
+                                                      h, w, _dtype_code("grouped_conv3x3", xd), _stream(xd)),
+                    "grouped_conv3x3_forward")
+        ctx.save_for_backward(xd, wd)
+        ctx.has_bias, ctx.wdtype, ctx.bdtype = bias is not None, weight.dtype, None if bias is None else bias.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        xd, wd = ctx.saved_tensors
+        lib = L.load()
+        n, cin, h, w = xd.shape
+        cout = wd.shape[0]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        gx = gw = gb = None
+        with torch.cuda.device(xd.device):
+            g = gout.to(xd.dtype).contiguous(memory_format=torch.channels_last)
+            if need_x:
+                gx = torch.empty_like(xd)
+            if need_w:
+                gw = torch.zeros(wd.shape, dtype=torch.float32, device=xd.device)
+                gb = torch.zeros(cout, dtype=torch.float32, device=xd.device)
+            L.check(lib.eavsr_grouped_conv3x3_backward(g.data_ptr(), xd.data_ptr(), wd.data_ptr(), _ptr(gx), _ptr(gw), _ptr(gb),
+                                                       n, cin, cout, h, w, _dtype_code("grouped_conv3x3", xd), _stream(xd)),
+                    "grouped_conv3x3_backward")
+        return (gx, None if gw is None else gw.to(ctx.wdtype),
+                None if (gb is None or not ctx.has_bias) else gb.to(ctx.bdtype))
+
+
+def grouped_conv3x3_eligible(conv: nn.Conv2d, x) -> bool:
+    """True for the grouped 3x3 convolutions of the AdaptBlocks (groups = out channels, 1 or 2 inputs per group,
+    stride 1, padding 1) on CUDA fp32 / bf16 tensors with channel counts that are multiples of 8."""
+    return (isinstance(conv, nn.Conv2d) and x.is_cuda and x.dim() == 4 and conv.kernel_size == (3, 3)
+            and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.padding_mode == "zeros"
+            and conv.groups == conv.out_channels and conv.in_channels // conv.out_channels in (1, 2)
+            and conv.in_channels % conv.out_channels == 0 and conv.out_channels % 8 == 0 and conv.in_channels % 8 == 0
+            and 256 % (conv.in_channels // 8) == 0 and x.shape[1] == conv.in_channels)
+
+
+def grouped_conv3x3(conv: nn.Conv2d, x):
+    """``conv(x)`` for an eligible grouped 3x3 convolution, differentiable, on the library's kernels; follows
+    torch.autocast like nn.Conv2d does (inputs and parameters are cast to the autocast dtype)."""
+    w, b = conv.weight, conv.bias
+    if torch.is_autocast_enabled():
+        dt = torch.get_autocast_dtype("cuda") if hasattr(torch, "get_autocast_dtype") else torch.get_autocast_gpu_dtype()
+        x, w, b = x.to(dt), w.to(dt), None if b is None else b.to(dt)
+        with torch.autocast("cuda", enabled=False):
+            return _GroupedConv3x3Fn.apply(x, w, b)
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"eavsr_b200.grouped_conv3x3: dtype {x.dtype} not supported (float32 / bfloat16)")
+    return _GroupedConv3x3Fn.apply(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
 
 
 def cat_channels(tensors, out=None, channel_offset: int = 0):

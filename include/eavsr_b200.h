@@ -246,6 +246,17 @@ int eavsr_ca_residual_forward(const void* res, const void* skip, const void* w1,
 int eavsr_bias_act_forward(void* x, const void* bias, int c, long long pixels, float negative_slope, int dtype,
                            void* stream);
 
+/* grouped_conv3x3: the grouped 3x3 convolutions of AdaptBlockOffset / AdaptBlock2_3x3 (`concat`: depthwise over
+ *   2*ch channels, `concat2`: 2 inputs per output channel; models/networks.py:289-290, 327-328), stride 1, pad 1,
+ *   differentiable: forward, d(input) and d(weight) + d(bias) -- the training step's replacement for cuDNN's grouped
+ *   kernels.  x (n,cin,h,w), out / gout (n,cout,h,w) dense NHWC in `dtype`; weight (cout, cin/cout, 3, 3) and bias
+ *   (cout) in `dtype`; groups = cout, cin/cout in {1, 2}, channel counts multiples of 8.  backward: gx may be NULL;
+ *   gweight (cout, cin/cout, 3, 3) and gbias (cout) are fp32, must be ZERO on entry and go together (or both NULL). */
+int eavsr_grouped_conv3x3_forward(const void* x, const void* weight, const void* bias, void* out, int n, int cin,
+                                  int cout, int h, int w, int dtype, void* stream);
+int eavsr_grouped_conv3x3_backward(const void* gout, const void* x, const void* weight, void* gx, float* gweight,
+                                   float* gbias, int n, int cin, int cout, int h, int w, int dtype, void* stream);
+
 /* nhwc_cat: torch.cat(dim=1) of `nsrc` (<= 8) dense NHWC tensors of `pixels` = n*h*w pixels into the channel slice
  *   [out_channel_offset, +sum(src_channels)) of a dense NHWC buffer with out_channels channels -- the inputs of the
  *   fusion / backbone / reconstruction convolutions, models/eavsrp_model.py:271-324 (torch.cat([cond1, cur, cond2])),

@@ -426,3 +426,49 @@ def test_cat_channels_equals_torch_cat(cuda, dtype):
     with torch.no_grad():                                              # NCHW-contiguous inputs: torch.cat
         c = torch.randn(2, 12, 6, 6, device=cuda)
         assert torch.equal(ops.cat_channels([c, c]), torch.cat([c, c], 1))
+
+
+@pytest.mark.parametrize("cin,cout", [(128, 128), (128, 64), (16, 16), (32, 16)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_grouped_conv3x3_forward_backward_match_conv2d(cuda, cin, cout, dtype, tol):
+    """Row a3, training path: the depthwise / two-inputs-per-group 3x3 convolutions of the AdaptBlocks
+    (models/networks.py:289-290, 327-328) on the library's kernels == nn.Conv2d in fp64: output, d(input),
+    d(weight), d(bias); odd sizes, batch > 1, with and without bias, and under torch.autocast."""
+    from eavsr_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout)
+    for n, h, w, bias in ((2, 13, 19, True), (1, 64, 64, True), (3, 5, 8, False)):
+        conv = torch.nn.Conv2d(cin, cout, 3, 1, 1, groups=cout, bias=bias)
+        with torch.no_grad():
+            for p in conv.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+        x = torch.randn(n, cin, h, w, generator=g)
+        go = torch.randn(n, cout, h, w, generator=g)
+        ref_conv = torch.nn.Conv2d(cin, cout, 3, 1, 1, groups=cout, bias=bias).double()
+        ref_conv.load_state_dict(conv.state_dict())
+        if dtype == torch.bfloat16:                            # reference on the bf16-rounded operands
+            with torch.no_grad():
+                for p in ref_conv.parameters():
+                    p.copy_(p.float().bfloat16().double())
+        xr = x.to(dtype).double().requires_grad_()
+        yr = ref_conv(xr)
+        yr.backward(go.to(dtype).double())
+        conv = conv.to(cuda, dtype)
+        assert ops.grouped_conv3x3_eligible(conv, x.to(cuda))
+        xg = _cl(x.to(cuda, dtype)).requires_grad_()
+        y = ops.grouped_conv3x3(conv, xg)
+        assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+        y.backward(_cl(go.to(cuda, dtype)))
+        scale = lambda t: max(1.0, t.abs().max().item())      # noqa: E731
+        assert (y.double().cpu() - yr).abs().max().item() <= tol * scale(yr)
+        assert (xg.grad.double().cpu() - xr.grad).abs().max().item() <= tol * scale(xr.grad)
+        assert (conv.weight.grad.double().cpu() - ref_conv.weight.grad).abs().max().item() <= tol * scale(ref_conv.weight.grad)
+        if bias:
+            assert (conv.bias.grad.double().cpu() - ref_conv.bias.grad).abs().max().item() <= tol * scale(ref_conv.bias.grad)
+    conv = torch.nn.Conv2d(cin, cout, 3, 1, 1, groups=cout).to(cuda)          # fp32 parameters, bf16 autocast
+    x = torch.randn(1, cin, 9, 11, device=cuda, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.grouped_conv3x3(conv, x)
+        yt = conv(x)
+    assert y.dtype == torch.bfloat16 and (y.float() - yt.float()).abs().max().item() <= 3e-2 * max(1.0, yt.abs().max().item())
+    y.float().sum().backward()
+    assert conv.weight.grad.dtype == torch.float32 and x.grad.dtype == torch.float32

@@ -13,7 +13,10 @@ wl = bench.TrainWorkload(torch.device("cuda:0"), graph=False, dtype=torch.bfloat
 for _ in range(3):
     wl.step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     wl.step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=90))
+if os.environ.get("BY_SHAPE"):
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=45))
+else:
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=90))
