@@ -647,3 +647,21 @@ extern "C" int eavsr_nhwc_cat_forward(const void* const* srcs, const int* src_ch
   nhwc_cat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, (uint4*)out, pixels);
   return check_launch("nhwc_cat");
 }
+
+// Per-(n, channel) sums over H*W of a dense NHWC tensor with 64 channels, fp32 (sums is zero-filled here): the
+// bias gradient of the 64-output convolutions and the global average pooling of CALayer in the training step, where
+// ATen's generic reduction of a channels_last tensor took 30 us per 4 MB tensor.
+extern "C" int eavsr_channel_sum_forward(const void* x, float* sums, int n, int c, long long hw, int dtype, void* stream) {
+  EAVSR_REQUIRE(x && sums, "channel_sum: null pointer");
+  EAVSR_REQUIRE(n > 0 && hw > 0 && hw < (1ll << 31) && n <= 65535, "channel_sum: bad shape");
+  if (c != 64) { set_error("channel_sum: only C=64 (got %d)", c); return EAVSR_ERR_UNSUPPORTED; }
+  EAVSR_REQUIRE(al16(x), "channel_sum: x must be 16-byte aligned dense NHWC");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)n * c * sizeof(float), st);
+  if (e != cudaSuccess) { set_error("channel_sum: memset: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  dim3 g1(ceil_div(hw, CS_PIX), n);
+  if (dtype == EAVSR_F32) channel_sum_kernel<float, 64><<<g1, CS_THREADS, 0, st>>>((const float*)x, sums, (int)hw);
+  else if (dtype == EAVSR_BF16) channel_sum_kernel<__nv_bfloat16, 64><<<g1, CS_THREADS, 0, st>>>((const __nv_bfloat16*)x, sums, (int)hw);
+  else { set_error("channel_sum: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("channel_sum");
+}

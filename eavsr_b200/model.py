@@ -23,7 +23,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, grouped_conv3x3, grouped_conv3x3_eligible, affine_offsets_mask, ca_residual, ca_scale, cat_channels, conv2d_bias_act,
+from .ops import (ModulatedDeformConv2d, adapt_mix, grouped_conv3x3, grouped_conv3x3_eligible, channel_mean,
+                  conv2d_native_bias_grad, affine_offsets_mask, ca_residual, ca_scale, cat_channels, conv2d_bias_act,
                   conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
                   conv3x3_64, conv3x3_64_ca, conv3x3_64_eligible, conv3x3_chain_eligible, rca_group_chain,
@@ -44,7 +45,7 @@ class _CALayer(nn.Module):
                                      nn.Conv2d(ch // reduction, ch, 1), nn.Sigmoid())
 
     def forward(self, x):
-        return x * self.conv_du(x.mean((2, 3), keepdim=True))
+        return x * self.conv_du(channel_mean(x))      # (native channel sums for CUDA channels_last maps)
 
 
 class _RCABlock(nn.Module):
@@ -68,7 +69,10 @@ class _RCABlock(nn.Module):
             c2 = self.res[2]
             res = F.conv2d(h, c2.weight, None, c2.stride, c2.padding)
             return ca_residual(res, x, du[0].weight, du[0].bias, du[2].weight, du[2].bias, 16, res_bias=c2.bias)
-        return self.ca(self.res(x)) + x
+        # differentiable path (training): cuDNN convolutions, bias gradients and the attention's pooling on the
+        # library's channel-sum kernel
+        h = F.relu(conv2d_native_bias_grad(self.res[0], x), inplace=True)
+        return self.ca(conv2d_native_bias_grad(self.res[2], h)) + x
 
 
 class _RCAGroup(nn.Module):
@@ -105,6 +109,8 @@ class _RCAGroup(nn.Module):
             y = blk(y)
         if conv3x3_64_eligible(self.rg[-1], y):
             return conv3x3_64(self.rg[-1], y, 1.0) + x
+        if torch.is_grad_enabled():
+            return conv2d_native_bias_grad(self.rg[-1], y) + x
         return conv2d_bias_act(self.rg[-1], y, 1.0) + x
 
 

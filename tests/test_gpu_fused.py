@@ -472,3 +472,35 @@ def test_grouped_conv3x3_forward_backward_match_conv2d(cuda, cin, cout, dtype, t
     assert y.dtype == torch.bfloat16 and (y.float() - yt.float()).abs().max().item() <= 3e-2 * max(1.0, yt.abs().max().item())
     y.float().sum().backward()
     assert conv.weight.grad.dtype == torch.float32 and x.grad.dtype == torch.float32
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_native_bias_gradient_and_channel_mean_match_torch(cuda, dtype, tol):
+    """Training path of the residual backbone: `conv2d_native_bias_grad` (cuDNN convolution, bias gradient on the
+    channel-sum kernel) and `channel_mean` (CALayer's global pooling, models/networks.py:431-447) == the PyTorch ops."""
+    from eavsr_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    conv = torch.nn.Conv2d(64, 64, 3, 1, 1).to(cuda, dtype).to(memory_format=torch.channels_last)
+    ref = torch.nn.Conv2d(64, 64, 3, 1, 1).to(cuda).double()
+    ref.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    for n, h, w in ((2, 19, 23), (8, 64, 64)):
+        x = _cl(torch.randn(n, 64, h, w, generator=g).to(cuda, dtype))
+        go = _cl(torch.randn(n, 64, h, w, generator=g).to(cuda, dtype))
+        xa, xb = x.clone().requires_grad_(), x.double().requires_grad_()
+        conv.zero_grad(); ref.zero_grad()
+        y = ops.conv2d_native_bias_grad(conv, xa)
+        y.backward(go)
+        yr = ref(xb)
+        yr.backward(go.double())
+        sc = lambda t: max(1.0, t.abs().max().item())         # noqa: E731
+        assert (y.double() - yr).abs().max().item() <= max(tol, 2e-2 if dtype == torch.bfloat16 else tol) * sc(yr)
+        assert (conv.bias.grad.double() - ref.bias.grad).abs().max().item() <= tol * sc(ref.bias.grad)
+        assert (xa.grad.double() - xb.grad).abs().max().item() <= max(tol, 2e-2 if dtype == torch.bfloat16 else tol) * sc(xb.grad)
+        xm, xr = x.clone().requires_grad_(), x.double().requires_grad_()
+        m = ops.channel_mean(xm)
+        mr = xr.mean((2, 3), keepdim=True)
+        assert m.shape == mr.shape and (m.double() - mr).abs().max().item() <= tol * sc(mr)
+        gm = torch.randn(m.shape, generator=g).to(cuda, dtype)
+        m.backward(gm)
+        mr.backward(gm.double())
+        assert (xm.grad.double() - xr.grad).abs().max().item() <= tol * sc(xr.grad)
