@@ -159,24 +159,39 @@ gconv_bwd_weight_kernel(const T* __restrict__ g, const T* __restrict__ x, float*
       }
     }
   }
-  // reduce over the pixel lanes: 80 values per thread through shared memory, one column (chunk) at a time
-  __shared__ float red[GC_THREADS];
+  // Reduce over the pixel lanes.  Threads with the same channel chunk are `cpi` apart: when cpi == 16 (128 input
+  // channels) lanes l and l + 16 of a warp share a chunk, so one shuffle halves the work; the warps then meet in
+  // shared memory one tap (8 values per thread) at a time -- 10 rounds instead of one per value.
+  __shared__ float red[GC_THREADS / 32][32][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fold = (cpi == 16);                               // lane and lane ^ 16 hold the same chunk
 #pragma unroll
-  for (int k = 0; k < 80; ++k) {
-    const float v = k < 72 ? acc[k / 8][k % 8] : accb[k - 72];
-    // (static indexing: the loop is unrolled by the compiler because k indexes register arrays)
-    red[threadIdx.x] = (pl < lanes) ? v : 0.f;
+  for (int t = 0; t < 10; ++t) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = t < 9 ? acc[t][e] : accb[e];
+      if (fold) v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lane][e] = v[e];
     __syncthreads();
-    if (threadIdx.x < cpi) {
-      float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += red[l * cpi + threadIdx.x];
-      const int c = threadIdx.x * 8 + (k < 72 ? k % 8 : k - 72);     // input channel
-      if (k < 72) {
-        const int t = k / 8;
-        atomicAdd(gw + (CPG == 1 ? c * 9 + t : ((c >> 1) * 2 + (c & 1)) * 9 + t), s);
-      } else if (CPG == 1 || (c & 1) == 0) {
-        atomicAdd(gb + (CPG == 1 ? c : c >> 1), s);           // CPG = 2: both inputs of a group saw the same gradient
+    // one thread per (chunk, element): sum the contributions of every warp (and, without the fold, of every lane
+    // of a warp that holds this chunk)
+    for (int o = threadIdx.x; o < cpi * 8; o += GC_THREADS) {
+      const int c8 = o >> 3, e = o & 7;
+      float sum = 0.f;
+      for (int wp = 0; wp < GC_THREADS / 32; ++wp) {
+        if (fold) {
+          sum += red[wp][c8][e];
+        } else {
+          for (int l = 0; l < 32; ++l)
+            if ((wp * 32 + l) % cpi == c8 && (wp * 32 + l) / cpi < lanes) sum += red[wp][l][e];
+        }
       }
+      const int c = c8 * 8 + e;                               // input channel
+      if (t < 9) atomicAdd(gw + c * 9 + t, sum);              // (cout, CPG, 3, 3) flattened == input channel * 9 + tap
+      else if (CPG == 1 || (c & 1) == 0) atomicAdd(gb + (CPG == 1 ? c : c >> 1), sum);   // CPG = 2: one sum per group
     }
     __syncthreads();
   }
@@ -197,8 +212,8 @@ int gconv_run(int mode, const void* a, const void* b, const void* c, void* o1, f
     return check_launch("grouped_conv3x3_backward(data)");
   }
   const int lanes = GC_THREADS / (cout * CPG / 8);
-  long long wb = ((long long)n * h * w + lanes * 8 - 1) / (lanes * 8);     // >= 8 pixels per thread
-  if (wb > 148 * 4) wb = 148 * 4;
+  long long wb = ((long long)n * h * w + lanes * 16 - 1) / (lanes * 16);   // >= 16 pixels per thread
+  if (wb > 148 * 2) wb = 148 * 2;
   if (wb < 1) wb = 1;
   gconv_bwd_weight_kernel<T, CPG><<<(unsigned)wb, GC_THREADS, 0, st>>>((const T*)a, (const T*)b, o2, o3, n, h, w, cout);
   return check_launch("grouped_conv3x3_backward(weight)");
