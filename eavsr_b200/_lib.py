@@ -91,6 +91,7 @@ _SIGNATURES = {
     "eavsr_grouped_conv3x3_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                c_int, c_int, c_int, c_int, c_void_p]),
     "eavsr_channel_sum_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_int, c_void_p]),
+    "eavsr_channel_dot_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_int, c_void_p]),
     "eavsr_nhwc_cat_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, ctypes.c_longlong, c_int,
                                        c_void_p]),
     "eavsr_bias_act_shuffle_forward": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_int, c_void_p]),

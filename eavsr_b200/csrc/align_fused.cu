@@ -237,9 +237,9 @@ affine_offsets_kernel(const T* __restrict__ tm, Strides4 ts, const T* __restrict
 constexpr int CS_THREADS = 256;
 constexpr int CS_PIX = 512;   // pixels per CTA
 
-template <typename T, int C>
+template <typename T, int C, bool PROD = false>
 __global__ void __launch_bounds__(CS_THREADS)
-channel_sum_kernel(const T* __restrict__ x, float* __restrict__ sums, int HW) {
+channel_sum_kernel(const T* __restrict__ x, float* __restrict__ sums, int HW, const T* __restrict__ x2 = nullptr) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int CPP = C / VEC;
   constexpr int PPI = CS_THREADS / CPP;          // pixels per iteration
@@ -255,8 +255,15 @@ channel_sum_kernel(const T* __restrict__ x, float* __restrict__ sums, int HW) {
   for (int p = p0 + pl; p < p1; p += PPI) {
     float v[VEC];
     VecLoad<T, VEC>::ld(xn + (size_t)p * C + ch * VEC, v);
+    if (PROD) {                                    // sums of the element-wise product of two tensors
+      float u[VEC];
+      VecLoad<T, VEC>::ld(x2 + (size_t)n * HW * C + (size_t)p * C + ch * VEC, u);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) acc[e] += v[e];
+      for (int e = 0; e < VEC; ++e) acc[e] += v[e] * u[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] += v[e];
+    }
   }
 #pragma unroll
   for (int e = 0; e < VEC; ++e) red[pl][ch * VEC + e] = acc[e];
@@ -664,4 +671,26 @@ extern "C" int eavsr_channel_sum_forward(const void* x, float* sums, int n, int 
   else if (dtype == EAVSR_BF16) channel_sum_kernel<__nv_bfloat16, 64><<<g1, CS_THREADS, 0, st>>>((const __nv_bfloat16*)x, sums, (int)hw);
   else { set_error("channel_sum: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
   return check_launch("channel_sum");
+}
+
+
+// sums(n, 64) = sum over the pixels of a * b (both (n, 64, h, w) dense NHWC): the gradient of the channel-attention
+// scale in `res * scale + skip` (d scale = sum_hw(grad * res)), one pass instead of a multiply + ATen reduction.
+extern "C" int eavsr_channel_dot_forward(const void* a, const void* b, float* sums, int n, int c, long long hw, int dtype,
+                                         void* stream) {
+  EAVSR_REQUIRE(a && b && sums, "channel_dot: null pointer");
+  EAVSR_REQUIRE(n > 0 && hw > 0 && hw < (1ll << 31) && n <= 65535, "channel_dot: bad shape");
+  if (c != 64) { set_error("channel_dot: only C=64 (got %d)", c); return EAVSR_ERR_UNSUPPORTED; }
+  EAVSR_REQUIRE(al16(a) && al16(b), "channel_dot: tensors must be 16-byte aligned dense NHWC");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)n * c * sizeof(float), st);
+  if (e != cudaSuccess) { set_error("channel_dot: memset: %s", cudaGetErrorString(e)); return EAVSR_ERR_CUDA; }
+  dim3 g1(ceil_div(hw, CS_PIX), n);
+  if (dtype == EAVSR_F32)
+    channel_sum_kernel<float, 64, true><<<g1, CS_THREADS, 0, st>>>((const float*)a, sums, (int)hw, (const float*)b);
+  else if (dtype == EAVSR_BF16)
+    channel_sum_kernel<__nv_bfloat16, 64, true><<<g1, CS_THREADS, 0, st>>>((const __nv_bfloat16*)a, sums, (int)hw,
+                                                                          (const __nv_bfloat16*)b);
+  else { set_error("channel_dot: bad dtype %d", dtype); return EAVSR_ERR_INVALID; }
+  return check_launch("channel_dot");
 }

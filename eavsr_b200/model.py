@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (ModulatedDeformConv2d, adapt_mix, grouped_conv3x3, grouped_conv3x3_eligible, channel_mean,
+from .ops import (ModulatedDeformConv2d, adapt_mix, grouped_conv3x3, grouped_conv3x3_eligible, channel_mean, scale_residual,
                   conv2d_native_bias_grad, affine_offsets_mask, ca_residual, ca_scale, cat_channels, conv2d_bias_act,
                   conv2d_bias_act_shuffle,
                   dcn_affine, dcn_affine_eligible,
@@ -72,7 +72,8 @@ class _RCABlock(nn.Module):
         # differentiable path (training): cuDNN convolutions, bias gradients and the attention's pooling on the
         # library's channel-sum kernel
         h = F.relu(conv2d_native_bias_grad(self.res[0], x), inplace=True)
-        return self.ca(conv2d_native_bias_grad(self.res[2], h)) + x
+        r = conv2d_native_bias_grad(self.res[2], h)
+        return scale_residual(r, self.ca.conv_du(channel_mean(r)), x)      # == self.ca(r) + x
 
 
 class _RCAGroup(nn.Module):

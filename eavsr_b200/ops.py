@@ -40,7 +40,7 @@ from . import _lib as L
 __all__ = [
     "modulated_deform_conv2d", "ModulatedDeformConv2d", "dcn_affine", "dcn_affine_eligible", "flow_warp", "flow_warp_nhw2",
     "backwarp", "get_backwarp", "invalidate_caches", "flow_warp_pyramid", "flow_warp_pyramid_eligible",
-    "spynet_level_input", "cat_channels", "grouped_conv3x3", "grouped_conv3x3_eligible", "conv2d_native_bias_grad", "channel_mean",
+    "spynet_level_input", "cat_channels", "grouped_conv3x3", "grouped_conv3x3_eligible", "conv2d_native_bias_grad", "channel_mean", "scale_residual",
     "FunctionCorrelation", "ModuleCorrelation", "dcn_uses_tensor_cores",
     "adapt_mix", "affine_offsets_mask", "ca_residual", "fused_inference_ok", "bias_act_", "conv2d_bias_act",
     "conv3x3_64", "conv3x3_64_ca", "conv3x3_64_eligible", "ca_scale", "conv2d_bias_act_shuffle",
@@ -898,6 +898,42 @@ class _ChannelMeanFn(Function):
         n, c, h, w = ctx.shape
         g = (gout * (1.0 / (h * w))).expand(n, c, h, w)
         return g.contiguous(memory_format=torch.channels_last)
+
+
+class _ScaleResidualFn(Function):
+    """res * scale + skip (scale broadcast over h, w) whose scale gradient sum_hw(grad * res) is one pass of the
+    library's channel-dot kernel instead of a multiply + ATen reduction."""
+
+    @staticmethod
+    def forward(ctx, res, scale, skip):
+        ctx.save_for_backward(res, scale)
+        return torch.addcmul(skip, res, scale)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        res, scale = ctx.saved_tensors
+        g = gout if gout.is_contiguous(memory_format=torch.channels_last) else gout.contiguous(memory_format=torch.channels_last)
+        gres = g * scale if ctx.needs_input_grad[0] else None
+        gscale = None
+        if ctx.needs_input_grad[1]:
+            n, c, h, w = res.shape
+            lib = L.load()
+            with torch.cuda.device(res.device):
+                sums = torch.empty((n, c), dtype=torch.float32, device=res.device)
+                L.check(lib.eavsr_channel_dot_forward(g.data_ptr(), res.data_ptr(), sums.data_ptr(), n, c, h * w,
+                                                      _dtype_code("scale_residual", res), _stream(res)), "channel_dot")
+            gscale = sums.to(scale.dtype).view(n, c, 1, 1)
+        return gres, gscale, gout if ctx.needs_input_grad[2] else None
+
+
+def scale_residual(res, scale, skip):
+    """``res * scale + skip`` (differentiable) for RCABlock's channel attention; native scale gradient for CUDA
+    channels_last 64-channel maps."""
+    if (_channel_sum_ok(res) and scale.shape == (res.shape[0], 64, 1, 1) and skip.shape == res.shape
+            and res.dtype == scale.dtype == skip.dtype and skip.is_contiguous(memory_format=torch.channels_last)):
+        return _ScaleResidualFn.apply(res, scale, skip)
+    return res * scale + skip
 
 
 def channel_mean(x):

@@ -262,6 +262,11 @@ int eavsr_grouped_conv3x3_backward(const void* gout, const void* x, const void* 
  *   pooling of CALayer (models/networks.py:431-447) in the training step. */
 int eavsr_channel_sum_forward(const void* x, float* sums, int n, int c, long long hw, int dtype, void* stream);
 
+/* channel_dot: sums(n, 64) [fp32, zero-filled by the call] = sum over the hw pixels of a * b: the gradient of the
+ *   channel-attention scale in RCABlock's `res * scale + x` (models/networks.py:449-465) in the training step. */
+int eavsr_channel_dot_forward(const void* a, const void* b, float* sums, int n, int c, long long hw, int dtype,
+                              void* stream);
+
 /* nhwc_cat: torch.cat(dim=1) of `nsrc` (<= 8) dense NHWC tensors of `pixels` = n*h*w pixels into the channel slice
  *   [out_channel_offset, +sum(src_channels)) of a dense NHWC buffer with out_channels channels -- the inputs of the
  *   fusion / backbone / reconstruction convolutions, models/eavsrp_model.py:271-324 (torch.cat([cond1, cur, cond2])),

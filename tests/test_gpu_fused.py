@@ -198,9 +198,11 @@ def test_model_uses_fused_path_only_without_grad(cuda):
     # with autograd on, none of the fused (non-differentiable) kernels runs: cuDNN convolutions + the differentiable
     # channel pooling of the attention layer (one channel-sum launch)
     assert _lib.launch_count() - n1 == 1 and y_torch.requires_grad
+    n2 = _lib.launch_count()
     assert (y_fused - y_torch.detach()).abs().max() < 1e-4
     y_torch.sum().backward()
     assert x.grad is not None and all(p.grad is not None for p in blk.parameters())
+    assert _lib.launch_count() - n2 == 3        # backward: two bias gradients + the attention scale's channel-dot
 
 
 @pytest.mark.parametrize("shape", [(1, 40, 72), (2, 37, 53), (1, 270, 480)])
@@ -508,3 +510,16 @@ def test_native_bias_gradient_and_channel_mean_match_torch(cuda, dtype, tol):
         m.backward(gm)
         mr.backward(gm.double())
         assert (xm.grad.double() - xr.grad).abs().max().item() <= tol * sc(xr.grad)
+        # res * scale + skip with the native scale gradient (RCABlock tail, models/networks.py:449-465)
+        r1, s1, k1 = (t.clone().requires_grad_() for t in (x, torch.rand(n, 64, 1, 1, generator=g).to(cuda, dtype), go))
+        r2, s2, k2 = (t.detach().double().requires_grad_() for t in (r1, s1, k1))
+        o1 = ops.scale_residual(r1, s1, k1)
+        o2 = r2 * s2 + k2
+        gg = _cl(torch.randn(n, 64, h, w, generator=g).to(cuda, dtype))
+        o1.backward(gg)
+        o2.backward(gg.double())
+        btol = max(tol, 2e-2 if dtype == torch.bfloat16 else tol)
+        assert (o1.double() - o2).abs().max().item() <= btol * sc(o2)
+        assert (r1.grad.double() - r2.grad).abs().max().item() <= btol * sc(r2.grad)
+        assert (s1.grad.double() - s2.grad).abs().max().item() <= btol * sc(s2.grad)
+        assert torch.equal(k1.grad, gg)
