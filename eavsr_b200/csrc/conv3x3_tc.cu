@@ -6,31 +6,32 @@
 //
 // D[128 positions x 64 cout] = sum_{tap} A_tap[128 x 64 cin] * W_tap[64 x 64]
 //
-// The trick that makes the nine A_tap operands free: the CTA stages ONE halo tile of the input
-// (6 rows x 32 columns of pixels) as a K-major, 128-byte-swizzled UMMA tile whose rows are the halo
-// pixels (128 B = 64 channels per row, 16-byte chunk c of row p stored at chunk c ^ (p & 7)).  The A
-// operand of tap (r, s) is the same buffer with the descriptor start address advanced by (r*32 + s)
-// rows (the 128B swizzle is a function of absolute address bits, so any whole-row shift of a tile that
-// was swizzled by absolute row index is again a valid operand) -- no im2col, no re-staging, no second copy.  (The first version used the non-swizzled layout with 16-byte rows; its tap views
-// started at 16-byte granularity, every 8x16 B core matrix straddled two 128-byte lines and the MMA
-// issue thread sat blocked on tcgen05.mma: profiles/r1_conv3x3_tc_ncu.txt.)
-// One MMA covers 128 consecutive halo positions = a 4 x 32 block of which 4 x 30 are real outputs
-// (the 2 wrap-around columns per row are computed and dropped: 6 % waste).
+// The trick that makes the A operands free: the CTA stages ONE halo tile of the input (6 rows x 32 columns of pixels)
+// as a K-major, 128-byte-swizzled UMMA tile whose rows are the halo pixels (128 B = 64 channels per row, 16-byte
+// chunk c of row p stored at chunk c ^ (p & 7)).  A shifted view of it -- the descriptor start address advanced by
+// whole rows -- is again a valid operand (the 128B swizzle is a function of absolute address bits): no im2col, no
+// re-staging, no second copy.  (The first version used the non-swizzled layout with 16-byte rows; every 8x16 B core
+// matrix straddled two 128-byte lines and the MMA issue thread sat blocked on tcgen05.mma:
+// profiles/r1_conv3x3_tc_ncu.txt.)  Round 1 issued one N = 64 MMA per tap and K step (36 per tile, views advanced by
+// r*32 + s rows); since round 2 ONE N = 192 MMA covers the three taps of a kernel row (view advanced by r*32 rows,
+// the three weight tiles of the row as one B operand) and the epilogue adds the three accumulator blocks one and
+// two TMEM lanes apart (12 MMAs per tile).  One tile = 128 consecutive halo positions = a 4 x 32
+// block of which 4 x 30 are real outputs (the 2 wrap-around columns per row are computed and dropped: 6 % waste).
 //
-// Warp roles (544 threads, 1 CTA / SM, persistent over tiles):
-//   warps 0-3  producers: cp.async (zero-fill outside the image = conv padding) into a 3-stage ring
-//   warp  4    one lane issues 36 tcgen05.mma per tile (A: no-swizzle descriptors, B: 9 resident
-//              128B-swizzled 64x64 weight tiles) and commits to mbarriers
-//   warps 5-12 epilogue, two groups of four: group g drains output channels 32g .. 32g+31 of every tile:
-//              tcgen05.ld -> +bias -> activation -> bf16 NHWC store (32-byte st.global.v8), channel sums
-//              kept in registers across the CTA's tiles and flushed with one atomicAdd per channel.
-//              ncu stall sampling of the single-group version (profiles/r1_conv3x3_tc_ncu.txt) showed the
-//              epilogue as the serial critical path: as many samples on the store-drain (WAR on the STG
-//              source registers, 30 half-filled sectors per STG.128) as on the wait for the MMAs.
-//   warps 13-16 helper producers, fused-input mode only (eavsr_conv3x3_ca_forward): the previous block's
-//              channel attention y = res * scale + skip is computed while the halo tile is staged (two
-//              warps per stage, 16 independent 16-byte loads in flight per lane) and y is written out once.
-// Two TMEM accumulators (2 x 64 columns) decouple the epilogues from the next tile's MMAs.
+// Warp roles (544 threads, 1 CTA / SM, persistent over tiles and over the layers of a chain):
+//   warp  4    one lane issues the MMAs (B: 9 resident 128B-swizzled 64x64 weight tiles) and commits to mbarriers;
+//              in tensor-load layers it also issues the halo tiles' 4-D tensor loads (6-stage ring: it re-requests a
+//              stage when the MMAs that read it have completed)
+//   warps 5-12 epilogue team 0, two groups of four: group g drains output channels 32g .. 32g+31:
+//              tcgen05.ld x3 -> shifted sum -> +bias -> activation -> bf16 NHWC store (32-byte st.global.v8), channel
+//              sums kept in registers across the CTA's tiles and flushed with one atomicAdd per channel
+//   warps 0-3, 13-16
+//              plain tensor-load layers: epilogue team 1 (the teams alternate tiles; a tile's epilogue is ~450
+//              dependent instructions per warp and paced the pipeline, profiles/r2_conv3x3_tc_ncu.txt);
+//              fused-input layers (channel attention y = res * scale + skip of the previous block folded in): the
+//              eight warps transform the TMA-staged skip / res tiles in shared memory and write y out once;
+//              without tensor maps (fallback): cp.async producers, one stage per warp, register-path transform.
+// Two TMEM accumulators (2 x 192 columns) decouple the epilogues from the next tile's MMAs.
 #include <cstdlib>
 
 #include <cuda.h>

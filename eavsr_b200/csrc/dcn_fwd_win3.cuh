@@ -9,21 +9,26 @@
 //     32 columns; the ring is NSA = 12 taps deep next to the two 64-column accumulators (512 columns in all).  A
 //     producer thread owns ONE pixel (TMEM lane = tile pixel = its lane in the warp's lane quadrant) and, for a tap,
 //     all 8 deformable groups of it, and writes the pixel's 64 channels with a single tcgen05.st.32x32b.x32.  No
-//     swizzled st.shared, no fence.proxy.async, 32 KB of shared memory back (spent on a deeper offsets ring).
+//     swizzled st.shared, no fence.proxy.async, 32 KB of shared memory back.
 //   * a tap is produced by FOUR warps (one per lane quadrant), not sixteen: the four warp sets work on four
 //     consecutive taps of the CTA's (tile, tap) stream at once and may drift up to NSA taps apart, so a set that hits
-//     far samples or a late offsets stage no longer stalls the other twelve warps.  The MMA thread consumes the ring in
-//     stream order.
+//     far samples no longer stalls the other twelve warps.  The MMA thread consumes the ring in stream order.
 //   * bank-conflict-free gathers need the 8 lanes of a quarter warp to read 8 different 16-byte chunks, while
 //     tcgen05.st wants every lane to present the same columns.  Lane l therefore samples group l ^ u at step u
-//     (u = 0..7, a Latin square) and un-permutes its 8 results in registers with a 3-stage XOR butterfly of selects
-//     (12 SEL per sample) -- cheaper than the swizzled store + proxy fence it replaces.
-//   * the feature window comes in ONE 4-D tensor load per tile with out-of-image cells zero-filled by the TMA unit
-//     (no border pass, no producer-wide barrier); offsets / masks as in the fourth generation (three 5-D tensor
-//     loads per tap), ring of NOS = 6 taps.
+//     (u = 0..7, a Latin square).  Bit 0 of that permutation is undone in registers (one stage of an XOR butterfly of
+//     selects); bits 1-2 move whole 16-channel K blocks and are undone by the MMA issuer: rows are in four classes
+//     c = (pixel >> 1) & 3, a class-c row keeps group pair j at column block j ^ c, and there is one MMA per (j, c)
+//     with the other classes' accumulator rows switched off by the disable-output-lane mask of tcgen05.mma.
+//   * the feature window (6-pixel apron) comes in ONE 4-D tensor load per tile with out-of-image cells zero-filled by
+//     the TMA unit (no border pass, no producer-wide barrier); offsets / masks as in the fourth generation (three 5-D
+//     tensor loads per tap, ring of NOS = 5 taps) by a loader warp that waits for nothing but its own ring, and a
+//     producer reads a tap's 24 values into registers first and hands the stage straight back (pure prefetch ring).
+//     The weight tiles (ring of 2) and the windows come from a second loader warp that follows the MMAs.
+//   * mbarrier waits park in hardware (try_wait with a suspend-time hint); tile coordinates without integer division.
 //
 // Arithmetic (bilinear weights, bf16x2 or fp32 blend, accumulation order over taps and channels) is the fourth
-// generation's, so the two kernels agree bit for bit (tests/test_gpu_ops.py asserts it).
+// generation's, so the two kernels agree bit for bit (tests/test_gpu_ops.py asserts it).  DESIGN.md 3.1c has the
+// step-by-step timings (68.1 -> 46.9 us) and the ablations.
 #pragma once
 #include <cuda.h>
 
